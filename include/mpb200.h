@@ -1,0 +1,145 @@
+/*
+ * mpb200.h -- C ABI of libmpb200.so, the B200 (sm_100a) back-end for the
+ * data-parallel hot path of schmrlng/MotionPlanning.jl.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.
+ * A Julia maintainer binds these with `ccall((:sym, "libmpb200"), Cint, ...)`
+ * (see INTEGRATION.md and julia/MotionPlanningB200.jl); the Python host mirror
+ * in motionplanning.jl_b200/ binds them with ctypes.
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative MPB200_E* code otherwise;
+ *    mpb200_last_error() returns the thread-local message.  No CPU fallback:
+ *    without a usable sm_100 GPU every compute entry point fails.
+ *  - host buffers are caller-owned (Julia GC / numpy); the library copies inputs
+ *    at *_create and writes outputs only between call and return.
+ *  - samples cross as the reference stores them: Vector{SVector{d,Float64}} ==
+ *    column-major d x N Float64 (primitivetypes.jl:21-23, statevec2mat).
+ *  - neighbour tables cross as Julia SparseMatrixCSC{Float64,Int64} fields:
+ *    colptr (ncols+1), rowval (nnz, ascending within a column), nzval (nnz),
+ *    all indices 1-based Int64 (nearneighbors.jl:23-28, ImmutableNNC.D).
+ *  - validity tables cross in Julia BitVector chunk layout: element k (0-based)
+ *    is bit (k & 63) of UInt64 word (k >> 6); unused high bits are zero.
+ *  - one process drives one GPU (mpb200_init(device)); multi-GPU sharding is by
+ *    query (column) range, see mpb200_samples_set_query_range.
+ */
+#ifndef MPB200_H
+#define MPB200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPB200_OK 0
+#define MPB200_EARG (-1)    /* bad argument */
+#define MPB200_ECUDA (-2)   /* CUDA runtime error / no usable GPU */
+#define MPB200_ESTATE (-3)  /* call out of order (e.g. fetch before build) */
+#define MPB200_ENOMEM (-4)
+
+typedef struct mpb200_samples mpb200_samples;     /* device copy of a sample set        */
+typedef struct mpb200_table mpb200_table;         /* device-resident CSC neighbour table */
+typedef struct mpb200_obstacles mpb200_obstacles; /* device copy of an obstacle set      */
+typedef struct mpb200_lq mpb200_lq;               /* linear-quadratic 2BVP               */
+
+/* ---- runtime ----------------------------------------------------------- */
+/* Select the CUDA device for this process and create the library stream.
+ * Fails (MPB200_ECUDA) when there is no GPU or it is not compute capability 10.x. */
+int mpb200_init(int device);
+void mpb200_shutdown(void);
+const char *mpb200_last_error(void);
+int mpb200_version(void);
+/* Launch on a caller-owned cudaStream_t (e.g. torch's current stream) instead of the
+ * library's own; pass NULL to return to the library stream. */
+int mpb200_set_stream(void *cuda_stream);
+int mpb200_synchronize(void);
+/* Pinned host memory for result buffers (fast D2H); plain malloc'ed buffers work too. */
+int mpb200_host_alloc(uint64_t bytes, void **out);
+int mpb200_host_free(void *p);
+/* Number of kernels this library has launched since mpb200_init (bench "gpu_launches"). */
+int64_t mpb200_launch_count(void);
+/* Device time of the last entry point, milliseconds, measured with CUDA events on the
+ * launching stream; phase 0 = whole call, 1.. = entry-point specific. */
+double mpb200_last_ms(int phase);
+
+/* ---- sample sets: replaces MetricNN/QuasiMetricNN.V (nearneighbors.jl:62-92) ---- */
+int mpb200_samples_create(const double *V_aos, int64_t N, int d, mpb200_samples **out);
+int mpb200_samples_destroy(mpb200_samples *s);
+/* Restrict this process to query columns [q0, q1) (0-based, half-open) of the table:
+ * the multi-GPU shard.  Default is [0, N). */
+int mpb200_samples_set_query_range(mpb200_samples *s, int64_t q0, int64_t q1);
+
+/* ---- Euclidean r-ball table --------------------------------------------------
+ * Replaces helper_data_structures(V, ::Euclidean) (geometric.jl:14-15: KDTree build)
+ * plus inball(V, dist, ::TreeDistanceDS, v, r) for every v in the query range
+ * (nearneighbors.jl:179-183), i.e. it produces the ImmutableNNC.D matrix that
+ * inball!(NN{..,ImmutableNNC}, v, r) = viewcol(D, v) serves (nearneighbors.jl:128).
+ * Member iff j != v and sum_i (V[v]_i - V[j]_i)^2 <= r*r (index order, no FMA);
+ * stored value sqrt of the same sum; rows ascending.
+ * If *table is non-NULL on entry its device buffers are reused. */
+int mpb200_inball_build(mpb200_samples *s, double r, mpb200_table **table, int64_t *nnz);
+/* Copy a table to caller buffers; any pointer may be NULL to skip that array.
+ * colptr has (q1-q0)+1 entries, relative to the shard (colptr[0] == 1). */
+int mpb200_table_fetch(const mpb200_table *t, int64_t *colptr, int64_t *rowval, double *nzval);
+int mpb200_table_nnz(const mpb200_table *t, int64_t *nnz, int64_t *ncols);
+int mpb200_table_destroy(mpb200_table *t);
+
+/* ---- obstacle sets ------------------------------------------------------------ */
+/* 2-D compound of circles and convex polygons, PRECOMPUTED on the host exactly as the
+ * reference constructors do (SAT2D.jl:12-98): the device never re-derives normals.
+ * shape_kind 0 = Circle  (data: cx cy r xlo xhi ylo yhi)
+ *            1 = Polygon (data: xlo xhi ylo yhi, K points, K unit normals, K nextrema)
+ * gates are the AABBs of enclosing Compound2D nodes (parent index or -1).
+ * flags bit0: use the intended point-in-polygon test instead of the reference's
+ * inverted one (SAT2D.jl:124-127). */
+typedef struct {
+    int32_t n_gates;
+    const int32_t *gate_parent;
+    const double *gate_aabb;
+    int32_t n_shapes;
+    const int32_t *shape_kind;
+    const int32_t *shape_gate;
+    const int32_t *shape_off;
+    const double *data;
+    int32_t flags;
+} mpb200_obstacles2d_desc;
+/* replaces PointRobot2D(obstacles) (robots2D.jl:5-10) */
+int mpb200_obstacles2d_create(const mpb200_obstacles2d_desc *desc, mpb200_obstacles **out);
+/* replaces PointRobotNDBoxes(boxes) (boxesND.jl:15-21); lo/hi box-major M x d */
+int mpb200_boxes_create(const double *lo, const double *hi, int M, int d, mpb200_obstacles **out);
+int mpb200_obstacles_destroy(mpb200_obstacles *o);
+
+/* BoundedStateSpace bounds + State2Workspace (statespaces.jl:29-34,45-60) */
+typedef struct {
+    int32_t n;           /* state dimension */
+    const double *lo;    /* n */
+    const double *hi;    /* n */
+    int32_t s2w_kind;    /* 0 Identity, 1 VectorView(inds), 2 OutputMatrix(C) */
+    int32_t dw;          /* workspace dimension */
+    const int32_t *inds; /* dw, 0-based (kind 1) */
+    const double *C;     /* dw x n column-major (kind 2) */
+} mpb200_space_desc;
+
+/* ---- batched validity ---------------------------------------------------------- */
+/* F[i] = is_free_state(V[i], CC, SS) for all N samples (fmt.jl:31-36, sampling.jl:25;
+ * statespaces.jl:151-152; robots2D.jl:12; boxesND.jl:42-43).  bits: ceil(N/64) words. */
+int mpb200_points_free(const mpb200_samples *s, const mpb200_obstacles *o, const mpb200_space_desc *ss,
+                       uint64_t *bitchunks);
+/* For every stored entry (row y, column x) of a table, in storage order:
+ * is_free_motion(V[y], V[x], CC, SS) with straight-line waypoints (fmt.jl:75;
+ * statespaces.jl:153-158; geometric.jl:20; robots2D.jl:13-14; boxesND.jl:52-56).
+ * bits: ceil(nnz/64) words.  *checks receives the number of segment checks that
+ * CC.count would have been incremented by. */
+int mpb200_edges_free(const mpb200_samples *s, const mpb200_table *t, const mpb200_obstacles *o,
+                      const mpb200_space_desc *ss, uint64_t *bitchunks, int64_t *checks);
+/* State-level batches for callers that hold states, not indices (sampling.jl:25,
+ * postprocessors.jl:11,21): n states / n straight segments, AoS d x n; out: 1 byte each. */
+int mpb200_states_free(const double *v_aos, int64_t n, int d, const mpb200_obstacles *o,
+                       const mpb200_space_desc *ss, uint8_t *out);
+int mpb200_segments_free(const double *v_aos, const double *w_aos, int64_t n, int d, const mpb200_obstacles *o,
+                         const mpb200_space_desc *ss, uint8_t *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,146 @@
+"""ctypes binding of libmpb200.so (include/mpb200.h).
+
+There is deliberately no fallback: if the CUDA library is missing or no B200 is present the
+first compute call raises.  The oracle under /oracle is test infrastructure and is never
+imported from here.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libmpb200.so")
+
+c_i64 = ctypes.c_int64
+c_i32 = ctypes.c_int32
+c_dbl = ctypes.c_double
+c_vp = ctypes.c_void_p
+P = ctypes.POINTER
+
+
+class MPB200Error(RuntimeError):
+    """Raised for any non-zero return of the C ABI (mirrors the reference's `error(...)`)."""
+
+
+class ObstaclesDesc(ctypes.Structure):
+    _fields_ = [
+        ("n_gates", c_i32), ("gate_parent", c_vp), ("gate_aabb", c_vp),
+        ("n_shapes", c_i32), ("shape_kind", c_vp), ("shape_gate", c_vp), ("shape_off", c_vp),
+        ("data", c_vp), ("flags", c_i32),
+    ]
+
+
+class SpaceDesc(ctypes.Structure):
+    _fields_ = [
+        ("n", c_i32), ("lo", c_vp), ("hi", c_vp), ("s2w_kind", c_i32), ("dw", c_i32),
+        ("inds", c_vp), ("C", c_vp),
+    ]
+
+
+# every symbol include/mpb200.h declares: name -> (restype, argtypes)
+SIGNATURES = {
+    "mpb200_init": (ctypes.c_int, [ctypes.c_int]),
+    "mpb200_shutdown": (None, []),
+    "mpb200_last_error": (ctypes.c_char_p, []),
+    "mpb200_version": (ctypes.c_int, []),
+    "mpb200_set_stream": (ctypes.c_int, [c_vp]),
+    "mpb200_synchronize": (ctypes.c_int, []),
+    "mpb200_host_alloc": (ctypes.c_int, [ctypes.c_uint64, P(c_vp)]),
+    "mpb200_host_free": (ctypes.c_int, [c_vp]),
+    "mpb200_launch_count": (c_i64, []),
+    "mpb200_last_ms": (c_dbl, [ctypes.c_int]),
+    "mpb200_samples_create": (ctypes.c_int, [c_vp, c_i64, ctypes.c_int, P(c_vp)]),
+    "mpb200_samples_destroy": (ctypes.c_int, [c_vp]),
+    "mpb200_samples_set_query_range": (ctypes.c_int, [c_vp, c_i64, c_i64]),
+    "mpb200_inball_build": (ctypes.c_int, [c_vp, c_dbl, P(c_vp), P(c_i64)]),
+    "mpb200_table_fetch": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp]),
+    "mpb200_table_nnz": (ctypes.c_int, [c_vp, P(c_i64), P(c_i64)]),
+    "mpb200_table_destroy": (ctypes.c_int, [c_vp]),
+    "mpb200_obstacles2d_create": (ctypes.c_int, [P(ObstaclesDesc), P(c_vp)]),
+    "mpb200_boxes_create": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, ctypes.c_int, P(c_vp)]),
+    "mpb200_obstacles_destroy": (ctypes.c_int, [c_vp]),
+    "mpb200_points_free": (ctypes.c_int, [c_vp, c_vp, P(SpaceDesc), c_vp]),
+    "mpb200_edges_free": (ctypes.c_int, [c_vp, c_vp, c_vp, P(SpaceDesc), c_vp, P(c_i64)]),
+    "mpb200_states_free": (ctypes.c_int, [c_vp, c_i64, ctypes.c_int, c_vp, P(SpaceDesc), c_vp]),
+    "mpb200_segments_free": (ctypes.c_int, [c_vp, c_vp, c_i64, ctypes.c_int, c_vp, P(SpaceDesc), c_vp]),
+}
+
+_lib = None
+_initialised = False
+
+
+def load():
+    """dlopen the library and declare every signature (no GPU needed for this)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise MPB200Error(
+                "libmpb200.so is not built (%s). Run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "or `python motionplanning.jl_b200/build.py`. There is no CPU fallback." % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = load().mpb200_last_error()
+        raise MPB200Error("libmpb200 error %d: %s" % (rc, msg.decode() if msg else "?"))
+
+
+def init(device=None):
+    """Bind this process to one GPU (LOCAL_RANK by default) -- one process per GPU."""
+    global _initialised
+    lib = load()
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+    check(lib.mpb200_init(int(device)))
+    _initialised = True
+    return lib
+
+
+def lib():
+    """The initialised library; raises if there is no usable B200."""
+    if not _initialised:
+        return init()
+    return _lib
+
+
+def ptr(a):
+    """void* of a C-contiguous numpy array (or None)."""
+    if a is None:
+        return None
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(c_vp)
+
+
+class PinnedPool:
+    """Reusable pinned host buffers for result arrays (D2H at PCIe speed)."""
+
+    def __init__(self):
+        self._bufs = {}
+
+    def array(self, key, n, dtype):
+        dtype = np.dtype(dtype)
+        nbytes = max(int(n) * dtype.itemsize, 8)
+        ent = self._bufs.get(key)
+        if ent is None or ent[1] < nbytes:
+            if ent is not None:
+                check(lib().mpb200_host_free(ent[0]))
+            cap = nbytes + nbytes // 8
+            p = c_vp()
+            check(lib().mpb200_host_alloc(cap, ctypes.byref(p)))
+            ent = (p, cap)
+            self._bufs[key] = ent
+        buf = (ctypes.c_char * ent[1]).from_address(ent[0].value)
+        return np.frombuffer(buf, dtype=dtype, count=int(n))
+
+    def release(self):
+        for p, _ in self._bufs.values():
+            load().mpb200_host_free(p)
+        self._bufs.clear()

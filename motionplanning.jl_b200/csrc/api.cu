@@ -1,0 +1,421 @@
+// api.cu -- the extern "C" entry points declared in include/mpb200.h, plus the runtime
+// plumbing (context, error strings, growing device buffers, event timing).
+#include "common.cuh"
+#include "predicates.cuh"
+#include <climits>
+#include <new>
+#include <vector>
+
+namespace mpb {
+
+Context &ctx() {
+    static Context c;
+    return c;
+}
+
+static thread_local char g_err[512] = "";
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int DevBuf::reserve(size_t bytes) {
+    if (bytes <= cap) return 0;
+    // grow geometrically so repeated builds with slightly different sizes settle quickly
+    size_t want = bytes + bytes / 8 + 256;
+    cudaStream_t st = ctx().stream;
+    cudaStreamSynchronize(st);
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+        e = cudaMalloc(&p, bytes);
+        want = bytes;
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        p = nullptr;
+        return fail(MPB200_ENOMEM, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+    }
+    cap = want;
+    return 0;
+}
+void DevBuf::release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+}
+
+int phase_mark(int i) {
+    Context &c = ctx();
+    if (i < 0 || i > kMaxPhases) return 0;
+    cudaEventRecord(c.ev[i], c.stream);
+    return 0;
+}
+int phases_collect(int n) {
+    Context &c = ctx();
+    for (int k = 0; k < kMaxPhases; ++k) c.last_ms[k] = 0;
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, c.ev[0], c.ev[n]) == cudaSuccess) c.last_ms[0] = ms;
+    for (int k = 0; k < n && k + 1 < kMaxPhases; ++k)
+        if (cudaEventElapsedTime(&ms, c.ev[k], c.ev[k + 1]) == cudaSuccess) c.last_ms[k + 1] = ms;
+    cudaGetLastError();
+    return 0;
+}
+
+// implemented in the kernel translation units
+int compute_bbox(mpb200_samples *s);
+int grid_inball_build(mpb200_samples *s, double r, mpb200_table *t);
+int points_free_device(const double *dV, int64_t n, int d, const mpb200_obstacles *o, const mpb200_space_desc *ss,
+                       uint32_t *d_bits32, uint8_t *d_bytes);
+int edges_free_device(const double *dV, int d, const mpb200_table *t, const mpb200_obstacles *o,
+                      const mpb200_space_desc *ss, uint32_t *d_bits32, unsigned long long *d_checks);
+int segments_free_device(const double *dA, const double *dB, int64_t n, int d, const mpb200_obstacles *o,
+                         const mpb200_space_desc *ss, uint8_t *d_out);
+
+}  // namespace mpb
+
+using namespace mpb;
+
+extern "C" {
+
+int mpb200_version(void) { return 100; }
+
+const char *mpb200_last_error(void) { return g_err; }
+
+int mpb200_init(int device) {
+    Context &c = ctx();
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(MPB200_ECUDA, "no CUDA device available (%s); libmpb200 has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= ndev) return fail(MPB200_EARG, "device %d out of range (0..%d)", device, ndev - 1);
+    if (c.ready && c.device == device) return MPB200_OK;
+    if (c.ready) mpb200_shutdown();
+    MPB_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    MPB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(MPB200_ECUDA, "device %d (%s) is compute capability %d.%d; libmpb200 is built for sm_100a only",
+                    device, prop.name, prop.major, prop.minor);
+    c.device = device;
+    c.sm_count = prop.multiProcessorCount;
+    MPB_CUDA(cudaStreamCreateWithFlags(&c.own_stream, cudaStreamNonBlocking));
+    c.stream = c.own_stream;
+    for (int i = 0; i <= kMaxPhases; ++i) MPB_CUDA(cudaEventCreate(&c.ev[i]));
+    MPB_CUDA(cudaMalloc(&c.d_scalar, sizeof(int64_t) * 16));
+    MPB_CUDA(cudaMallocHost(&c.h_scalar, sizeof(int64_t) * 16));
+    c.launches = 0;
+    c.ready = true;
+    return MPB200_OK;
+}
+
+void mpb200_shutdown(void) {
+    Context &c = ctx();
+    if (!c.ready) return;
+    cudaDeviceSynchronize();
+    for (int i = 0; i <= kMaxPhases; ++i)
+        if (c.ev[i]) cudaEventDestroy(c.ev[i]), c.ev[i] = nullptr;
+    if (c.d_scalar) cudaFree(c.d_scalar), c.d_scalar = nullptr;
+    if (c.h_scalar) cudaFreeHost(c.h_scalar), c.h_scalar = nullptr;
+    if (c.own_stream) cudaStreamDestroy(c.own_stream), c.own_stream = nullptr;
+    c.stream = nullptr;
+    c.ready = false;
+}
+
+int mpb200_set_stream(void *cuda_stream) {
+    MPB_REQUIRE_INIT();
+    Context &c = ctx();
+    MPB_CUDA(cudaStreamSynchronize(c.stream));
+    c.stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : c.own_stream;
+    return MPB200_OK;
+}
+int mpb200_synchronize(void) {
+    MPB_REQUIRE_INIT();
+    MPB_CUDA(cudaStreamSynchronize(ctx().stream));
+    return MPB200_OK;
+}
+int mpb200_host_alloc(uint64_t bytes, void **out) {
+    MPB_REQUIRE_INIT();
+    MPB_CHECK_ARG(out != nullptr, "out is NULL");
+    *out = nullptr;
+    MPB_CUDA(cudaMallocHost(out, bytes ? bytes : 1));
+    return MPB200_OK;
+}
+int mpb200_host_free(void *p) {
+    if (p) MPB_CUDA(cudaFreeHost(p));
+    return MPB200_OK;
+}
+int64_t mpb200_launch_count(void) { return ctx().launches; }
+double mpb200_last_ms(int phase) {
+    if (phase < 0 || phase >= kMaxPhases) return 0;
+    return ctx().last_ms[phase];
+}
+
+// ---- samples -----------------------------------------------------------------------
+int mpb200_samples_create(const double *V_aos, int64_t N, int d, mpb200_samples **out) {
+    MPB_REQUIRE_INIT();
+    MPB_CHECK_ARG(out != nullptr, "out is NULL");
+    MPB_CHECK_ARG(N >= 0 && N < INT_MAX, "N out of range");
+    MPB_CHECK_ARG(d >= 1 && d <= kMaxDim, "d out of range (1..16)");
+    MPB_CHECK_ARG(V_aos != nullptr || N == 0, "V is NULL");
+    mpb200_samples *s = new (std::nothrow) mpb200_samples();
+    if (!s) return fail(MPB200_ENOMEM, "out of host memory");
+    s->N = N;
+    s->d = d;
+    s->q0 = 0;
+    s->q1 = N;
+    int rc = s->V.reserve(sizeof(double) * (size_t)(N * d + 1));
+    if (rc) { delete s; return rc; }
+    cudaStream_t st = ctx().stream;
+    if (N > 0) {
+        cudaError_t e = cudaMemcpyAsync(s->V.p, V_aos, sizeof(double) * (size_t)(N * d), cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) { s->V.release(); delete s; return fail(MPB200_ECUDA, "H2D copy failed: %s", cudaGetErrorString(e)); }
+        rc = compute_bbox(s);
+        if (rc) { mpb200_samples_destroy(s); return rc; }
+    }
+    MPB_CUDA(cudaStreamSynchronize(st));
+    *out = s;
+    return MPB200_OK;
+}
+int mpb200_samples_destroy(mpb200_samples *s) {
+    if (!s) return MPB200_OK;
+    if (ctx().ready) cudaStreamSynchronize(ctx().stream);
+    s->V.release(); s->cell_start.release(); s->cell_fill.release(); s->sorted_idx.release();
+    s->sorted_pos.release(); s->minmax.release(); s->scan_tmp.release(); s->point_bits.release();
+    delete s;
+    return MPB200_OK;
+}
+int mpb200_samples_set_query_range(mpb200_samples *s, int64_t q0, int64_t q1) {
+    MPB_CHECK_ARG(s != nullptr, "samples handle is NULL");
+    MPB_CHECK_ARG(0 <= q0 && q0 <= q1 && q1 <= s->N, "query range must satisfy 0 <= q0 <= q1 <= N");
+    s->q0 = q0;
+    s->q1 = q1;
+    return MPB200_OK;
+}
+
+// ---- Euclidean r-ball table -----------------------------------------------------------
+int mpb200_inball_build(mpb200_samples *s, double r, mpb200_table **table, int64_t *nnz) {
+    MPB_REQUIRE_INIT();
+    MPB_CHECK_ARG(s != nullptr && table != nullptr, "NULL handle");
+    MPB_CHECK_ARG(r >= 0 && r == r, "r must be a non-negative number");
+    mpb200_table *t = *table;
+    bool fresh = false;
+    if (!t) {
+        t = new (std::nothrow) mpb200_table();
+        if (!t) return fail(MPB200_ENOMEM, "out of host memory");
+        fresh = true;
+    }
+    int rc;
+    if (s->N == 0) {
+        rc = t->colptr.reserve(sizeof(int64_t));
+        if (!rc) {
+            int64_t one = 1;
+            cudaMemcpy(t->colptr.p, &one, sizeof(one), cudaMemcpyHostToDevice);
+            t->ncols = 0; t->col0 = 0; t->nnz = 0; t->r = r;
+        }
+    } else if (s->d <= 3 && s->d >= 2) {
+        rc = grid_inball_build(s, r, t);
+    } else {
+        rc = fail(MPB200_EARG, "Euclidean r-ball for d = %d is not built in this library version", s->d);
+    }
+    if (rc) {
+        if (fresh) mpb200_table_destroy(t);
+        return rc;
+    }
+    *table = t;
+    if (nnz) *nnz = t->nnz;
+    return MPB200_OK;
+}
+int mpb200_table_nnz(const mpb200_table *t, int64_t *nnz, int64_t *ncols) {
+    MPB_CHECK_ARG(t != nullptr, "table handle is NULL");
+    if (nnz) *nnz = t->nnz;
+    if (ncols) *ncols = t->ncols;
+    return MPB200_OK;
+}
+int mpb200_table_fetch(const mpb200_table *t, int64_t *colptr, int64_t *rowval, double *nzval) {
+    MPB_REQUIRE_INIT();
+    MPB_CHECK_ARG(t != nullptr, "table handle is NULL");
+    cudaStream_t st = ctx().stream;
+    if (colptr)
+        MPB_CUDA(cudaMemcpyAsync(colptr, t->colptr.p, sizeof(int64_t) * (size_t)(t->ncols + 1), cudaMemcpyDeviceToHost, st));
+    if (rowval && t->nnz)
+        MPB_CUDA(cudaMemcpyAsync(rowval, t->rowval.p, sizeof(int64_t) * (size_t)t->nnz, cudaMemcpyDeviceToHost, st));
+    if (nzval && t->nnz)
+        MPB_CUDA(cudaMemcpyAsync(nzval, t->nzval.p, sizeof(double) * (size_t)t->nnz, cudaMemcpyDeviceToHost, st));
+    MPB_CUDA(cudaStreamSynchronize(st));
+    return MPB200_OK;
+}
+int mpb200_table_destroy(mpb200_table *t) {
+    if (!t) return MPB200_OK;
+    if (ctx().ready) cudaStreamSynchronize(ctx().stream);
+    t->colptr.release(); t->rowval.release(); t->nzval.release(); t->counts.release();
+    t->edge_bits.release(); t->scratch.release();
+    delete t;
+    return MPB200_OK;
+}
+
+// ---- obstacles ----------------------------------------------------------------------------
+int mpb200_obstacles2d_create(const mpb200_obstacles2d_desc *d, mpb200_obstacles **out) {
+    MPB_REQUIRE_INIT();
+    MPB_CHECK_ARG(d != nullptr && out != nullptr, "NULL argument");
+    MPB_CHECK_ARG(d->n_gates >= 0 && d->n_gates <= kMaxGates, "too many compound gates (max 32)");
+    MPB_CHECK_ARG(d->n_shapes >= 0, "negative shape count");
+    MPB_CHECK_ARG(d->n_shapes == 0 || (d->shape_kind && d->shape_gate && d->shape_off && d->data), "NULL shape arrays");
+    MPB_CHECK_ARG(d->n_gates == 0 || (d->gate_parent && d->gate_aabb), "NULL gate arrays");
+    const int G = d->n_gates, S = d->n_shapes;
+    const int data_words = S ? d->shape_off[S] : 0;
+    const int base = 4 + 5 * G + 4 * S;
+    std::vector<double> T((size_t)(base + data_words + 1), 0.0);
+    T[0] = G; T[1] = S; T[2] = d->flags; T[3] = 0;
+    for (int g = 0; g < G; ++g) {
+        MPB_CHECK_ARG(d->gate_parent[g] < g, "gate parents must precede their children");
+        T[4 + 5 * g] = d->gate_parent[g];
+        for (int k = 0; k < 4; ++k) T[4 + 5 * g + 1 + k] = d->gate_aabb[4 * g + k];
+    }
+    for (int s = 0; s < S; ++s) {
+        int len = d->shape_off[s + 1] - d->shape_off[s];
+        int kind = d->shape_kind[s];
+        MPB_CHECK_ARG(kind == 0 || kind == 1, "shape_kind must be 0 (Circle) or 1 (Polygon)");
+        MPB_CHECK_ARG(d->shape_gate[s] >= -1 && d->shape_gate[s] < G, "shape_gate out of range");
+        int K = 0;
+        if (kind == 0) {
+            MPB_CHECK_ARG(len == 7, "Circle record must have 7 doubles");
+            MPB_CHECK_ARG(d->data[d->shape_off[s] + 2] > 0, "Radius must be positive");  // SAT2D.jl:19
+        } else {
+            MPB_CHECK_ARG(len >= 4 + 18 && (len - 4) % 6 == 0, "Polygon record must have 4+6K doubles, K >= 3");  // SAT2D.jl:39
+            K = (len - 4) / 6;
+        }
+        double *dir = &T[4 + 5 * G + 4 * s];
+        dir[0] = kind; dir[1] = d->shape_gate[s]; dir[2] = base + d->shape_off[s]; dir[3] = K;
+    }
+    for (int i = 0; i < data_words; ++i) T[base + i] = d->data[i];
+    mpb200_obstacles *o = new (std::nothrow) mpb200_obstacles();
+    if (!o) return fail(MPB200_ENOMEM, "out of host memory");
+    o->kind = 0; o->n_gates = G; o->n_shapes = S; o->flags = d->flags;
+    o->table_words = base + data_words;
+    o->M = 0; o->d = 2;
+    int rc = o->table.reserve(sizeof(double) * T.size());
+    if (rc) { delete o; return rc; }
+    MPB_CUDA(cudaMemcpy(o->table.p, T.data(), sizeof(double) * T.size(), cudaMemcpyHostToDevice));
+    *out = o;
+    return MPB200_OK;
+}
+int mpb200_boxes_create(const double *lo, const double *hi, int M, int d, mpb200_obstacles **out) {
+    MPB_REQUIRE_INIT();
+    MPB_CHECK_ARG(out != nullptr, "out is NULL");
+    MPB_CHECK_ARG(M >= 0 && d >= 1 && d <= kMaxDim, "bad box count / dimension");
+    MPB_CHECK_ARG(M == 0 || (lo && hi), "NULL box arrays");
+    std::vector<double> T((size_t)(2 * M * d + 1), 0.0);
+    for (int i = 0; i < M * d; ++i) { T[i] = lo[i]; T[(size_t)M * d + i] = hi[i]; }
+    mpb200_obstacles *o = new (std::nothrow) mpb200_obstacles();
+    if (!o) return fail(MPB200_ENOMEM, "out of host memory");
+    o->kind = 1; o->M = M; o->d = d; o->table_words = 2 * M * d;
+    int rc = o->table.reserve(sizeof(double) * T.size());
+    if (rc) { delete o; return rc; }
+    MPB_CUDA(cudaMemcpy(o->table.p, T.data(), sizeof(double) * T.size(), cudaMemcpyHostToDevice));
+    *out = o;
+    return MPB200_OK;
+}
+int mpb200_obstacles_destroy(mpb200_obstacles *o) {
+    if (!o) return MPB200_OK;
+    if (ctx().ready) cudaStreamSynchronize(ctx().stream);
+    o->table.release();
+    delete o;
+    return MPB200_OK;
+}
+
+// ---- batched validity ------------------------------------------------------------------------
+int mpb200_points_free(const mpb200_samples *s_, const mpb200_obstacles *o, const mpb200_space_desc *ss,
+                       uint64_t *bitchunks) {
+    MPB_REQUIRE_INIT();
+    MPB_CHECK_ARG(s_ != nullptr, "samples handle is NULL");
+    mpb200_samples *s = const_cast<mpb200_samples *>(s_);
+    cudaStream_t st = ctx().stream;
+    const size_t words = (size_t)ceil_div(s->N, 64);
+    if (int rc = s->point_bits.reserve(sizeof(uint64_t) * (words + 1))) return rc;
+    phase_mark(0);
+    MPB_CUDA(cudaMemsetAsync(s->point_bits.p, 0, sizeof(uint64_t) * (words + 1), st));
+    if (int rc = points_free_device(s->V.as<double>(), s->N, s->d, o, ss, s->point_bits.as<uint32_t>(), nullptr)) return rc;
+    phase_mark(1);
+    if (bitchunks && words)
+        MPB_CUDA(cudaMemcpyAsync(bitchunks, s->point_bits.p, sizeof(uint64_t) * words, cudaMemcpyDeviceToHost, st));
+    MPB_CUDA(cudaStreamSynchronize(st));
+    phases_collect(1);
+    return MPB200_OK;
+}
+
+int mpb200_edges_free(const mpb200_samples *s, const mpb200_table *t_, const mpb200_obstacles *o,
+                      const mpb200_space_desc *ss, uint64_t *bitchunks, int64_t *checks) {
+    MPB_REQUIRE_INIT();
+    MPB_CHECK_ARG(s != nullptr && t_ != nullptr, "NULL handle");
+    mpb200_table *t = const_cast<mpb200_table *>(t_);
+    Context &c = ctx();
+    cudaStream_t st = c.stream;
+    const size_t words = (size_t)ceil_div(t->nnz, 64);
+    if (int rc = t->edge_bits.reserve(sizeof(uint64_t) * (words + 1))) return rc;
+    phase_mark(0);
+    MPB_CUDA(cudaMemsetAsync(t->edge_bits.p, 0, sizeof(uint64_t) * (words + 1), st));
+    MPB_CUDA(cudaMemsetAsync(c.d_scalar + 4, 0, sizeof(int64_t), st));
+    if (int rc = edges_free_device(s->V.as<double>(), s->d, t, o, ss, t->edge_bits.as<uint32_t>(),
+                                   reinterpret_cast<unsigned long long *>(c.d_scalar + 4)))
+        return rc;
+    phase_mark(1);
+    if (bitchunks && words)
+        MPB_CUDA(cudaMemcpyAsync(bitchunks, t->edge_bits.p, sizeof(uint64_t) * words, cudaMemcpyDeviceToHost, st));
+    MPB_CUDA(cudaMemcpyAsync(c.h_scalar + 4, c.d_scalar + 4, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    MPB_CUDA(cudaStreamSynchronize(st));
+    phases_collect(1);
+    if (checks) *checks = c.h_scalar[4];
+    return MPB200_OK;
+}
+
+static int batch_states(const double *v, const double *w, int64_t n, int d, const mpb200_obstacles *o,
+                        const mpb200_space_desc *ss, uint8_t *out) {
+    MPB_REQUIRE_INIT();
+    MPB_CHECK_ARG(n >= 0 && d >= 1 && d <= kMaxDim, "bad batch size / dimension");
+    MPB_CHECK_ARG(n == 0 || (v && out), "NULL buffers");
+    if (n == 0) return MPB200_OK;
+    cudaStream_t st = ctx().stream;
+    static DevBuf bufA, bufB, bufO;  // reused staging (single caller thread, see DESIGN.md threading)
+    size_t bytes = sizeof(double) * (size_t)(n * d);
+    if (int rc = bufA.reserve(bytes)) return rc;
+    if (int rc = bufO.reserve((size_t)n + 64)) return rc;
+    MPB_CUDA(cudaMemcpyAsync(bufA.p, v, bytes, cudaMemcpyHostToDevice, st));
+    int rc;
+    if (w) {
+        if ((rc = bufB.reserve(bytes))) return rc;
+        MPB_CUDA(cudaMemcpyAsync(bufB.p, w, bytes, cudaMemcpyHostToDevice, st));
+        rc = segments_free_device(bufA.as<double>(), bufB.as<double>(), n, d, o, ss, bufO.as<uint8_t>());
+    } else {
+        rc = points_free_device(bufA.as<double>(), n, d, o, ss, nullptr, bufO.as<uint8_t>());
+    }
+    if (rc) return rc;
+    MPB_CUDA(cudaMemcpyAsync(out, bufO.p, (size_t)n, cudaMemcpyDeviceToHost, st));
+    MPB_CUDA(cudaStreamSynchronize(st));
+    return MPB200_OK;
+}
+int mpb200_states_free(const double *v_aos, int64_t n, int d, const mpb200_obstacles *o, const mpb200_space_desc *ss,
+                       uint8_t *out) {
+    return batch_states(v_aos, nullptr, n, d, o, ss, out);
+}
+int mpb200_segments_free(const double *v_aos, const double *w_aos, int64_t n, int d, const mpb200_obstacles *o,
+                         const mpb200_space_desc *ss, uint8_t *out) {
+    MPB_CHECK_ARG(n == 0 || w_aos != nullptr, "w is NULL");
+    return batch_states(v_aos, w_aos, n, d, o, ss, out);
+}
+
+}  // extern "C"

@@ -1,0 +1,291 @@
+// collide.cu -- K6 (batched point validity), K7 (batched segment vs 2-D compound) and
+// K8 (batched segment vs N-d box list).
+//
+// Replaces the per-call loops of the reference: F[i] = is_free_state(V[i], CC, SS)
+// (fmt.jl:31-36, sampling.jl:25) and the lazy is_free_motion(V[y], V[x], CC, SS) of fmt.jl:75,
+// batched over every stored entry of a neighbour table.  One lane per point / edge, the
+// obstacle table staged once per CTA into shared memory, results packed by warp ballot into
+// Julia BitVector words (bit k&63 of word k>>6 == bit k&31 of 32-bit word k>>5, little endian).
+#include "common.cuh"
+#include "predicates.cuh"
+
+namespace mpb {
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ const double *stage_table(const double *__restrict__ g_table, int words, bool use_smem,
+                                                     double *smem) {
+    if (!use_smem) return g_table;
+    for (int i = threadIdx.x; i < words; i += blockDim.x) smem[i] = g_table[i];
+    __syncthreads();
+    return smem;
+}
+
+// is_free_state(v, CC, SS): statespaces.jl:151-152
+template <int N, int DW, int KIND>
+__device__ __forceinline__ bool state_free(const SpaceDev &S, const double *T, int M, const double *v) {
+    if (!in_state_space<N>(S, v)) return false;
+    double p[DW];
+    state2workspace<N, DW>(S, v, p);
+    if (KIND == 0) return !point_colliding_2d(T, p[0], p[DW > 1 ? 1 : 0]);
+    return box_point_free<DW>(T, M, p);
+}
+// is_free_motion(v, w, CC, SS) with waypoints (v, w): statespaces.jl:153-158, geometric.jl:20.
+// `checked` reports whether the segment test ran (CC.count += 1, robots2D.jl:13 / boxesND.jl:26).
+template <int N, int DW, int KIND>
+__device__ __forceinline__ bool motion_free(const SpaceDev &S, const double *T, int M, const double *v,
+                                            const double *w, bool *checked) {
+    *checked = false;
+    if (!in_state_space<N>(S, v)) return false;  // the last waypoint is never bounds-checked (Q4)
+    double p[DW], q[DW];
+    state2workspace<N, DW>(S, v, p);
+    state2workspace<N, DW>(S, w, q);
+    *checked = true;
+    if (KIND == 0) return !line_colliding_2d(T, p[0], p[DW > 1 ? 1 : 0], q[0], q[DW > 1 ? 1 : 0]);
+    return box_segment_free<DW>(T, M, p, q);
+}
+
+template <int N, int DW, int KIND>
+__global__ void __launch_bounds__(kThreads)
+points_free_kernel(const double *__restrict__ V, int64_t n, SpaceDev S, const double *__restrict__ g_table,
+                   int table_words, int M, bool use_smem, uint32_t *__restrict__ bits32,
+                   uint8_t *__restrict__ bytes) {
+    extern __shared__ double s_table[];
+    const double *T = stage_table(g_table, table_words, use_smem, s_table);
+    const int64_t n_pad = (n + 31) & ~int64_t(31);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += (int64_t)gridDim.x * blockDim.x) {
+        bool ok = false;
+        if (i < n) {
+            double v[N];
+#pragma unroll
+            for (int k = 0; k < N; ++k) v[k] = V[i * N + k];
+            ok = state_free<N, DW, KIND>(S, T, M, v);
+        }
+        unsigned m = __ballot_sync(0xffffffffu, ok);
+        if (bits32 && (threadIdx.x & 31) == 0) bits32[i >> 5] = m;
+        if (bytes && i < n) bytes[i] = ok ? 1 : 0;
+    }
+}
+
+// column (0-based, shard-local) of stored entry e: the w with colptr[w] <= e+1 < colptr[w+1]
+__device__ __forceinline__ int64_t column_of(const int64_t *__restrict__ colptr, int64_t lo, int64_t hi, int64_t e1) {
+    // upper_bound(e1) over colptr[lo..hi] minus one
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (colptr[mid] <= e1) lo = mid + 1; else hi = mid;
+    }
+    return lo - 1;
+}
+
+template <int N, int DW, int KIND>
+__global__ void __launch_bounds__(kThreads)
+edges_free_kernel(const double *__restrict__ V, const int64_t *__restrict__ colptr,
+                  const int64_t *__restrict__ rowval, int64_t ncols, int64_t col0, int64_t nnz, SpaceDev S,
+                  const double *__restrict__ g_table, int table_words, int M, bool use_smem,
+                  uint32_t *__restrict__ bits32, unsigned long long *__restrict__ checks) {
+    extern __shared__ double s_table[];
+    const double *T = stage_table(g_table, table_words, use_smem, s_table);
+    const int lane = threadIdx.x & 31;
+    const int64_t nnz_pad = (nnz + 31) & ~int64_t(31);
+    unsigned long long my_checks = 0;
+    for (int64_t e0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) & ~int64_t(31); e0 < nnz_pad;
+         e0 += (int64_t)gridDim.x * blockDim.x) {
+        // warp-uniform bracket of columns spanned by the 32 edges, then a short per-lane search
+        int64_t e_last = e0 + 31 < nnz ? e0 + 31 : nnz - 1;
+        int64_t c_first = column_of(colptr, 0, ncols + 1, e0 + 1);
+        int64_t c_last = column_of(colptr, c_first, ncols + 1, e_last + 1);
+        const int64_t e = e0 + lane;
+        bool ok = false;
+        if (e < nnz) {
+            int64_t w = column_of(colptr, c_first, c_last + 2, e + 1);
+            const int64_t x = col0 + w;
+            const int64_t y = rowval[e] - 1;
+            double a[N], b[N];
+#pragma unroll
+            for (int k = 0; k < N; ++k) { a[k] = V[y * N + k]; b[k] = V[x * N + k]; }
+            bool checked;
+            ok = motion_free<N, DW, KIND>(S, T, M, a, b, &checked);
+            my_checks += checked ? 1 : 0;
+        }
+        unsigned m = __ballot_sync(0xffffffffu, ok);
+        if (lane == 0) bits32[e0 >> 5] = m;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) my_checks += __shfl_xor_sync(0xffffffffu, my_checks, o);
+    if (lane == 0 && my_checks) atomicAdd(checks, my_checks);
+}
+
+template <int N, int DW, int KIND>
+__global__ void __launch_bounds__(kThreads)
+segments_free_kernel(const double *__restrict__ A, const double *__restrict__ B, int64_t n, SpaceDev S,
+                     const double *__restrict__ g_table, int table_words, int M, bool use_smem,
+                     uint8_t *__restrict__ out) {
+    extern __shared__ double s_table[];
+    const double *T = stage_table(g_table, table_words, use_smem, s_table);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double a[N], b[N];
+#pragma unroll
+        for (int k = 0; k < N; ++k) { a[k] = A[i * N + k]; b[k] = B[i * N + k]; }
+        bool checked;
+        out[i] = motion_free<N, DW, KIND>(S, T, M, a, b, &checked) ? 1 : 0;
+    }
+}
+
+// ---- host dispatch --------------------------------------------------------------------
+constexpr size_t kSmemTableMax = 160 * 1024;
+
+struct LaunchCfg {
+    const double *table;
+    int words, M;
+    bool use_smem;
+    size_t smem;
+    unsigned grid;
+};
+static LaunchCfg make_cfg(const mpb200_obstacles *o, int64_t work) {
+    LaunchCfg L;
+    L.table = o->table.as<double>();
+    L.words = o->table_words;
+    L.M = o->M;
+    size_t bytes = sizeof(double) * (size_t)o->table_words;
+    L.use_smem = bytes <= kSmemTableMax;
+    L.smem = L.use_smem ? bytes : 0;
+    int64_t blocks = ceil_div(work > 0 ? work : 1, kThreads);
+    int64_t cap = (int64_t)ctx().sm_count * 8;  // persistent-style grid: a multiple of the SM count
+    L.grid = (unsigned)(blocks < cap ? blocks : cap);
+    return L;
+}
+template <class K>
+static int prep_kernel(K kernel, size_t smem) {
+    if (smem > 48 * 1024) MPB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    return 0;
+}
+
+int make_space(const mpb200_space_desc *ss, int d_state, SpaceDev *out, int *dw) {
+    MPB_CHECK_ARG(ss != nullptr, "space descriptor is NULL");
+    MPB_CHECK_ARG(ss->n == d_state, "space dimension does not match the sample dimension");
+    MPB_CHECK_ARG(ss->n >= 1 && ss->n <= kMaxDim, "state dimension out of range (1..16)");
+    MPB_CHECK_ARG(ss->lo && ss->hi, "space bounds are NULL");
+    SpaceDev S;
+    memset(&S, 0, sizeof(S));
+    S.n = ss->n;
+    S.s2w_kind = ss->s2w_kind;
+    for (int i = 0; i < ss->n; ++i) { S.lo[i] = ss->lo[i]; S.hi[i] = ss->hi[i]; }
+    if (ss->s2w_kind == 0) {
+        S.dw = ss->n;
+    } else if (ss->s2w_kind == 1) {
+        MPB_CHECK_ARG(ss->inds && ss->dw >= 1 && ss->dw <= kMaxDim, "VectorView needs inds and 1 <= dw <= 16");
+        S.dw = ss->dw;
+        for (int i = 0; i < ss->dw; ++i) {
+            MPB_CHECK_ARG(ss->inds[i] >= 0 && ss->inds[i] < ss->n, "VectorView index out of range");
+            S.inds[i] = ss->inds[i];
+        }
+    } else if (ss->s2w_kind == 2) {
+        MPB_CHECK_ARG(ss->C && ss->dw >= 1 && ss->dw * ss->n <= kMaxDim * 4, "OutputMatrix needs C with dw*n <= 64");
+        S.dw = ss->dw;
+        for (int i = 0; i < ss->dw * ss->n; ++i) S.C[i] = ss->C[i];
+    } else {
+        return fail(MPB200_EARG, "unknown s2w_kind %d", ss->s2w_kind);
+    }
+    *out = S;
+    *dw = S.dw;
+    return 0;
+}
+
+// (N, DW) pairs compiled: Identity spaces N == DW in 2..10, and double-integrator style
+// position views (4,2), (6,3).
+#define MPB_DISPATCH_DIMS(N_, DW_, KIND_, CALL)                                            \
+    do {                                                                                   \
+        bool done__ = false;                                                               \
+        if (KIND_ == 0) {                                                                  \
+            if (DW_ != 2) return fail(MPB200_EARG, "2-D obstacles need a 2-D workspace");  \
+            if (N_ == 2) { CALL(2, 2, 0); done__ = true; }                                 \
+            else if (N_ == 3) { CALL(3, 2, 0); done__ = true; }                            \
+            else if (N_ == 4) { CALL(4, 2, 0); done__ = true; }                            \
+            else if (N_ == 6) { CALL(6, 2, 0); done__ = true; }                            \
+        } else {                                                                           \
+            if (N_ == 2 && DW_ == 2) { CALL(2, 2, 1); done__ = true; }                     \
+            else if (N_ == 3 && DW_ == 3) { CALL(3, 3, 1); done__ = true; }                \
+            else if (N_ == 4 && DW_ == 4) { CALL(4, 4, 1); done__ = true; }                \
+            else if (N_ == 5 && DW_ == 5) { CALL(5, 5, 1); done__ = true; }                \
+            else if (N_ == 6 && DW_ == 6) { CALL(6, 6, 1); done__ = true; }                \
+            else if (N_ == 7 && DW_ == 7) { CALL(7, 7, 1); done__ = true; }                \
+            else if (N_ == 8 && DW_ == 8) { CALL(8, 8, 1); done__ = true; }                \
+            else if (N_ == 9 && DW_ == 9) { CALL(9, 9, 1); done__ = true; }                \
+            else if (N_ == 10 && DW_ == 10) { CALL(10, 10, 1); done__ = true; }            \
+            else if (N_ == 4 && DW_ == 2) { CALL(4, 2, 1); done__ = true; }                \
+            else if (N_ == 6 && DW_ == 3) { CALL(6, 3, 1); done__ = true; }                \
+        }                                                                                  \
+        if (!done__)                                                                       \
+            return fail(MPB200_EARG, "unsupported (state dim %d, workspace dim %d) combination", N_, DW_); \
+    } while (0)
+
+static int check_obstacles(const mpb200_obstacles *o, int dw) {
+    MPB_CHECK_ARG(o != nullptr, "obstacle handle is NULL");
+    if (o->kind == 1 && o->d != dw) return fail(MPB200_EARG, "box dimension %d != workspace dimension %d", o->d, dw);
+    return 0;
+}
+
+int points_free_device(const double *dV, int64_t n, int d, const mpb200_obstacles *o, const mpb200_space_desc *ss,
+                       uint32_t *d_bits32, uint8_t *d_bytes) {
+    SpaceDev S;
+    int dw;
+    if (int rc = make_space(ss, d, &S, &dw)) return rc;
+    if (int rc = check_obstacles(o, dw)) return rc;
+    LaunchCfg L = make_cfg(o, n);
+    cudaStream_t st = ctx().stream;
+#define CALL(N_, DW_, K_)                                                                              \
+    do {                                                                                               \
+        if (int rc = prep_kernel(points_free_kernel<N_, DW_, K_>, L.smem)) return rc;                  \
+        points_free_kernel<N_, DW_, K_><<<L.grid, kThreads, L.smem, st>>>(dV, n, S, L.table, L.words, L.M, \
+                                                                          L.use_smem, d_bits32, d_bytes); \
+    } while (0)
+    MPB_DISPATCH_DIMS(S.n, dw, o->kind, CALL);
+#undef CALL
+    MPB_LAUNCHED();
+    return 0;
+}
+
+int edges_free_device(const double *dV, int d, const mpb200_table *t, const mpb200_obstacles *o,
+                      const mpb200_space_desc *ss, uint32_t *d_bits32, unsigned long long *d_checks) {
+    SpaceDev S;
+    int dw;
+    if (int rc = make_space(ss, d, &S, &dw)) return rc;
+    if (int rc = check_obstacles(o, dw)) return rc;
+    LaunchCfg L = make_cfg(o, t->nnz);
+    cudaStream_t st = ctx().stream;
+    const int64_t *colptr = t->colptr.as<int64_t>();
+    const int64_t *rowval = t->rowval.as<int64_t>();
+#define CALL(N_, DW_, K_)                                                                                  \
+    do {                                                                                                   \
+        if (int rc = prep_kernel(edges_free_kernel<N_, DW_, K_>, L.smem)) return rc;                       \
+        edges_free_kernel<N_, DW_, K_><<<L.grid, kThreads, L.smem, st>>>(dV, colptr, rowval, t->ncols, t->col0, \
+                                                                         t->nnz, S, L.table, L.words, L.M, \
+                                                                         L.use_smem, d_bits32, d_checks);  \
+    } while (0)
+    MPB_DISPATCH_DIMS(S.n, dw, o->kind, CALL);
+#undef CALL
+    MPB_LAUNCHED();
+    return 0;
+}
+
+int segments_free_device(const double *dA, const double *dB, int64_t n, int d, const mpb200_obstacles *o,
+                         const mpb200_space_desc *ss, uint8_t *d_out) {
+    SpaceDev S;
+    int dw;
+    if (int rc = make_space(ss, d, &S, &dw)) return rc;
+    if (int rc = check_obstacles(o, dw)) return rc;
+    LaunchCfg L = make_cfg(o, n);
+    cudaStream_t st = ctx().stream;
+#define CALL(N_, DW_, K_)                                                                               \
+    do {                                                                                                \
+        if (int rc = prep_kernel(segments_free_kernel<N_, DW_, K_>, L.smem)) return rc;                 \
+        segments_free_kernel<N_, DW_, K_><<<L.grid, kThreads, L.smem, st>>>(dA, dB, n, S, L.table, L.words, \
+                                                                            L.M, L.use_smem, d_out);    \
+    } while (0)
+    MPB_DISPATCH_DIMS(S.n, dw, o->kind, CALL);
+#undef CALL
+    MPB_LAUNCHED();
+    return 0;
+}
+
+}  // namespace mpb

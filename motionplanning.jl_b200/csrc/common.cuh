@@ -1,0 +1,117 @@
+// common.cuh -- runtime plumbing shared by every translation unit of libmpb200.so.
+// Error convention, the per-process context (device, stream, timing events), device
+// buffers that grow and are reused, and launch accounting.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdarg>
+#include <cstring>
+#include "../../include/mpb200.h"
+
+namespace mpb {
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+constexpr int kMaxPhases = 8;
+
+struct Context {
+    bool ready = false;
+    int device = -1;
+    int sm_count = kNumSMs;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;  // the launching stream (own or caller's)
+    cudaEvent_t ev[kMaxPhases + 1] = {};
+    double last_ms[kMaxPhases] = {};
+    int64_t launches = 0;
+    int64_t *d_scalar = nullptr;  // small device scratch for scalars read back to the host
+    int64_t *h_scalar = nullptr;  // pinned mirror
+};
+Context &ctx();
+
+void set_error(const char *fmt, ...);
+int fail(int code, const char *fmt, ...);
+
+#define MPB_CUDA(call)                                                                          \
+    do {                                                                                        \
+        cudaError_t e__ = (call);                                                               \
+        if (e__ != cudaSuccess)                                                                 \
+            return mpb::fail(MPB200_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+                             __FILE__, __LINE__);                                               \
+    } while (0)
+
+#define MPB_REQUIRE_INIT()                                                             \
+    do {                                                                               \
+        if (!mpb::ctx().ready)                                                         \
+            return mpb::fail(MPB200_ESTATE, "mpb200_init has not been called (no CPU fallback exists)"); \
+    } while (0)
+
+#define MPB_CHECK_ARG(cond, msg)                         \
+    do {                                                 \
+        if (!(cond)) return mpb::fail(MPB200_EARG, msg); \
+    } while (0)
+
+// count + check a kernel launch
+#define MPB_LAUNCHED()                                                                            \
+    do {                                                                                          \
+        mpb::ctx().launches++;                                                                    \
+        cudaError_t e__ = cudaGetLastError();                                                     \
+        if (e__ != cudaSuccess)                                                                   \
+            return mpb::fail(MPB200_ECUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), \
+                             __FILE__, __LINE__);                                                 \
+    } while (0)
+
+// A device buffer that only grows; reused across calls so the steady state has no cudaMalloc.
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes);
+    void release();
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+// timing phases: phase_begin(0) ... phase_end(0) record events on the launching stream
+int phase_mark(int i);                 // record event i
+int phases_collect(int n_marks);       // after a sync: last_ms[k] = elapsed(ev[k], ev[k+1]), last_ms[0] = total
+
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+}  // namespace mpb
+
+// ---- handle layouts (opaque in the C ABI) ---------------------------------------
+struct mpb200_table {
+    int64_t ncols = 0;     // columns in this shard
+    int64_t col0 = 0;      // first global column (0-based)
+    int64_t nnz = 0;
+    double r = 0;
+    mpb::DevBuf colptr;    // int64 (ncols+1), 1-based, relative to the shard
+    mpb::DevBuf rowval;    // int64 nnz, 1-based global row ids
+    mpb::DevBuf nzval;     // f64 nnz
+    mpb::DevBuf counts;    // int32 ncols (scratch)
+    mpb::DevBuf edge_bits; // uint64 ceil(nnz/64): last mpb200_edges_free result
+    mpb::DevBuf scratch;   // big-column spill etc.
+};
+
+struct mpb200_samples {
+    int64_t N = 0;
+    int d = 0;
+    int64_t q0 = 0, q1 = 0;
+    mpb::DevBuf V;           // f64 d x N column-major (AoS), as the caller gave it
+    // uniform grid (built per radius by mpb200_inball_build)
+    mpb::DevBuf cell_start;  // int32 ncells+1
+    mpb::DevBuf cell_fill;   // int32 ncells (scatter cursors)
+    mpb::DevBuf sorted_idx;  // int32 N   original index of the k-th point in cell order
+    mpb::DevBuf sorted_pos;  // f64 d x N positions in cell order (AoS)
+    mpb::DevBuf minmax;      // f64 2*d bounding box
+    mpb::DevBuf scan_tmp;    // scan block sums
+    mpb::DevBuf point_bits;  // uint64 ceil(N/64): last mpb200_points_free result
+};
+
+struct mpb200_obstacles {
+    int kind = 0;            // 0 = 2-D compound, 1 = N-d boxes
+    // 2-D compound, packed for the device: see predicates.cuh
+    int n_gates = 0, n_shapes = 0, flags = 0;
+    int table_words = 0;     // size of the packed table in doubles
+    mpb::DevBuf table;       // packed f64 table
+    // boxes
+    int M = 0, d = 0;
+};

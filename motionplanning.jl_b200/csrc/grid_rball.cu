@@ -1,0 +1,410 @@
+// grid_rball.cu -- K1 (uniform-grid build) + K2 (r-ball count / fill) for d = 2, 3.
+//
+// Replaces helper_data_structures(V, ::Euclidean) = KDTree build (geometric.jl:14-15) and,
+// for every query column, inball(V, dist, ::TreeDistanceDS, v, r) (nearneighbors.jl:179-183):
+// member iff j != v and s = sum_i (V[v]_i - V[j]_i)^2 <= r*r, evaluated in index order
+// with one rounding per operation (no FMA); stored value sqrt(s); rows ascending.
+//
+// Data layout in HBM: samples stay AoS (d x N column-major, exactly the reference's
+// Vector{SVector{d,Float64}}); the grid adds a cell-ordered AoS copy + the permutation, so a
+// 3-cell x-run of candidates is one contiguous, coalesced span.  One warp per query; three
+// (d=2) or nine (d=3) x-runs per query; hits are compacted with warp ballots into a
+// per-warp shared-memory stage, rank-sorted by sample index there, and written as one
+// contiguous Int64/Float64 burst per column.
+#include "common.cuh"
+#include "scan.cuh"
+
+namespace mpb {
+
+constexpr int kWarpsPerBlock = 8;
+constexpr int kStageCap = 256;  // hits staged per warp; larger columns take the spill path
+
+struct GridDev {
+    double lo[3];
+    double inv_h;
+    int n[3];
+};
+
+template <int D>
+__device__ __forceinline__ void cell_of(const GridDev &g, const double *p, int *c) {
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+        // explicit intrinsics: every kernel must compute the identical cell for a point
+        double q = __dmul_rn(__dsub_rn(p[i], g.lo[i]), g.inv_h);
+        int ci = (int)floor(q);
+        ci = ci < 0 ? 0 : ci;
+        ci = ci >= g.n[i] ? g.n[i] - 1 : ci;
+        c[i] = ci;
+    }
+}
+template <int D>
+__device__ __forceinline__ int cell_linear(const GridDev &g, const int *c) {
+    int l = c[D - 1];
+#pragma unroll
+    for (int i = D - 2; i >= 0; --i) l = l * g.n[i] + c[i];
+    return l;
+}
+
+// ---- bounding box ------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bbox_partial(const double *__restrict__ V, int64_t N, int d,
+                                                    double *__restrict__ part /*grid x 2d*/) {
+    __shared__ double smin[8][16], smax[8][16];
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    for (int i = 0; i < d; ++i) {
+        double mn = inf, mx = -inf;
+        for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < N; j += (int64_t)gridDim.x * blockDim.x) {
+            double x = V[j * d + i];
+            mn = fmin(mn, x);
+            mx = fmax(mx, x);
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        }
+        if ((threadIdx.x & 31) == 0) { smin[threadIdx.x >> 5][i] = mn; smax[threadIdx.x >> 5][i] = mx; }
+    }
+    __syncthreads();
+    if (threadIdx.x < d) {
+        double mn = inf, mx = -inf;
+        for (int w = 0; w < 8; ++w) { mn = fmin(mn, smin[w][threadIdx.x]); mx = fmax(mx, smax[w][threadIdx.x]); }
+        part[(size_t)blockIdx.x * 2 * d + threadIdx.x] = mn;
+        part[(size_t)blockIdx.x * 2 * d + d + threadIdx.x] = mx;
+    }
+}
+__global__ void bbox_final(const double *__restrict__ part, int nb, int d, double *__restrict__ out) {
+    int i = threadIdx.x;
+    if (i >= d) return;
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    double mn = inf, mx = -inf;
+    for (int b = 0; b < nb; ++b) { mn = fmin(mn, part[(size_t)b * 2 * d + i]); mx = fmax(mx, part[(size_t)b * 2 * d + d + i]); }
+    out[i] = mn; out[d + i] = mx;
+}
+
+// ---- K1: grid build ------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(256) cell_histogram(const double *__restrict__ V, int64_t N, GridDev g,
+                                                      int *__restrict__ hist, int *__restrict__ cell_id) {
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= N) return;
+    double p[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) p[i] = V[j * D + i];
+    int c[D];
+    cell_of<D>(g, p, c);
+    int l = cell_linear<D>(g, c);
+    cell_id[j] = l;
+    atomicAdd(&hist[l], 1);
+}
+template <int D>
+__global__ void __launch_bounds__(256) cell_scatter(const double *__restrict__ V, int64_t N,
+                                                    const int *__restrict__ cell_id,
+                                                    const int *__restrict__ cell_start, int *__restrict__ cursor,
+                                                    int *__restrict__ sorted_idx, double *__restrict__ sorted_pos) {
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= N) return;
+    int l = cell_id[j];
+    int pos = cell_start[l] + atomicAdd(&cursor[l], 1);
+    sorted_idx[pos] = (int)j;
+#pragma unroll
+    for (int i = 0; i < D; ++i) sorted_pos[(size_t)pos * D + i] = V[j * D + i];
+}
+
+// ---- K2: r-ball ------------------------------------------------------------------------
+// squared distance in the reference's order: s = (a1-b1)^2; s = s + (a_i-b_i)^2 ...
+template <int D>
+__device__ __forceinline__ double sqdist(const double *a, const double *b) {
+    double t = __dsub_rn(a[0], b[0]);
+    double s = __dmul_rn(t, t);
+#pragma unroll
+    for (int i = 1; i < D; ++i) {
+        t = __dsub_rn(a[i], b[i]);
+        s = __dadd_rn(s, __dmul_rn(t, t));
+    }
+    return s;
+}
+
+// Enumerate the candidate span [beg, end) of x-run `run` (0 .. 3^(D-1)-1) around cell c.
+template <int D>
+__device__ __forceinline__ bool run_span(const GridDev &g, const int *c, int run, const int *__restrict__ cell_start,
+                                         int *beg, int *end) {
+    int cc[D];
+    cc[0] = 0;
+    int rr = run;
+#pragma unroll
+    for (int i = 1; i < D; ++i) {
+        int dlt = rr % 3 - 1;
+        rr /= 3;
+        cc[i] = c[i] + dlt;
+        if (cc[i] < 0 || cc[i] >= g.n[i]) return false;
+    }
+    int x0 = c[0] > 0 ? c[0] - 1 : 0;
+    int x1 = c[0] + 1 < g.n[0] ? c[0] + 1 : g.n[0] - 1;
+    cc[0] = x0;
+    int l0 = cell_linear<D>(g, cc);
+    *beg = cell_start[l0];
+    *end = cell_start[l0 + (x1 - x0) + 1];
+    return true;
+}
+
+template <int D>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+rball_count(const double *__restrict__ V, int64_t q0, int64_t nq, GridDev g, double r2,
+            const int *__restrict__ cell_start, const int *__restrict__ sorted_idx,
+            const double *__restrict__ sorted_pos, int *__restrict__ counts, int *__restrict__ big_list,
+            unsigned long long *__restrict__ n_big) {
+    constexpr int kRuns = (D == 2) ? 3 : 9;
+    const int lane = threadIdx.x & 31;
+    const int64_t w = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (w >= nq) return;
+    const int64_t v = q0 + w;
+    double p[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) p[i] = V[v * D + i];
+    int c[D];
+    cell_of<D>(g, p, c);
+    int cnt = 0;
+#pragma unroll
+    for (int run = 0; run < kRuns; ++run) {
+        int beg, end;
+        if (!run_span<D>(g, c, run, cell_start, &beg, &end)) continue;
+        for (int k = beg + lane; k < end; k += 32) {
+            double b[D];
+#pragma unroll
+            for (int i = 0; i < D; ++i) b[i] = sorted_pos[(size_t)k * D + i];
+            int idx = sorted_idx[k];
+            double s = sqdist<D>(p, b);
+            cnt += (idx != (int)v && s <= r2) ? 1 : 0;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) {
+        counts[w] = cnt;
+        if (cnt > kStageCap) {
+            unsigned long long slot = atomicAdd(n_big, 1ULL);
+            big_list[slot] = (int)w;
+        }
+    }
+}
+
+template <int D>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+rball_fill(const double *__restrict__ V, int64_t q0, int64_t nq, GridDev g, double r2,
+           const int *__restrict__ cell_start, const int *__restrict__ sorted_idx,
+           const double *__restrict__ sorted_pos, const int64_t *__restrict__ colptr,
+           int64_t *__restrict__ rowval, double *__restrict__ nzval,
+           int64_t *__restrict__ spill_row, double *__restrict__ spill_val) {
+    constexpr int kRuns = (D == 2) ? 3 : 9;
+    __shared__ int s_idx[kWarpsPerBlock][kStageCap];
+    __shared__ double s_sq[kWarpsPerBlock][kStageCap];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t w = (int64_t)blockIdx.x * kWarpsPerBlock + wid;
+    if (w >= nq) return;
+    const int64_t v = q0 + w;
+    const int64_t base = colptr[w] - 1;
+    const int k_total = (int)(colptr[w + 1] - colptr[w]);
+    if (k_total == 0) return;
+    const bool big = k_total > kStageCap;  // warp-uniform
+    double p[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) p[i] = V[v * D + i];
+    int c[D];
+    cell_of<D>(g, p, c);
+    int n_hit = 0;
+#pragma unroll
+    for (int run = 0; run < kRuns; ++run) {
+        int beg, end;
+        if (!run_span<D>(g, c, run, cell_start, &beg, &end)) continue;
+        for (int k0 = beg; k0 < end; k0 += 32) {
+            int k = k0 + lane;
+            bool hit = false;
+            int idx = 0;
+            double s = 0;
+            if (k < end) {
+                double b[D];
+#pragma unroll
+                for (int i = 0; i < D; ++i) b[i] = sorted_pos[(size_t)k * D + i];
+                idx = sorted_idx[k];
+                s = sqdist<D>(p, b);
+                hit = (idx != (int)v) && (s <= r2);
+            }
+            unsigned m = __ballot_sync(0xffffffffu, hit);
+            int off = n_hit + __popc(m & ((1u << lane) - 1u));
+            if (hit) {
+                if (!big) {
+                    s_idx[wid][off] = idx;
+                    s_sq[wid][off] = s;
+                } else {  // spill path: unsorted, sorted later by sort_big_columns
+                    spill_row[base + off] = (int64_t)idx + 1;
+                    spill_val[base + off] = sqrt(s);
+                }
+            }
+            n_hit += __popc(m);
+        }
+    }
+    if (big) return;
+    __syncwarp();
+    // rank sort by sample index (indices are distinct), then one contiguous burst per column
+    for (int e = lane; e < n_hit; e += 32) {
+        int mine = s_idx[wid][e];
+        int rank = 0;
+        for (int j = 0; j < n_hit; ++j) rank += (s_idx[wid][j] < mine) ? 1 : 0;
+        rowval[base + rank] = (int64_t)mine + 1;
+        nzval[base + rank] = sqrt(s_sq[wid][e]);
+    }
+}
+
+// spill path: one block per over-sized column; rank sort from the unsorted spill copy
+__global__ void __launch_bounds__(256)
+sort_big_columns(const int *__restrict__ big_list, const int64_t *__restrict__ colptr,
+                 const int64_t *__restrict__ spill_row, const double *__restrict__ spill_val,
+                 int64_t *__restrict__ rowval, double *__restrict__ nzval) {
+    __shared__ int64_t tile[256];
+    const int w = big_list[blockIdx.x];
+    const int64_t base = colptr[w] - 1;
+    const int k = (int)(colptr[w + 1] - colptr[w]);
+    for (int e0 = 0; e0 < k; e0 += 256) {
+        int e = e0 + threadIdx.x;
+        int64_t mine = (e < k) ? spill_row[base + e] : 0;
+        int rank = 0;
+        for (int t0 = 0; t0 < k; t0 += 256) {
+            __syncthreads();
+            if (t0 + (int)threadIdx.x < k) tile[threadIdx.x] = spill_row[base + t0 + threadIdx.x];
+            __syncthreads();
+            int lim = min(256, k - t0);
+            for (int j = 0; j < lim; ++j) rank += (tile[j] < mine) ? 1 : 0;
+        }
+        if (e < k) {
+            rowval[base + rank] = mine;
+            nzval[base + rank] = spill_val[base + e];
+        }
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------
+template <int D>
+static int build_table(mpb200_samples *s, double r, mpb200_table *t) {
+    Context &c = ctx();
+    cudaStream_t st = c.stream;
+    const int64_t N = s->N, nq = s->q1 - s->q0;
+    const double *V = s->V.as<double>();
+
+    // bounding box -> grid geometry (host reads 2*D doubles: one tiny sync per build)
+    double bb[6];
+    MPB_CUDA(cudaMemcpyAsync(bb, s->minmax.as<double>(), sizeof(double) * 2 * D, cudaMemcpyDeviceToHost, st));
+    MPB_CUDA(cudaStreamSynchronize(st));
+    GridDev g;
+    const int max_per_dim = (D == 2) ? 4096 : 256;
+    double ext_max = 0;
+    for (int i = 0; i < D; ++i) ext_max = fmax(ext_max, bb[D + i] - bb[i]);
+    // cell edge >= r(1+1e-6): two points within r are always in adjacent cells, rounding included
+    double h = r * (1.0 + 1e-6);
+    if (!(h > ext_max / max_per_dim)) h = ext_max / max_per_dim;
+    if (!(h > 0)) h = 1.0;
+    int64_t ncells = 1;
+    for (int i = 0; i < D; ++i) {
+        g.lo[i] = bb[i];
+        double cnt = floor((bb[D + i] - bb[i]) / h) + 1.0;
+        if (cnt > max_per_dim + 1) cnt = max_per_dim + 1;
+        g.n[i] = (int)cnt;
+        ncells *= g.n[i];
+    }
+    for (int i = D; i < 3; ++i) { g.lo[i] = 0; g.n[i] = 1; }
+    g.inv_h = 1.0 / h;
+
+    if (int rc = s->cell_start.reserve(sizeof(int) * (size_t)(ncells + 1))) return rc;
+    if (int rc = s->cell_fill.reserve(sizeof(int) * (size_t)(ncells + 1))) return rc;
+    if (int rc = s->sorted_idx.reserve(sizeof(int) * (size_t)(2 * N + 2))) return rc;  // + cell_id scratch
+    if (int rc = s->sorted_pos.reserve(sizeof(double) * (size_t)(D * N + 1))) return rc;
+    int *hist = s->cell_fill.as<int>();
+    int *cell_start = s->cell_start.as<int>();
+    int *sorted_idx = s->sorted_idx.as<int>();
+    int *cell_id = sorted_idx + N;
+    double *sorted_pos = s->sorted_pos.as<double>();
+
+    phase_mark(0);
+    MPB_CUDA(cudaMemsetAsync(hist, 0, sizeof(int) * (size_t)(ncells + 1), st));
+    const unsigned nbN = (unsigned)ceil_div(N > 0 ? N : 1, 256);
+    cell_histogram<D><<<nbN, 256, 0, st>>>(V, N, g, hist, cell_id);
+    MPB_LAUNCHED();
+    if (int rc = exclusive_scan<int, int>(hist, ncells, cell_start, 0, s->scan_tmp, nullptr)) return rc;
+    MPB_CUDA(cudaMemsetAsync(hist, 0, sizeof(int) * (size_t)(ncells + 1), st));
+    cell_scatter<D><<<nbN, 256, 0, st>>>(V, N, cell_id, cell_start, hist, sorted_idx, sorted_pos);
+    MPB_LAUNCHED();
+    phase_mark(1);
+
+    // count pass
+    if (int rc = t->counts.reserve(sizeof(int) * (size_t)(2 * nq + 2))) return rc;
+    if (int rc = t->colptr.reserve(sizeof(int64_t) * (size_t)(nq + 1))) return rc;
+    int *counts = t->counts.as<int>();
+    int *big_list = counts + nq;
+    unsigned long long *d_nbig = reinterpret_cast<unsigned long long *>(c.d_scalar + 1);
+    MPB_CUDA(cudaMemsetAsync(c.d_scalar, 0, sizeof(int64_t) * 2, st));
+    const double r2 = r * r;
+    const unsigned nbQ = (unsigned)ceil_div(nq > 0 ? nq : 1, kWarpsPerBlock);
+    if (nq > 0) {
+        rball_count<D><<<nbQ, kWarpsPerBlock * 32, 0, st>>>(V, s->q0, nq, g, r2, cell_start, sorted_idx, sorted_pos,
+                                                           counts, big_list, d_nbig);
+        MPB_LAUNCHED();
+    }
+    if (int rc = exclusive_scan<int, int64_t>(counts, nq, t->colptr.as<int64_t>(), (int64_t)1, s->scan_tmp,
+                                              c.d_scalar))
+        return rc;
+    phase_mark(2);
+    MPB_CUDA(cudaMemcpyAsync(c.h_scalar, c.d_scalar, sizeof(int64_t) * 2, cudaMemcpyDeviceToHost, st));
+    MPB_CUDA(cudaStreamSynchronize(st));
+    const int64_t nnz = c.h_scalar[0];
+    const int64_t n_big = c.h_scalar[1];
+
+    if (int rc = t->rowval.reserve(sizeof(int64_t) * (size_t)(nnz + 1))) return rc;
+    if (int rc = t->nzval.reserve(sizeof(double) * (size_t)(nnz + 1))) return rc;
+    int64_t *spill_row = nullptr;
+    double *spill_val = nullptr;
+    if (n_big > 0) {
+        if (int rc = t->scratch.reserve(16 * (size_t)(nnz + 1))) return rc;
+        spill_row = t->scratch.as<int64_t>();
+        spill_val = reinterpret_cast<double *>(spill_row + nnz);
+    }
+    phase_mark(3);
+    if (nq > 0 && nnz > 0) {
+        rball_fill<D><<<nbQ, kWarpsPerBlock * 32, 0, st>>>(V, s->q0, nq, g, r2, cell_start, sorted_idx, sorted_pos,
+                                                          t->colptr.as<int64_t>(), t->rowval.as<int64_t>(),
+                                                          t->nzval.as<double>(), spill_row, spill_val);
+        MPB_LAUNCHED();
+        if (n_big > 0) {
+            sort_big_columns<<<(unsigned)n_big, 256, 0, st>>>(big_list, t->colptr.as<int64_t>(), spill_row, spill_val,
+                                                              t->rowval.as<int64_t>(), t->nzval.as<double>());
+            MPB_LAUNCHED();
+        }
+    }
+    phase_mark(4);
+    MPB_CUDA(cudaStreamSynchronize(st));
+    phases_collect(4);
+    t->ncols = nq;
+    t->col0 = s->q0;
+    t->nnz = nnz;
+    t->r = r;
+    return 0;
+}
+
+int compute_bbox(mpb200_samples *s) {
+    Context &c = ctx();
+    const int nb = 2 * c.sm_count;
+    if (int rc = s->minmax.reserve(sizeof(double) * (size_t)(2 * s->d) * (size_t)(nb + 1))) return rc;
+    double *out = s->minmax.as<double>();
+    double *part = out + 2 * s->d;
+    bbox_partial<<<nb, 256, 0, c.stream>>>(s->V.as<double>(), s->N, s->d, part);
+    MPB_LAUNCHED();
+    bbox_final<<<1, 32, 0, c.stream>>>(part, nb, s->d, out);
+    MPB_LAUNCHED();
+    return 0;
+}
+
+int grid_inball_build(mpb200_samples *s, double r, mpb200_table *t) {
+    if (s->d == 2) return build_table<2>(s, r, t);
+    if (s->d == 3) return build_table<3>(s, r, t);
+    return fail(MPB200_EARG, "grid r-ball supports d = 2, 3 (got %d)", s->d);
+}
+
+}  // namespace mpb

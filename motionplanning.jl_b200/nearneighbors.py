@@ -1,0 +1,221 @@
+"""Near-neighbour sample sets served from GPU-built tables.
+
+Mirror of src/nearneighbors.jl: SampleSet / MetricNN (:62-74), ImmutableNNC (:23-28),
+filter_neighborhood (:104-107), the cached inball!/inballF!/inballB! dispatch (:120-136,200-203)
+and viewcol (src/utilities/utils.jl:76-82).  Where the reference fills a MutableNNC lazily, one
+query at a time through a KD-tree (geometric.jl:14; nearneighbors.jl:179-183), this back-end
+builds the whole ImmutableNNC.D matrix in one GPU pass (mpb200_inball_build) and serves columns
+with viewcol -- the seam the reference already has at nearneighbors.jl:128.
+
+Indices are 1-based Int64 exactly as in Julia's SparseMatrixCSC, so the arrays can be handed to
+`SparseMatrixCSC(N, N, colptr, rowval, nzval)` unchanged.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from .statespaces import Euclidean
+
+
+class SparseMatrixCSC:
+    """Field-for-field Julia SparseMatrixCSC{Float64,Int64} (1-based colptr/rowval)."""
+
+    def __init__(self, m, n, colptr, rowval, nzval):
+        self.m, self.n = int(m), int(n)
+        self.colptr, self.rowval, self.nzval = colptr, rowval, nzval
+
+    @property
+    def nnz(self):
+        return int(self.colptr[-1] - 1)
+
+
+class SparseVectorView:
+    """utils.jl:63-75"""
+
+    def __init__(self, n, nzind, nzval):
+        self.n, self.nzind, self.nzval = n, nzind, nzval
+
+    def __len__(self):
+        return self.n
+
+
+def nonzeroinds(x):
+    return x.nzind
+
+
+def nonzeros(x):
+    return x.nzval
+
+
+def viewcol(x, j):
+    """utils.jl:76-82 (j is 1-based)"""
+    if not 1 <= j <= x.n:
+        raise IndexError("BoundsError")
+    r1 = int(x.colptr[j - 1]) - 1
+    r2 = int(x.colptr[j]) - 1
+    return SparseVectorView(x.m, x.rowval[r1:r2], x.nzval[r1:r2])
+
+
+def filter_neighborhood(n, f):
+    """nearneighbors.jl:104-107; f is a boolean mask indexed by 0-based sample position."""
+    inds, ds = n.nzind, n.nzval
+    keep = f[inds - 1]
+    return SparseVectorView(n.n, inds[keep], ds[keep])
+
+
+class ImmutableNNC:
+    """nearneighbors.jl:23-28 -- a fully precomputed neighbour table; `r` is informational
+    (the reference never re-validates it)."""
+
+    def __init__(self, D, r):
+        self.D = D
+        self.r = r
+
+
+class DeviceTable:
+    """Owner of a device-resident CSC table handle (mpb200_table)."""
+
+    def __init__(self):
+        self.h = _lib.c_vp()
+        self.nnz = 0
+        self.ncols = 0
+
+    def close(self):
+        if self.h:
+            _lib.load().mpb200_table_destroy(self.h)
+            self.h = _lib.c_vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class SampleSet:
+    """nearneighbors.jl:14 -- common part of MetricNN / QuasiMetricNN: the sample matrix on the
+    host (N x d, one state per row == Julia's d x N column-major) and its device copy."""
+
+    def __init__(self, V, dist, init):
+        self.V = np.ascontiguousarray(V, dtype=np.float64)
+        if self.V.ndim != 2:
+            raise ValueError("V must be an N x d array (one state per row)")
+        self.dist = dist
+        self.init = np.asarray(init, dtype=np.float64)
+        self._handle = None
+        self.q0, self.q1 = 0, self.V.shape[0]
+        self.pool = _lib.PinnedPool()
+
+    def __len__(self):
+        return self.V.shape[0]
+
+    def __getitem__(self, i):
+        """nearneighbors.jl:111 -- 1-based; NN[0] is the init state"""
+        return self.V[i - 1] if i > 0 else self.init
+
+    def handle(self):
+        if self._handle is None:
+            lib = _lib.lib()
+            h = _lib.c_vp()
+            _lib.check(lib.mpb200_samples_create(_lib.ptr(self.V), self.V.shape[0], self.V.shape[1], ctypes.byref(h)))
+            self._handle = h
+            if (self.q0, self.q1) != (0, self.V.shape[0]):
+                _lib.check(lib.mpb200_samples_set_query_range(h, self.q0, self.q1))
+        return self._handle
+
+    def set_query_range(self, q0, q1):
+        """Multi-GPU shard: this process owns query columns [q0, q1) (0-based)."""
+        self.q0, self.q1 = int(q0), int(q1)
+        if self._handle is not None:
+            _lib.check(_lib.lib().mpb200_samples_set_query_range(self._handle, self.q0, self.q1))
+
+    def close(self):
+        if self._handle is not None:
+            _lib.load().mpb200_samples_destroy(self._handle)
+            self._handle = None
+        self.pool.release()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- batched validity over this sample set --------------------------------------------
+    def points_free(self, CC, SS, fetch=True):
+        """F[i] = is_free_state(V[i], CC, SS) for all i (fmt.jl:31-36) as BitVector chunks."""
+        n = len(self)
+        d = SS.desc()
+        bits = self.pool.array("point_bits", (n + 63) // 64, np.uint64) if fetch else None
+        _lib.check(_lib.lib().mpb200_points_free(self.handle(), CC.handle(), ctypes.byref(d), _lib.ptr(bits)))
+        return bits
+
+    def edges_free(self, table, CC, SS, fetch=True):
+        """Validity bit per stored entry (row y -> column x) of `table`; returns (chunks, checks)."""
+        d = SS.desc()
+        bits = self.pool.array(("edge_bits", id(table)), (table.nnz + 63) // 64, np.uint64) if fetch else None
+        checks = _lib.c_i64(0)
+        _lib.check(_lib.lib().mpb200_edges_free(self.handle(), table.h, CC.handle(), ctypes.byref(d), _lib.ptr(bits),
+                                                ctypes.byref(checks)))
+        CC.count += checks.value
+        return bits, checks.value
+
+    def fetch_table(self, table, key="nn"):
+        """Copy a device table into (pinned, reused) host arrays -> SparseMatrixCSC over the shard."""
+        colptr = self.pool.array((key, "colptr"), table.ncols + 1, np.int64)
+        rowval = self.pool.array((key, "rowval"), table.nnz, np.int64)
+        nzval = self.pool.array((key, "nzval"), table.nnz, np.float64)
+        _lib.check(_lib.lib().mpb200_table_fetch(table.h, _lib.ptr(colptr), _lib.ptr(rowval), _lib.ptr(nzval)))
+        return SparseMatrixCSC(len(self), table.ncols, colptr, rowval, nzval)
+
+
+class MetricNN(SampleSet):
+    """nearneighbors.jl:62-74 for symmetric distances (Euclidean).
+
+    `precompute(r)` plays the role of helper_data_structures + every inball: afterwards
+    `self.cache` is an ImmutableNNC and inball/inballF/inballB are column views."""
+
+    def __init__(self, V, dist=None, init=None):
+        V = np.ascontiguousarray(V, dtype=np.float64)
+        super().__init__(V, dist if dist is not None else Euclidean(), init if init is not None else V[0])
+        self.cache = None
+        self.table = DeviceTable()
+
+    def build_table(self, r):
+        """Device-only: grid build + count + fill; the table stays in HBM. Returns nnz."""
+        nnz = _lib.c_i64(0)
+        _lib.check(_lib.lib().mpb200_inball_build(self.handle(), float(r), ctypes.byref(self.table.h),
+                                                  ctypes.byref(nnz)))
+        self.table.nnz = nnz.value
+        self.table.ncols = self.q1 - self.q0
+        self.r = float(r)
+        return nnz.value
+
+    def precompute(self, r):
+        self.build_table(r)
+        D = self.fetch_table(self.table)
+        self.cache = ImmutableNNC(D, float(r))
+        return self.cache
+
+    def close(self):
+        self.table.close()
+        super().close()
+
+
+def addpoints(NN, W):
+    """nearneighbors.jl:108-109 -- rebuilds the sample set from scratch, as the reference does."""
+    return type(NN)(np.vstack([NN.V, np.atleast_2d(W)]), NN.dist, NN.init)
+
+
+def inball(NN, v, r, f=None):
+    """inball!(NN, v, r[, f]) for a precomputed table (nearneighbors.jl:120,128): v is 1-based
+    and global; with sharded tables v must lie in the owned column range."""
+    if NN.cache is None:
+        NN.precompute(r)
+    col = viewcol(NN.cache.D, v - NN.q0)
+    return filter_neighborhood(col, f) if f is not None else col
+
+
+inballF = inball  # nearneighbors.jl:200-203: for a MetricNN forwards == backwards
+inballB = inball

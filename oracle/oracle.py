@@ -1,0 +1,282 @@
+"""ctypes front-end of the CPU oracle (oracle/_build/liboracle.so).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs -- never by the product package.  See mp_oracle.h for
+the parity-pinning statement.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "liboracle.so")
+c_i64, c_i32, c_dbl, c_vp = ctypes.c_int64, ctypes.c_int32, ctypes.c_double, ctypes.c_void_p
+P = ctypes.POINTER
+_lib = None
+
+
+def build(force=False):
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".c", ".h"))]
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(s) for s in srcs):
+        res = subprocess.run(["make", "-C", _HERE] + (["-B"] if force else []), capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("oracle build failed:\n" + res.stdout + res.stderr)
+    return _SO
+
+
+class Obs2D(ctypes.Structure):
+    _fields_ = [("n_gates", c_i32), ("gate_parent", c_vp), ("gate_aabb", c_vp), ("n_shapes", c_i32),
+                ("shape_kind", c_vp), ("shape_gate", c_vp), ("shape_off", c_vp), ("data", c_vp), ("flags", c_i32)]
+
+
+class Space(ctypes.Structure):
+    _fields_ = [("n", c_i32), ("lo", c_vp), ("hi", c_vp), ("s2w_kind", c_i32), ("dw", c_i32), ("inds", c_vp),
+                ("C", c_vp)]
+
+
+class Checker(ctypes.Structure):
+    _fields_ = [("kind", c_i32), ("obs2d", P(Obs2D)), ("box_lo", c_vp), ("box_hi", c_vp), ("M", c_i32), ("d", c_i32)]
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = ctypes.CDLL(build())
+        L = _lib
+        L.orc_circle_build.argtypes = [c_dbl, c_dbl, c_dbl, c_vp]
+        L.orc_polygon_build.argtypes = [c_vp, ctypes.c_int, c_vp]
+        L.orc_point_colliding_2d.argtypes = [P(Obs2D), c_dbl, c_dbl]
+        L.orc_line_colliding_2d.argtypes = [P(Obs2D), c_dbl, c_dbl, c_dbl, c_dbl]
+        L.orc_points_free_2d.argtypes = [P(Obs2D), c_vp, c_i64, c_vp]
+        L.orc_segments_free_2d.argtypes = [P(Obs2D), c_vp, c_vp, c_i64, c_vp]
+        L.orc_points_free_boxes.argtypes = [c_vp, c_vp, ctypes.c_int, ctypes.c_int, c_vp, c_i64, c_vp]
+        L.orc_segments_free_boxes.argtypes = [c_vp, c_vp, ctypes.c_int, ctypes.c_int, c_vp, c_vp, c_i64, c_vp]
+        L.orc_states_free.argtypes = [P(Checker), P(Space), c_vp, c_i64, c_vp]
+        L.orc_edges_free_csc.argtypes = [P(Checker), P(Space), c_vp, c_i64, c_vp, c_vp, c_i64, c_i64, c_vp, P(c_i64)]
+        L.orc_is_free_motion_straight.argtypes = [P(Checker), P(Space), c_vp, c_vp, P(c_i64)]
+        L.orc_rball_brute.argtypes = [c_vp, c_i64, ctypes.c_int, c_dbl, ctypes.c_int, c_i64, c_i64, c_vp, c_vp, c_vp]
+        L.orc_kdtree_build.restype = c_vp
+        L.orc_kdtree_build.argtypes = [c_vp, c_i64, ctypes.c_int, ctypes.c_int]
+        L.orc_kdtree_free.argtypes = [c_vp]
+        L.orc_rball_kdtree.argtypes = [c_vp, c_dbl, c_i64, c_i64, c_vp, c_vp, c_vp]
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(c_vp)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+# ---- 2-D obstacle tables built by the oracle's own constructors ---------------------------
+def circle_record(c, r):
+    out = np.zeros(7)
+    if lib().orc_circle_build(float(c[0]), float(c[1]), float(r), _p(out)) != 0:
+        raise ValueError("Radius must be positive")
+    return out
+
+
+def polygon_record(points):
+    pts = _f64(points).reshape(-1, 2)
+    out = np.zeros(4 + 6 * len(pts))
+    rc = lib().orc_polygon_build(_p(pts), len(pts), _p(out))
+    if rc == -1:
+        raise ValueError("Polygons need at least 3 points! Try Line?")
+    if rc == -2:
+        raise ValueError("Polygon must be convex")
+    return out
+
+
+class Obstacles2D:
+    """spec: ("compound", [specs...]) | ("circle", (cx, cy), r) | ("polygon", [(x, y), ...])"""
+
+    def __init__(self, spec, fixed_point_test=False):
+        gp, ga, kinds, gates, offs, data = [], [], [], [], [0], []
+
+        def walk(s, parent):
+            if s[0] == "compound":
+                g = len(gp)
+                gp.append(parent)
+                ga.append(None)
+                recs = [walk(c, g) for c in s[1]]
+                if recs:  # SAT2D.jl:91-95
+                    ga[g] = [min(r[0] for r in recs), max(r[1] for r in recs), min(r[2] for r in recs),
+                             max(r[3] for r in recs)]
+                else:  # SAT2D.jl:89
+                    ga[g] = [0.0, 0.0, 0.0, 0.0]
+                return ga[g]
+            if s[0] == "circle":
+                rec = circle_record(s[1], s[2])
+                kinds.append(0)
+                aabb = [rec[3], rec[4], rec[5], rec[6]]
+            else:
+                rec = polygon_record(s[1])
+                kinds.append(1)
+                aabb = [rec[0], rec[1], rec[2], rec[3]]
+            gates.append(parent)
+            data.extend(rec.tolist())
+            offs.append(len(data))
+            return aabb
+
+        walk(spec, -1)
+        self.gate_parent = np.asarray(gp, dtype=np.int32)
+        self.gate_aabb = _f64(np.asarray(ga, dtype=np.float64).reshape(-1))
+        self.shape_kind = np.asarray(kinds, dtype=np.int32)
+        self.shape_gate = np.asarray(gates, dtype=np.int32)
+        self.shape_off = np.asarray(offs, dtype=np.int32)
+        self.data = _f64(data)
+        self.c = Obs2D(len(gp), _p(self.gate_parent), _p(self.gate_aabb), len(kinds), _p(self.shape_kind),
+                       _p(self.shape_gate), _p(self.shape_off), _p(self.data), 1 if fixed_point_test else 0)
+
+    def points_free(self, Pts):
+        Pts = _f64(Pts).reshape(-1, 2)
+        out = np.zeros(len(Pts), dtype=np.uint8)
+        lib().orc_points_free_2d(ctypes.byref(self.c), _p(Pts), len(Pts), _p(out))
+        return out.astype(bool)
+
+    def segments_free(self, V, W):
+        V, W = _f64(V).reshape(-1, 2), _f64(W).reshape(-1, 2)
+        out = np.zeros(len(V), dtype=np.uint8)
+        lib().orc_segments_free_2d(ctypes.byref(self.c), _p(V), _p(W), len(V), _p(out))
+        return out.astype(bool)
+
+    def checker(self):
+        return Checker(0, ctypes.pointer(self.c), None, None, 0, 2)
+
+
+def spec_from_shape(shape):
+    """Raw constructor inputs of a product-side shape tree (reads c/r, points, parts only)."""
+    name = type(shape).__name__
+    if name == "Compound2D":
+        return ("compound", [spec_from_shape(p) for p in shape.parts])
+    if name == "Circle":
+        return ("circle", tuple(shape.c), shape.r)
+    return ("polygon", [tuple(p) for p in shape.points])
+
+
+class Boxes:
+    def __init__(self, box_list):
+        """box_list: list of d x 2 [lo hi] matrices (test/obstaclesets/ND.jl) or (lo, hi) pairs"""
+        los, his = [], []
+        for b in box_list:
+            if isinstance(b, tuple):
+                lo, hi = b
+            else:
+                b = np.asarray(b, dtype=np.float64)
+                lo, hi = b[:, 0], b[:, 1]
+            los.append(np.asarray(lo, dtype=np.float64))
+            his.append(np.asarray(hi, dtype=np.float64))
+        self.M = len(los)
+        self.d = len(los[0]) if los else 1
+        self.lo = _f64(np.stack(los)) if los else np.zeros((0, 1))
+        self.hi = _f64(np.stack(his)) if his else np.zeros((0, 1))
+
+    def points_free(self, Pts):
+        Pts = _f64(Pts).reshape(-1, self.d)
+        out = np.zeros(len(Pts), dtype=np.uint8)
+        lib().orc_points_free_boxes(_p(self.lo), _p(self.hi), self.M, self.d, _p(Pts), len(Pts), _p(out))
+        return out.astype(bool)
+
+    def segments_free(self, V, W):
+        V, W = _f64(V).reshape(-1, self.d), _f64(W).reshape(-1, self.d)
+        out = np.zeros(len(V), dtype=np.uint8)
+        lib().orc_segments_free_boxes(_p(self.lo), _p(self.hi), self.M, self.d, _p(V), _p(W), len(V), _p(out))
+        return out.astype(bool)
+
+    def checker(self):
+        return Checker(1, None, _p(self.lo), _p(self.hi), self.M, self.d)
+
+
+class StateSpace:
+    """lo/hi bounds + s2w: None (Identity) | ("view", [1-based inds]) | ("matrix", C)"""
+
+    def __init__(self, lo, hi, s2w=None):
+        self.lo, self.hi = _f64(lo), _f64(hi)
+        n = len(self.lo)
+        self.inds = self.C = None
+        kind, dw = 0, n
+        if s2w is not None and s2w[0] == "view":
+            kind, self.inds = 1, np.asarray([i - 1 for i in s2w[1]], dtype=np.int32)
+            dw = len(self.inds)
+        elif s2w is not None and s2w[0] == "matrix":
+            C = np.asarray(s2w[1], dtype=np.float64)
+            kind, dw = 2, C.shape[0]
+            self.C = np.ascontiguousarray(C.ravel(order="F"))
+        self.n, self.dw = n, dw
+        self.c = Space(n, _p(self.lo), _p(self.hi), kind, dw, _p(self.inds), _p(self.C))
+
+
+def states_free(obs, space, Pts):
+    Pts = _f64(Pts).reshape(-1, space.n)
+    out = np.zeros(len(Pts), dtype=np.uint8)
+    cc = obs.checker()
+    lib().orc_states_free(ctypes.byref(cc), ctypes.byref(space.c), _p(Pts), len(Pts), _p(out))
+    return out.astype(bool)
+
+
+def motions_free_straight(obs, space, V, W):
+    """is_free_motion(v, w, CC, SS) per pair; returns (bool[n], CC.count increment)."""
+    V, W = _f64(V).reshape(-1, space.n), _f64(W).reshape(-1, space.n)
+    cc = obs.checker()
+    cnt = c_i64(0)
+    out = np.zeros(len(V), dtype=bool)
+    L = lib()
+    for i in range(len(V)):
+        out[i] = bool(L.orc_is_free_motion_straight(ctypes.byref(cc), ctypes.byref(space.c), _p(V[i]), _p(W[i]),
+                                                    ctypes.byref(cnt)))
+    return out, cnt.value
+
+
+def edges_free_csc(obs, space, V, colptr, rowval, c0=0):
+    """validity per stored entry (row y -> column x); returns (uint8[nnz], count)"""
+    V = _f64(V)
+    colptr = np.ascontiguousarray(colptr, dtype=np.int64)
+    rowval = np.ascontiguousarray(rowval, dtype=np.int64)
+    ncols = len(colptr) - 1
+    out = np.zeros(len(rowval), dtype=np.uint8)
+    cc = obs.checker()
+    cnt = c_i64(0)
+    lib().orc_edges_free_csc(ctypes.byref(cc), ctypes.byref(space.c), _p(V), len(V), _p(colptr), _p(rowval), c0,
+                             c0 + ncols, _p(out), ctypes.byref(cnt))
+    return out, cnt.value
+
+
+# ---- r-ball ------------------------------------------------------------------------------------
+def rball_brute(V, r, pred=0, q0=0, q1=None):
+    V = _f64(V)
+    N, d = V.shape
+    q1 = N if q1 is None else q1
+    colptr = np.zeros(q1 - q0 + 1, dtype=np.int64)
+    lib().orc_rball_brute(_p(V), N, d, float(r), pred, q0, q1, _p(colptr), None, None)
+    nnz = int(colptr[-1] - 1)
+    rowval = np.zeros(nnz, dtype=np.int64)
+    nzval = np.zeros(nnz, dtype=np.float64)
+    lib().orc_rball_brute(_p(V), N, d, float(r), pred, q0, q1, _p(colptr), _p(rowval), _p(nzval))
+    return colptr, rowval, nzval
+
+
+class KDTree:
+    def __init__(self, V, leafsize=10):
+        self.V = _f64(V)
+        self.h = lib().orc_kdtree_build(_p(self.V), self.V.shape[0], self.V.shape[1], leafsize)
+
+    def __del__(self):
+        try:
+            lib().orc_kdtree_free(self.h)
+        except Exception:
+            pass
+
+    def rball(self, r, q0=0, q1=None):
+        N = self.V.shape[0]
+        q1 = N if q1 is None else q1
+        colptr = np.zeros(q1 - q0 + 1, dtype=np.int64)
+        lib().orc_rball_kdtree(self.h, float(r), q0, q1, _p(colptr), None, None)
+        nnz = int(colptr[-1] - 1)
+        rowval = np.zeros(nnz, dtype=np.int64)
+        nzval = np.zeros(nnz, dtype=np.float64)
+        lib().orc_rball_kdtree(self.h, float(r), q0, q1, _p(colptr), _p(rowval), _p(nzval))
+        return colptr, rowval, nzval
