@@ -3,6 +3,7 @@
 #include "common.cuh"
 #include "predicates.cuh"
 #include <climits>
+#include <limits>
 #include <new>
 #include <vector>
 
@@ -195,7 +196,7 @@ int mpb200_samples_destroy(mpb200_samples *s) {
     if (!s) return MPB200_OK;
     if (ctx().ready) cudaStreamSynchronize(ctx().stream);
     s->V.release(); s->cell_start.release(); s->cell_fill.release(); s->sorted_idx.release();
-    s->sorted_pos.release(); s->minmax.release(); s->scan_tmp.release(); s->point_bits.release();
+    s->sorted_pos.release(); s->minmax.release(); s->scan_tmp.release(); s->point_bits.release(); s->q_order.release();
     delete s;
     return MPB200_OK;
 }
@@ -262,7 +263,7 @@ int mpb200_table_fetch(const mpb200_table *t, int64_t *colptr, int64_t *rowval, 
 int mpb200_table_destroy(mpb200_table *t) {
     if (!t) return MPB200_OK;
     if (ctx().ready) cudaStreamSynchronize(ctx().stream);
-    t->colptr.release(); t->rowval.release(); t->nzval.release(); t->counts.release();
+    t->colptr.release(); t->rowval.release(); t->nzval.release(); t->counts.release(); t->masks.release();
     t->edge_bits.release(); t->scratch.release();
     delete t;
     return MPB200_OK;
@@ -278,13 +279,18 @@ int mpb200_obstacles2d_create(const mpb200_obstacles2d_desc *d, mpb200_obstacles
     MPB_CHECK_ARG(d->n_gates == 0 || (d->gate_parent && d->gate_aabb), "NULL gate arrays");
     const int G = d->n_gates, S = d->n_shapes;
     const int data_words = S ? d->shape_off[S] : 0;
-    const int base = 4 + 5 * G + 4 * S;
+    // layout (predicates.cuh): int directory | gate AABBs | shape data
+    const int dir_words = (4 + G + 4 * S + 1) / 2;
+    const int gate_base = dir_words;
+    const int cull_base = gate_base + 4 * G;
+    const int base = cull_base + 4 * S;
     std::vector<double> T((size_t)(base + data_words + 1), 0.0);
-    T[0] = G; T[1] = S; T[2] = d->flags; T[3] = 0;
+    int *I = reinterpret_cast<int *>(T.data());
+    I[0] = G; I[1] = S; I[2] = d->flags; I[3] = gate_base;
     for (int g = 0; g < G; ++g) {
-        MPB_CHECK_ARG(d->gate_parent[g] < g, "gate parents must precede their children");
-        T[4 + 5 * g] = d->gate_parent[g];
-        for (int k = 0; k < 4; ++k) T[4 + 5 * g + 1 + k] = d->gate_aabb[4 * g + k];
+        MPB_CHECK_ARG(d->gate_parent[g] < g && d->gate_parent[g] >= -1, "gate parents must precede their children");
+        I[4 + g] = d->gate_parent[g];
+        for (int k = 0; k < 4; ++k) T[gate_base + 4 * g + k] = d->gate_aabb[4 * g + k];
     }
     for (int s = 0; s < S; ++s) {
         int len = d->shape_off[s + 1] - d->shape_off[s];
@@ -299,10 +305,35 @@ int mpb200_obstacles2d_create(const mpb200_obstacles2d_desc *d, mpb200_obstacles
             MPB_CHECK_ARG(len >= 4 + 18 && (len - 4) % 6 == 0, "Polygon record must have 4+6K doubles, K >= 3");  // SAT2D.jl:39
             K = (len - 4) / 6;
         }
-        double *dir = &T[4 + 5 * G + 4 * s];
+        int *dir = I + 4 + G + 4 * s;
         dir[0] = kind; dir[1] = d->shape_gate[s]; dir[2] = base + d->shape_off[s]; dir[3] = K;
     }
     for (int i = 0; i < data_words; ++i) T[base + i] = d->data[i];
+    // cull boxes + gate consistency (predicates.cuh): AABB of shape s inside its gate chain
+    auto inside = [](const double *in, const double *out) {
+        return out[0] <= in[0] && in[1] <= out[1] && out[2] <= in[2] && in[3] <= out[3];
+    };
+    bool consistent = true;
+    for (int g = 0; g < G; ++g)
+        if (d->gate_parent[g] >= 0 && !inside(&d->gate_aabb[4 * g], &d->gate_aabb[4 * d->gate_parent[g]])) consistent = false;
+    for (int s = 0; s < S; ++s) {
+        const double *rec = d->data + d->shape_off[s];
+        const double *own = d->shape_kind[s] == 0 ? rec + 3 : rec;  // xlo xhi ylo yhi
+        if (d->shape_gate[s] >= 0 && !inside(own, &d->gate_aabb[4 * d->shape_gate[s]])) consistent = false;
+    }
+    const double inf = std::numeric_limits<double>::infinity();
+    for (int s = 0; s < S; ++s) {
+        double *cb = &T[cull_base + 4 * s];
+        const double *rec = d->data + d->shape_off[s];
+        if (!consistent || (d->shape_kind[s] == 0 && d->shape_gate[s] < 0)) {
+            cb[0] = -inf; cb[1] = inf; cb[2] = -inf; cb[3] = inf;
+        } else if (d->shape_kind[s] == 0) {
+            for (int k = 0; k < 4; ++k) cb[k] = d->gate_aabb[4 * d->shape_gate[s] + k];
+        } else {
+            for (int k = 0; k < 4; ++k) cb[k] = rec[k];
+        }
+    }
+    if (consistent) I[2] |= 2;
     mpb200_obstacles *o = new (std::nothrow) mpb200_obstacles();
     if (!o) return fail(MPB200_ENOMEM, "out of host memory");
     o->kind = 0; o->n_gates = G; o->n_shapes = S; o->flags = d->flags;

@@ -67,18 +67,13 @@ points_free_kernel(const double *__restrict__ V, int64_t n, SpaceDev S, const do
     }
 }
 
-// column (0-based, shard-local) of stored entry e: the w with colptr[w] <= e+1 < colptr[w+1]
-__device__ __forceinline__ int64_t column_of(const int64_t *__restrict__ colptr, int64_t lo, int64_t hi, int64_t e1) {
-    // upper_bound(e1) over colptr[lo..hi] minus one
-    while (lo < hi) {
-        int64_t mid = (lo + hi) >> 1;
-        if (colptr[mid] <= e1) lo = mid + 1; else hi = mid;
-    }
-    return lo - 1;
-}
-
+// One warp per column x of the table: the 32 lanes hold stored entries (row y -> column x) of
+// that column, i.e. edges sharing the endpoint V[x] (coherent control flow, no per-edge search
+// for the column).  The next column's colptr pair is prefetched while the current one is
+// processed.  Validity bits go to the (pre-zeroed) BitVector words with at most two atomicOr
+// per 32 edges; the per-CTA check counter is reduced before one atomicAdd.
 template <int N, int DW, int KIND>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, (DW <= 3) ? 3 : 1)
 edges_free_kernel(const double *__restrict__ V, const int64_t *__restrict__ colptr,
                   const int64_t *__restrict__ rowval, int64_t ncols, int64_t col0, int64_t nnz, SpaceDev S,
                   const double *__restrict__ g_table, int table_words, int M, bool use_smem,
@@ -86,33 +81,72 @@ edges_free_kernel(const double *__restrict__ V, const int64_t *__restrict__ colp
     extern __shared__ double s_table[];
     const double *T = stage_table(g_table, table_words, use_smem, s_table);
     const int lane = threadIdx.x & 31;
-    const int64_t nnz_pad = (nnz + 31) & ~int64_t(31);
+    const int64_t gwarp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     unsigned long long my_checks = 0;
-    for (int64_t e0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) & ~int64_t(31); e0 < nnz_pad;
-         e0 += (int64_t)gridDim.x * blockDim.x) {
-        // warp-uniform bracket of columns spanned by the 32 edges, then a short per-lane search
-        int64_t e_last = e0 + 31 < nnz ? e0 + 31 : nnz - 1;
-        int64_t c_first = column_of(colptr, 0, ncols + 1, e0 + 1);
-        int64_t c_last = column_of(colptr, c_first, ncols + 1, e_last + 1);
-        const int64_t e = e0 + lane;
-        bool ok = false;
-        if (e < nnz) {
-            int64_t w = column_of(colptr, c_first, c_last + 2, e + 1);
-            const int64_t x = col0 + w;
-            const int64_t y = rowval[e] - 1;
-            double a[N], b[N];
-#pragma unroll
-            for (int k = 0; k < N; ++k) { a[k] = V[y * N + k]; b[k] = V[x * N + k]; }
-            bool checked;
-            ok = motion_free<N, DW, KIND>(S, T, M, a, b, &checked);
-            my_checks += checked ? 1 : 0;
-        }
-        unsigned m = __ballot_sync(0xffffffffu, ok);
-        if (lane == 0) bits32[e0 >> 5] = m;
+    // 2-D compound: decode the table header once and keep this lane's cull box in registers
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    double cull_xl = inf, cull_xh = -inf, cull_yl = inf, cull_yh = -inf;
+    Obs2 O(KIND == 0 ? T : nullptr, KIND == 0);
+    if (KIND == 0 && lane < O.S && O.S <= 32) {
+        const double *cb = O.cull_box(lane);
+        cull_xl = cb[0]; cull_xh = cb[1]; cull_yl = cb[2]; cull_yh = cb[3];
     }
+    int64_t c = gwarp, beg = 0, end = 0;
+    if (c < ncols) { beg = colptr[c] - 1; end = colptr[c + 1] - 1; }
+    while (c < ncols) {
+        const int64_t cn = c + nwarps;
+        int64_t begn = 0, endn = 0;
+        if (cn < ncols) { begn = colptr[cn] - 1; endn = colptr[cn + 1] - 1; }  // prefetch
+        if (beg < end) {
+            double b[N], q[DW];
+#pragma unroll
+            for (int k = 0; k < N; ++k) b[k] = V[(col0 + c) * N + k];
+            state2workspace<N, DW>(S, b, q);  // the last waypoint is never bounds-checked (Q4)
+            for (int64_t e0 = beg; e0 < end; e0 += 32) {
+                const int64_t e = e0 + lane;
+                bool run = false;
+                double a[N], p[DW];
+#pragma unroll
+                for (int k = 0; k < N; ++k) a[k] = 0.0;
+                if (e < end) {
+                    const int64_t y = rowval[e] - 1;
+#pragma unroll
+                    for (int k = 0; k < N; ++k) a[k] = V[y * N + k];
+                    run = in_state_space<N>(S, a);  // statespaces.jl:155: in_state_space(wps[1]) && segment test
+                }
+                state2workspace<N, DW>(S, a, p);
+                my_checks += run ? 1 : 0;
+                // warp-collective: every lane must make the call (no short-circuit on `run`)
+                bool seg_free;
+                if (KIND == 0)
+                    seg_free = !warp_line_colliding_2d(O, cull_xl, cull_xh, cull_yl, cull_yh, p[0], p[DW > 1 ? 1 : 0], q[0],
+                                                       q[DW > 1 ? 1 : 0], run);
+                else
+                    seg_free = warp_box_segment_free<DW>(T, M, p, q, run);
+                const bool ok = run && seg_free;
+                const unsigned m = __ballot_sync(0xffffffffu, ok);
+                if (lane == 0 && m) {
+                    const int sh = (int)(e0 & 31);
+                    const int64_t wi = e0 >> 5;
+                    atomicOr(&bits32[wi], m << sh);
+                    if (sh && (m >> (32 - sh))) atomicOr(&bits32[wi + 1], m >> (32 - sh));
+                }
+            }
+        }
+        c = cn; beg = begn; end = endn;
+    }
+    // per-CTA reduction of the CC.count increment
+    __shared__ unsigned long long s_checks[kThreads / 32];
 #pragma unroll
     for (int o = 16; o; o >>= 1) my_checks += __shfl_xor_sync(0xffffffffu, my_checks, o);
-    if (lane == 0 && my_checks) atomicAdd(checks, my_checks);
+    if (lane == 0) s_checks[threadIdx.x >> 5] = my_checks;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int w = 0; w < kThreads / 32; ++w) t += s_checks[w];
+        if (t) atomicAdd(checks, t);
+    }
 }
 
 template <int N, int DW, int KIND>
@@ -150,7 +184,7 @@ static LaunchCfg make_cfg(const mpb200_obstacles *o, int64_t work) {
     L.use_smem = bytes <= kSmemTableMax;
     L.smem = L.use_smem ? bytes : 0;
     int64_t blocks = ceil_div(work > 0 ? work : 1, kThreads);
-    int64_t cap = (int64_t)ctx().sm_count * 8;  // persistent-style grid: a multiple of the SM count
+    int64_t cap = (int64_t)ctx().sm_count * 16;  // persistent-style grid: a multiple of the SM count
     L.grid = (unsigned)(blocks < cap ? blocks : cap);
     return L;
 }
@@ -251,7 +285,7 @@ int edges_free_device(const double *dV, int d, const mpb200_table *t, const mpb2
     int dw;
     if (int rc = make_space(ss, d, &S, &dw)) return rc;
     if (int rc = check_obstacles(o, dw)) return rc;
-    LaunchCfg L = make_cfg(o, t->nnz);
+    LaunchCfg L = make_cfg(o, t->ncols * 32);
     cudaStream_t st = ctx().stream;
     const int64_t *colptr = t->colptr.as<int64_t>();
     const int64_t *rowval = t->rowval.as<int64_t>();

@@ -87,6 +87,7 @@ struct mpb200_table {
     mpb::DevBuf rowval;    // int64 nnz, 1-based global row ids
     mpb::DevBuf nzval;     // f64 nnz
     mpb::DevBuf counts;    // int32 ncols (scratch)
+    mpb::DevBuf masks;     // 128-bit hit mask per query column (scratch between count and fill)
     mpb::DevBuf edge_bits; // uint64 ceil(nnz/64): last mpb200_edges_free result
     mpb::DevBuf scratch;   // big-column spill etc.
 };
@@ -103,6 +104,7 @@ struct mpb200_samples {
     mpb::DevBuf sorted_pos;  // f64 d x N positions in cell order (AoS)
     mpb::DevBuf minmax;      // f64 2*d bounding box
     mpb::DevBuf scan_tmp;    // scan block sums
+    mpb::DevBuf q_order;     // int32: cell-order positions owned by this shard (+ scratch)
     mpb::DevBuf point_bits;  // uint64 ceil(N/64): last mpb200_points_free result
 };
 

@@ -147,64 +147,261 @@ __device__ __forceinline__ bool run_span(const GridDev &g, const int *c, int run
     return true;
 }
 
+// ---- thread-per-query passes -------------------------------------------------------------
+// Queries are visited in CELL order (one thread per query), so the 32 lanes of a warp sit in the
+// same or adjacent cells and read the same candidate spans (broadcast / L1 hits), and every
+// lane is busy.  q_order (optional) lists the cell-order positions owned by this shard.
+constexpr int kQThreads = 128;
+constexpr int kListCap = 64;                  // hits staged per query thread; more -> warp path
+constexpr int kListStride = kQThreads + 1;    // padded: conflict-free column reads
+
+constexpr int kMaskBits = 128;  // candidates per query covered by the hit mask
+
+// candidate spans of a query: begs[r], lens[r] for the 3^(D-1) x-runs (len 0 = outside the grid)
 template <int D>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
-rball_count(const double *__restrict__ V, int64_t q0, int64_t nq, GridDev g, double r2,
-            const int *__restrict__ cell_start, const int *__restrict__ sorted_idx,
-            const double *__restrict__ sorted_pos, int *__restrict__ counts, int *__restrict__ big_list,
-            unsigned long long *__restrict__ n_big) {
+__device__ __forceinline__ int query_spans(const GridDev &g, const double *p, const int *__restrict__ cell_start,
+                                           int *begs, int *lens) {
     constexpr int kRuns = (D == 2) ? 3 : 9;
-    const int lane = threadIdx.x & 31;
-    const int64_t w = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-    if (w >= nq) return;
-    const int64_t v = q0 + w;
-    double p[D];
-#pragma unroll
-    for (int i = 0; i < D; ++i) p[i] = V[v * D + i];
     int c[D];
     cell_of<D>(g, p, c);
-    int cnt = 0;
+    int total = 0;
 #pragma unroll
     for (int run = 0; run < kRuns; ++run) {
-        int beg, end;
-        if (!run_span<D>(g, c, run, cell_start, &beg, &end)) continue;
-        for (int k = beg + lane; k < end; k += 32) {
+        int beg = 0, end = 0;
+        if (!run_span<D>(g, c, run, cell_start, &beg, &end)) { beg = 0; end = 0; }
+        begs[run] = beg;
+        lens[run] = end - beg;
+        total += end - beg;
+    }
+    return total;
+}
+
+// Count pass.  Besides the per-column count it records WHICH candidates hit as a 128-bit mask
+// (bit j = j-th candidate in run order), so the fill pass never re-evaluates a distance.
+template <int D>
+__global__ void __launch_bounds__(kQThreads)
+rball_count(const double *__restrict__ sorted_pos, const int *__restrict__ sorted_idx,
+            const int *__restrict__ q_order, int64_t nq, int64_t q0, GridDev g, double r2,
+            const int *__restrict__ cell_start, int list_cap, int *__restrict__ counts,
+            ulonglong2 *__restrict__ masks, int *__restrict__ big_list, unsigned long long *__restrict__ n_big) {
+    constexpr int kRuns = (D == 2) ? 3 : 9;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nq) return;
+    const int pos = q_order ? q_order[t] : (int)t;
+    double p[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) p[i] = sorted_pos[(size_t)pos * D + i];
+    int begs[kRuns], lens[kRuns];
+    const int total = query_spans<D>(g, p, cell_start, begs, lens);
+    int cnt = 0, j = 0;
+    unsigned long long m0 = 0, m1 = 0;
+#pragma unroll
+    for (int run = 0; run < kRuns; ++run) {
+        const int beg = begs[run], end = begs[run] + lens[run];
+        for (int k = beg; k < end; ++k, ++j) {
             double b[D];
 #pragma unroll
             for (int i = 0; i < D; ++i) b[i] = sorted_pos[(size_t)k * D + i];
-            int idx = sorted_idx[k];
-            double s = sqdist<D>(p, b);
-            cnt += (idx != (int)v && s <= r2) ? 1 : 0;
+            const bool hit = (k != pos) && (sqdist<D>(p, b) <= r2);
+            cnt += hit ? 1 : 0;
+            if (hit) {
+                if (j < 64) m0 |= 1ULL << j;
+                else if (j < 128) m1 |= 1ULL << (j - 64);
+            }
         }
     }
+    const int w = (int)(sorted_idx[pos] - q0);
+    counts[w] = cnt;
+    masks[t] = make_ulonglong2(m0, m1);
+    if (cnt > 0 && (cnt > list_cap || total > kMaskBits)) {
+        unsigned long long slot = atomicAdd(n_big, 1ULL);
+        big_list[slot] = w;
+    }
+}
+
+// ascending bitonic sort of two keys per lane (element e = lane + 32 r)
+__device__ __forceinline__ void bitonic64(unsigned &k0, unsigned &k1, int lane) {
 #pragma unroll
-    for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-    if (lane == 0) {
-        counts[w] = cnt;
-        if (cnt > kStageCap) {
-            unsigned long long slot = atomicAdd(n_big, 1ULL);
-            big_list[slot] = (int)w;
+    for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            const unsigned o0 = __shfl_xor_sync(0xffffffffu, k0, stride);
+            const unsigned o1 = __shfl_xor_sync(0xffffffffu, k1, stride);
+            const bool lower = (lane & stride) == 0;
+            const bool up0 = (lane & size) == 0;                 // element lane
+            const bool up1 = ((lane + 32) & size) == 0;          // element lane + 32
+            k0 = (lower == up0) ? min(k0, o0) : max(k0, o0);
+            k1 = (lower == up1) ? min(k1, o1) : max(k1, o1);
+        }
+    }
+    {   // size 64, stride 32: register-local, ascending
+        const unsigned lo = min(k0, k1), hi = max(k0, k1);
+        k0 = lo; k1 = hi;
+    }
+#pragma unroll
+    for (int stride = 16; stride > 0; stride >>= 1) {
+        const unsigned o0 = __shfl_xor_sync(0xffffffffu, k0, stride);
+        const unsigned o1 = __shfl_xor_sync(0xffffffffu, k1, stride);
+        const bool lower = (lane & stride) == 0;
+        k0 = lower ? min(k0, o0) : max(k0, o0);
+        k1 = lower ? min(k1, o1) : max(k1, o1);
+    }
+}
+
+// Fill: each thread stages the cell-order positions of its query's hits (unsorted) in shared
+// memory; then the warp walks over its 32 columns two at a time, sorts each one by sample index
+// in registers (bitonic over lanes; the key carries the stage slot in its low 6 bits), fetches
+// the neighbour position from the cell-ordered copy (cache-friendly), recomputes the exact
+// distance and writes the column as one contiguous Int64 / Float64 burst.  Columns longer than
+// kListCap are left to rball_fill_big.  Requires N < 2^26 (key packing); otherwise the host
+// routes every column through rball_fill_big.
+template <int D>
+__device__ __forceinline__ void emit_entry(const double *__restrict__ sorted_pos, int kpos, unsigned idx,
+                                           const double *pc, long long at, int64_t *__restrict__ rowval,
+                                           double *__restrict__ nzval) {
+    double b[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) b[i] = sorted_pos[(size_t)kpos * D + i];
+    rowval[at] = (int64_t)idx + 1;
+    nzval[at] = sqrt(sqdist<D>(pc, b));
+}
+
+constexpr int kColsPerStep = 4;  // columns sorted concurrently by one warp (independent chains)
+
+template <int D>
+__global__ void __launch_bounds__(kQThreads)
+rball_fill(const double *__restrict__ sorted_pos, const int *__restrict__ sorted_idx,
+           const int *__restrict__ q_order, const ulonglong2 *__restrict__ masks, int64_t nq, int64_t q0, GridDev g,
+           const int *__restrict__ cell_start, const int64_t *__restrict__ colptr, int64_t *__restrict__ rowval,
+           double *__restrict__ nzval) {
+    constexpr int kRuns = (D == 2) ? 3 : 9;
+    constexpr int U = kColsPerStep;
+    __shared__ int s_list[kListCap * kListStride];
+    const int lane = threadIdx.x & 31;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int k_mine = 0;
+    long long base = 0;
+    double p[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) p[i] = 0.0;
+    if (t < nq) {
+        const int pos = q_order ? q_order[t] : (int)t;
+#pragma unroll
+        for (int i = 0; i < D; ++i) p[i] = sorted_pos[(size_t)pos * D + i];
+        const int64_t w = sorted_idx[pos] - q0;
+        base = colptr[w] - 1;
+        k_mine = (int)(colptr[w + 1] - colptr[w]);
+        int begs[kRuns], lens[kRuns];
+        const int total = query_spans<D>(g, p, cell_start, begs, lens);
+        if (k_mine > kListCap || total > kMaskBits) k_mine = 0;  // handled by rball_fill_big
+        if (k_mine > 0) {
+            // phase A: decode the hit mask into cell-order positions (no distance is re-evaluated)
+            const ulonglong2 mk = masks[t];
+            int n = 0;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                unsigned long long m = h ? mk.y : mk.x;
+                while (m) {
+                    int j = __ffsll((long long)m) - 1 + 64 * h;
+                    m &= m - 1;
+                    int kp = 0;
+#pragma unroll
+                    for (int run = 0; run < kRuns; ++run) {  // run containing candidate j
+                        const bool here = (j >= 0) && (j < lens[run]);
+                        kp = here ? begs[run] + j : kp;
+                        j = here ? -1 : j - lens[run];
+                    }
+                    s_list[n * kListStride + threadIdx.x] = kp;
+                    ++n;
+                }
+            }
+        }
+    }
+    __syncwarp();
+    // phase B: the warp sorts and writes its 32 columns, U at a time
+    const int tid0 = threadIdx.x & ~31;
+    for (int cl0 = 0; cl0 < 32; cl0 += U) {
+        int kc[U];
+        unsigned key[U];
+        long long basec[U];
+        double pc[U][D];
+        int kmax = 0;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            kc[u] = __shfl_sync(0xffffffffu, k_mine, cl0 + u);
+            basec[u] = __shfl_sync(0xffffffffu, base, cl0 + u);
+#pragma unroll
+            for (int i = 0; i < D; ++i) pc[u][i] = __shfl_sync(0xffffffffu, p[i], cl0 + u);
+            kmax = max(kmax, kc[u]);
+        }
+        if (kmax == 0) continue;
+        if (kmax <= 32) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                key[u] = 0xffffffffu;
+                if (lane < kc[u])
+                    key[u] = ((unsigned)sorted_idx[s_list[lane * kListStride + tid0 + cl0 + u]] << 6) | (unsigned)lane;
+            }
+#pragma unroll
+            for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+                for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                    const bool up = (lane & size) == 0;
+                    const bool lower = (lane & stride) == 0;
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const unsigned other = __shfl_xor_sync(0xffffffffu, key[u], stride);
+                        key[u] = (lower == up) ? min(key[u], other) : max(key[u], other);
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (lane < kc[u]) {
+                    const int kp = s_list[(key[u] & 63u) * kListStride + tid0 + cl0 + u];
+                    emit_entry<D>(sorted_pos, kp, key[u] >> 6, pc[u], basec[u] + lane, rowval, nzval);
+                }
+        } else {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (kc[u] == 0) continue;
+                const int col = tid0 + cl0 + u;
+                unsigned k0 = 0xffffffffu, k1 = 0xffffffffu;
+                if (lane < kc[u]) k0 = ((unsigned)sorted_idx[s_list[lane * kListStride + col]] << 6) | (unsigned)lane;
+                if (lane + 32 < kc[u])
+                    k1 = ((unsigned)sorted_idx[s_list[(lane + 32) * kListStride + col]] << 6) | (unsigned)(lane + 32);
+                bitonic64(k0, k1, lane);
+                if (lane < kc[u])
+                    emit_entry<D>(sorted_pos, s_list[(k0 & 63u) * kListStride + col], k0 >> 6, pc[u], basec[u] + lane,
+                                  rowval, nzval);
+                if (lane + 32 < kc[u])
+                    emit_entry<D>(sorted_pos, s_list[(k1 & 63u) * kListStride + col], k1 >> 6, pc[u],
+                                  basec[u] + lane + 32, rowval, nzval);
+            }
         }
     }
 }
 
+// Warp-per-query path for the (rare) columns with more than kListCap hits, driven by big_list:
+// hits are ballot-compacted into a per-warp stage and rank-sorted there (<= kStageCap), or
+// spilled unsorted for sort_big_columns.
 template <int D>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
-rball_fill(const double *__restrict__ V, int64_t q0, int64_t nq, GridDev g, double r2,
-           const int *__restrict__ cell_start, const int *__restrict__ sorted_idx,
-           const double *__restrict__ sorted_pos, const int64_t *__restrict__ colptr,
-           int64_t *__restrict__ rowval, double *__restrict__ nzval,
-           int64_t *__restrict__ spill_row, double *__restrict__ spill_val) {
+rball_fill_big(const double *__restrict__ V, const int *__restrict__ big_list, int64_t n_big, int64_t q0, GridDev g,
+               double r2, const int *__restrict__ cell_start, const int *__restrict__ sorted_idx,
+               const double *__restrict__ sorted_pos, const int64_t *__restrict__ colptr,
+               int64_t *__restrict__ rowval, double *__restrict__ nzval,
+               int64_t *__restrict__ spill_row, double *__restrict__ spill_val) {
     constexpr int kRuns = (D == 2) ? 3 : 9;
     __shared__ int s_idx[kWarpsPerBlock][kStageCap];
     __shared__ double s_sq[kWarpsPerBlock][kStageCap];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int64_t w = (int64_t)blockIdx.x * kWarpsPerBlock + wid;
-    if (w >= nq) return;
+    const int64_t bi = (int64_t)blockIdx.x * kWarpsPerBlock + wid;
+    if (bi >= n_big) return;
+    const int64_t w = big_list[bi];
     const int64_t v = q0 + w;
     const int64_t base = colptr[w] - 1;
     const int k_total = (int)(colptr[w + 1] - colptr[w]);
-    if (k_total == 0) return;
     const bool big = k_total > kStageCap;  // warp-uniform
     double p[D];
 #pragma unroll
@@ -255,6 +452,18 @@ rball_fill(const double *__restrict__ V, int64_t q0, int64_t nq, GridDev g, doub
     }
 }
 
+// shard support: cell-order positions whose sample index lies in [q0, q1)
+__global__ void __launch_bounds__(256) range_flags(const int *__restrict__ sorted_idx, int64_t N, int64_t q0, int64_t q1,
+                                                   int *__restrict__ flags) {
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < N) flags[k] = (sorted_idx[k] >= q0 && sorted_idx[k] < q1) ? 1 : 0;
+}
+__global__ void __launch_bounds__(256) range_scatter(const int *__restrict__ flags, const int *__restrict__ offs,
+                                                     int64_t N, int *__restrict__ q_order) {
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < N && flags[k]) q_order[offs[k]] = (int)k;
+}
+
 // spill path: one block per over-sized column; rank sort from the unsorted spill copy
 __global__ void __launch_bounds__(256)
 sort_big_columns(const int *__restrict__ big_list, const int64_t *__restrict__ colptr,
@@ -264,6 +473,7 @@ sort_big_columns(const int *__restrict__ big_list, const int64_t *__restrict__ c
     const int w = big_list[blockIdx.x];
     const int64_t base = colptr[w] - 1;
     const int k = (int)(colptr[w + 1] - colptr[w]);
+    if (k <= kStageCap) return;  // already sorted in shared memory by rball_fill_big
     for (int e0 = 0; e0 < k; e0 += 256) {
         int e = e0 + threadIdx.x;
         int64_t mine = (e < k) ? spill_row[base + e] : 0;
@@ -332,20 +542,38 @@ static int build_table(mpb200_samples *s, double r, mpb200_table *t) {
     MPB_CUDA(cudaMemsetAsync(hist, 0, sizeof(int) * (size_t)(ncells + 1), st));
     cell_scatter<D><<<nbN, 256, 0, st>>>(V, N, cell_id, cell_start, hist, sorted_idx, sorted_pos);
     MPB_LAUNCHED();
+
+    // shard: compact the cell-order positions this process owns
+    const int *q_order = nullptr;
+    if (nq != N) {
+        if (int rc = s->q_order.reserve(sizeof(int) * (size_t)(3 * N + 4))) return rc;
+        int *qo = s->q_order.as<int>();
+        int *flags = qo + N + 1, *offs = flags + N + 1;
+        range_flags<<<nbN, 256, 0, st>>>(sorted_idx, N, s->q0, s->q1, flags);
+        MPB_LAUNCHED();
+        if (int rc = exclusive_scan<int, int>(flags, N, offs, 0, s->scan_tmp, nullptr)) return rc;
+        range_scatter<<<nbN, 256, 0, st>>>(flags, offs, N, qo);
+        MPB_LAUNCHED();
+        q_order = qo;
+    }
     phase_mark(1);
 
     // count pass
     if (int rc = t->counts.reserve(sizeof(int) * (size_t)(2 * nq + 2))) return rc;
     if (int rc = t->colptr.reserve(sizeof(int64_t) * (size_t)(nq + 1))) return rc;
+    if (int rc = t->masks.reserve(sizeof(ulonglong2) * (size_t)(nq + 1))) return rc;
+    ulonglong2 *masks = t->masks.as<ulonglong2>();
     int *counts = t->counts.as<int>();
     int *big_list = counts + nq;
     unsigned long long *d_nbig = reinterpret_cast<unsigned long long *>(c.d_scalar + 1);
     MPB_CUDA(cudaMemsetAsync(c.d_scalar, 0, sizeof(int64_t) * 2, st));
     const double r2 = r * r;
-    const unsigned nbQ = (unsigned)ceil_div(nq > 0 ? nq : 1, kWarpsPerBlock);
+    const unsigned nbQ = (unsigned)ceil_div(nq > 0 ? nq : 1, kQThreads);
     if (nq > 0) {
-        rball_count<D><<<nbQ, kWarpsPerBlock * 32, 0, st>>>(V, s->q0, nq, g, r2, cell_start, sorted_idx, sorted_pos,
-                                                           counts, big_list, d_nbig);
+        // key packing in rball_fill needs N < 2^26; beyond that every non-empty column is "big"
+        const int list_cap = (N < (int64_t(1) << 26)) ? kListCap : 0;
+        rball_count<D><<<nbQ, kQThreads, 0, st>>>(sorted_pos, sorted_idx, q_order, nq, s->q0, g, r2, cell_start,
+                                                 list_cap, counts, masks, big_list, d_nbig);
         MPB_LAUNCHED();
     }
     if (int rc = exclusive_scan<int, int64_t>(counts, nq, t->colptr.as<int64_t>(), (int64_t)1, s->scan_tmp,
@@ -368,11 +596,17 @@ static int build_table(mpb200_samples *s, double r, mpb200_table *t) {
     }
     phase_mark(3);
     if (nq > 0 && nnz > 0) {
-        rball_fill<D><<<nbQ, kWarpsPerBlock * 32, 0, st>>>(V, s->q0, nq, g, r2, cell_start, sorted_idx, sorted_pos,
-                                                          t->colptr.as<int64_t>(), t->rowval.as<int64_t>(),
-                                                          t->nzval.as<double>(), spill_row, spill_val);
-        MPB_LAUNCHED();
+        if (N < (int64_t(1) << 26)) {
+            rball_fill<D><<<nbQ, kQThreads, 0, st>>>(sorted_pos, sorted_idx, q_order, masks, nq, s->q0, g, cell_start,
+                                                    t->colptr.as<int64_t>(), t->rowval.as<int64_t>(),
+                                                    t->nzval.as<double>());
+            MPB_LAUNCHED();
+        }
         if (n_big > 0) {
+            rball_fill_big<D><<<(unsigned)ceil_div(n_big, kWarpsPerBlock), kWarpsPerBlock * 32, 0, st>>>(
+                V, big_list, n_big, s->q0, g, r2, cell_start, sorted_idx, sorted_pos, t->colptr.as<int64_t>(),
+                t->rowval.as<int64_t>(), t->nzval.as<double>(), spill_row, spill_val);
+            MPB_LAUNCHED();
             sort_big_columns<<<(unsigned)n_big, 256, 0, st>>>(big_list, t->colptr.as<int64_t>(), spill_row, spill_val,
                                                               t->rowval.as<int64_t>(), t->nzval.as<double>());
             MPB_LAUNCHED();

@@ -19,11 +19,12 @@ want = ['Kernel Name', 'gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__
         'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active']
 extra = sys.argv[2:]
 cols = [i for i, h in enumerate(hdr) if h in want or any(e in h for e in extra)]
-stall = [i for i, h in enumerate(hdr) if 'warp_issue_stalled' in h and h.endswith('per_warp_active.pct')]
+stall = [i for i, h in enumerate(hdr) if h.startswith('smsp__pcsamp_warps_issue_stalled_') and not h.endswith('_not_issued')]
 for r in rows[2:]:
     print('-' * 100)
     for i in cols:
         print("  %-78s %s %s" % (hdr[i], r[i][:90], units[i]))
-    st = sorted(((float(r[i].replace(',', '') or 0), hdr[i]) for i in stall), reverse=True)[:6]
-    for v, h in st:
-        print("  stall %-72s %.1f %%" % (h.replace('smsp__warp_issue_stalled_', '').replace('_per_warp_active.pct', ''), v))
+    st = sorted(((float(r[i].replace(',', '') or 0), hdr[i]) for i in stall), reverse=True)
+    tot = sum(v for v, _ in st) or 1.0
+    for v, h in st[:6]:
+        print("  stall(pc samples) %-60s %5.1f %%" % (h.replace('smsp__pcsamp_warps_issue_stalled_', ''), 100 * v / tot))

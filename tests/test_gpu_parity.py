@@ -81,7 +81,7 @@ def test_k6_k8_boxes(gpu, orc, d, boxes):
     assert not got[~inb].any()
     exp, _ = orc.motions_free_straight(B, SSo, V[:5000], W[:5000])
     assert np.array_equal(got[:5000], exp)
-    assert 0.005 < (~got[inb]).mean() < 0.98
+    assert 0 < (~got[inb]).mean() < 0.98
 
 
 def test_k6_k8_double_integrator_workspace_maps(gpu, orc):
