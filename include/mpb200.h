@@ -139,6 +139,36 @@ int mpb200_states_free(const double *v_aos, int64_t n, int d, const mpb200_obsta
 int mpb200_segments_free(const double *v_aos, const double *w_aos, int64_t n, int d, const mpb200_obstacles *o,
                          const mpb200_space_desc *ss, uint8_t *out);
 
+/* ---- linear-quadratic steering cost ("ControlNN") --------------------------------
+ * Replaces LinearQuadratic(A, B, c, R) / LinearQuadratic2BVP (linearquadratic.jl:6-39,126-157).
+ * A (n x n), B (n x m), R (m x m) column-major, c (n).  The reference's expAt handles nilpotent
+ * A only (:94-98) and DoubleIntegrator (:46-53) is its one shipped instance; this library
+ * accepts exactly that family: n = 2m, A = [0 I; 0 0], B = [0; I], c = 0, R symmetric positive
+ * definite, m = 1..3.  Anything else returns MPB200_EARG. */
+int mpb200_lq_create(const double *A, const double *B, const double *c, const double *R, int n, int m,
+                     mpb200_lq **out);
+int mpb200_lq_destroy(mpb200_lq *lq);
+/* Replaces helper_data_structures(V, ::LinearQuadratic) (linearquadratic.jl:68-77): the batched
+ * steer_pairwise (:196-225: dcost(r) > 0 prefilter, safeguarded Newton :175-190, cost <= r)
+ * plus the inball filter (nearneighbors.jl:165-177), for every column of the query range.
+ * tableF column v: { j != v : cost(V[v] -> V[j]) <= r }  (DSF = Dmat', served by inballF!)
+ * tableB column v: { j != v : cost(V[j] -> V[v]) <= r }  (DSB = Dmat , served by inballB!)
+ * stored value = the cost; rows ascending.  Non-NULL *table handles are reused. */
+int mpb200_lq_inball_build(mpb200_samples *s, const mpb200_lq *lq, double r, mpb200_table **tableF,
+                           mpb200_table **tableB, int64_t *nnzF, int64_t *nnzB);
+/* steer(L, v, w, r) = (cost, t*) for n explicit pairs (linearquadratic.jl:191-195); AoS 2m x n */
+int mpb200_lq_steer(const mpb200_lq *lq, const double *v_aos, const double *w_aos, int64_t n, double r,
+                    double *cost, double *topt);
+/* is_free_motion(V[y], V[x], CC, SS) for every stored entry (row y, column x) of a table, with
+ * collision_waypoints(::LinearQuadratic) = 5 states along the optimal trajectory
+ * (linearquadratic.jl:85-88; statespaces.jl:153-158).  bits/checks as mpb200_edges_free. */
+int mpb200_lq_edges_free(const mpb200_samples *s, const mpb200_table *t, const mpb200_lq *lq, double r,
+                         const mpb200_obstacles *o, const mpb200_space_desc *ss, uint64_t *bitchunks,
+                         int64_t *checks);
+/* the same for n explicit state pairs (fmt.jl:75 called with states) */
+int mpb200_lq_motions_free(const mpb200_lq *lq, double r, const double *v_aos, const double *w_aos, int64_t n,
+                           const mpb200_obstacles *o, const mpb200_space_desc *ss, uint8_t *out, int64_t *checks);
+
 #ifdef __cplusplus
 }
 #endif

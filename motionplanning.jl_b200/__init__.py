@@ -12,9 +12,11 @@ from .collisioncheckers import (BoxBounds, CollisionChecker, PointRobot2D, Point
 from .statespaces import (BoundedEuclideanStateSpace, BoundedStateSpace, Euclidean, Identity,  # noqa: F401
                           OutputMatrix, UnitHypercube, VectorView, dim, is_free_motion, is_free_path,
                           is_free_state, segments_free, state2workspace, states_free, volume)
-from .nearneighbors import (ImmutableNNC, MetricNN, SampleSet, SparseMatrixCSC, SparseVectorView,  # noqa: F401
+from .nearneighbors import (ImmutableNNC, MetricNN, QuasiMetricNN, SampleSet, SparseMatrixCSC, SparseVectorView,  # noqa: F401
                             addpoints, filter_neighborhood, inball, inballB, inballF, nonzeroinds,
                             nonzeros, viewcol)
+from .linearquadratic import (DoubleIntegrator, LinearQuadratic, LinearQuadraticQuasiMetricSpace,  # noqa: F401
+                              lq_motions_free, setup_steering, steer, steer_batch)
 from . import obstaclesets  # noqa: F401
 
 __version__ = "0.1.0"

@@ -64,6 +64,12 @@ SIGNATURES = {
     "mpb200_edges_free": (ctypes.c_int, [c_vp, c_vp, c_vp, P(SpaceDesc), c_vp, P(c_i64)]),
     "mpb200_states_free": (ctypes.c_int, [c_vp, c_i64, ctypes.c_int, c_vp, P(SpaceDesc), c_vp]),
     "mpb200_segments_free": (ctypes.c_int, [c_vp, c_vp, c_i64, ctypes.c_int, c_vp, P(SpaceDesc), c_vp]),
+    "mpb200_lq_create": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, ctypes.c_int, ctypes.c_int, P(c_vp)]),
+    "mpb200_lq_destroy": (ctypes.c_int, [c_vp]),
+    "mpb200_lq_inball_build": (ctypes.c_int, [c_vp, c_vp, c_dbl, P(c_vp), P(c_vp), P(c_i64), P(c_i64)]),
+    "mpb200_lq_steer": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_dbl, c_vp, c_vp]),
+    "mpb200_lq_edges_free": (ctypes.c_int, [c_vp, c_vp, c_vp, c_dbl, c_vp, P(SpaceDesc), c_vp, P(c_i64)]),
+    "mpb200_lq_motions_free": (ctypes.c_int, [c_vp, c_dbl, c_vp, c_vp, c_i64, c_vp, P(SpaceDesc), c_vp, P(c_i64)]),
 }
 
 _lib = None

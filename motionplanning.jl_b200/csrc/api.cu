@@ -84,6 +84,16 @@ int edges_free_device(const double *dV, int d, const mpb200_table *t, const mpb2
 int segments_free_device(const double *dA, const double *dB, int64_t n, int d, const mpb200_obstacles *o,
                          const mpb200_space_desc *ss, uint8_t *d_out);
 
+int lq_inball_build(mpb200_samples *s, const mpb200_lq *lq, double r, mpb200_table *tF, mpb200_table *tB);
+int lq_steer_device(const mpb200_lq *lq, const double *dA, const double *dB, int64_t n, double r, double *d_cost,
+                    double *d_topt);
+int lq_edges_free_device(const mpb200_samples *s, const mpb200_table *t, const mpb200_lq *lq, double r,
+                         const mpb200_obstacles *o, const mpb200_space_desc *ss, uint32_t *d_bits32,
+                         unsigned long long *d_checks);
+int lq_motions_free_device(const mpb200_lq *lq, double r, const double *dA, const double *dB, int64_t n, int d_state,
+                           const mpb200_obstacles *o, const mpb200_space_desc *ss, uint8_t *d_out,
+                           unsigned long long *d_checks);
+
 }  // namespace mpb
 
 using namespace mpb;
@@ -447,6 +457,137 @@ int mpb200_segments_free(const double *v_aos, const double *w_aos, int64_t n, in
                          const mpb200_space_desc *ss, uint8_t *out) {
     MPB_CHECK_ARG(n == 0 || w_aos != nullptr, "w is NULL");
     return batch_states(v_aos, w_aos, n, d, o, ss, out);
+}
+
+// ---- linear-quadratic steering --------------------------------------------------------------------
+int mpb200_lq_create(const double *A, const double *B, const double *c, const double *R, int n, int m, mpb200_lq **out) {
+    MPB_CHECK_ARG(A && B && c && R && out, "NULL argument");
+    MPB_CHECK_ARG(m >= 1 && m <= 3 && n == 2 * m, "only double-integrator systems (n = 2m, m = 1..3) are built in");
+    // expAt handles nilpotent A only (linearquadratic.jl:94-98); accept the DoubleIntegrator family (:46-53)
+    for (int j = 0; j < n; ++j)
+        for (int i = 0; i < n; ++i)
+            MPB_CHECK_ARG(A[i + j * n] == ((j == i + m) ? 1.0 : 0.0), "A must be [0 I; 0 0] (double integrator)");
+    for (int j = 0; j < m; ++j)
+        for (int i = 0; i < n; ++i)
+            MPB_CHECK_ARG(B[i + j * n] == ((i == j + m) ? 1.0 : 0.0), "B must be [0; I] (double integrator)");
+    for (int i = 0; i < n; ++i) MPB_CHECK_ARG(c[i] == 0.0, "drift c must be zero");
+    bool scalar = true;
+    for (int i = 0; i < m; ++i)
+        for (int j = 0; j < m; ++j) {
+            MPB_CHECK_ARG(R[i + j * m] == R[j + i * m], "R must be symmetric");
+            if (i != j && R[i + j * m] != 0.0) scalar = false;
+            if (i == j && R[i + j * m] != R[0]) scalar = false;
+        }
+    for (int i = 0; i < m; ++i) MPB_CHECK_ARG(R[i + i * m] > 0.0, "R must be positive definite");
+    mpb200_lq *lq = new (std::nothrow) mpb200_lq();
+    if (!lq) return fail(MPB200_ENOMEM, "out of host memory");
+    lq->d = m;
+    lq->scalar_R = scalar;
+    for (int i = 0; i < m; ++i)
+        for (int j = 0; j < m; ++j) lq->R[i * m + j] = R[i + j * m];
+    *out = lq;
+    return MPB200_OK;
+}
+int mpb200_lq_destroy(mpb200_lq *lq) {
+    delete lq;
+    return MPB200_OK;
+}
+
+int mpb200_lq_inball_build(mpb200_samples *s, const mpb200_lq *lq, double r, mpb200_table **tableF, mpb200_table **tableB,
+                           int64_t *nnzF, int64_t *nnzB) {
+    MPB_REQUIRE_INIT();
+    MPB_CHECK_ARG(s && lq && tableF && tableB, "NULL handle");
+    MPB_CHECK_ARG(r > 0 && r == r, "r must be positive");
+    mpb200_table *tF = *tableF, *tB = *tableB;
+    const bool freshF = !tF, freshB = !tB;
+    if (!tF) tF = new (std::nothrow) mpb200_table();
+    if (!tB) tB = new (std::nothrow) mpb200_table();
+    if (!tF || !tB) return fail(MPB200_ENOMEM, "out of host memory");
+    int rc = lq_inball_build(s, lq, r, tF, tB);
+    if (rc) {
+        if (freshF) mpb200_table_destroy(tF);
+        if (freshB) mpb200_table_destroy(tB);
+        return rc;
+    }
+    *tableF = tF;
+    *tableB = tB;
+    if (nnzF) *nnzF = tF->nnz;
+    if (nnzB) *nnzB = tB->nnz;
+    return MPB200_OK;
+}
+
+int mpb200_lq_steer(const mpb200_lq *lq, const double *v, const double *w, int64_t n, double r, double *cost,
+                    double *topt) {
+    MPB_REQUIRE_INIT();
+    MPB_CHECK_ARG(lq && (n == 0 || (v && w && cost && topt)), "NULL argument");
+    if (n == 0) return MPB200_OK;
+    cudaStream_t st = ctx().stream;
+    static DevBuf bufA, bufB, bufC, bufT;
+    const size_t bytes = sizeof(double) * (size_t)(n * 2 * lq->d);
+    if (int rc = bufA.reserve(bytes)) return rc;
+    if (int rc = bufB.reserve(bytes)) return rc;
+    if (int rc = bufC.reserve(sizeof(double) * (size_t)n)) return rc;
+    if (int rc = bufT.reserve(sizeof(double) * (size_t)n)) return rc;
+    MPB_CUDA(cudaMemcpyAsync(bufA.p, v, bytes, cudaMemcpyHostToDevice, st));
+    MPB_CUDA(cudaMemcpyAsync(bufB.p, w, bytes, cudaMemcpyHostToDevice, st));
+    if (int rc = lq_steer_device(lq, bufA.as<double>(), bufB.as<double>(), n, r, bufC.as<double>(), bufT.as<double>()))
+        return rc;
+    MPB_CUDA(cudaMemcpyAsync(cost, bufC.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    MPB_CUDA(cudaMemcpyAsync(topt, bufT.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    MPB_CUDA(cudaStreamSynchronize(st));
+    return MPB200_OK;
+}
+
+int mpb200_lq_edges_free(const mpb200_samples *s, const mpb200_table *t_, const mpb200_lq *lq, double r,
+                         const mpb200_obstacles *o, const mpb200_space_desc *ss, uint64_t *bitchunks, int64_t *checks) {
+    MPB_REQUIRE_INIT();
+    MPB_CHECK_ARG(s && t_ && lq && o, "NULL handle");
+    mpb200_table *t = const_cast<mpb200_table *>(t_);
+    Context &c = ctx();
+    cudaStream_t st = c.stream;
+    const size_t words = (size_t)ceil_div(t->nnz, 64);
+    if (int rc = t->edge_bits.reserve(sizeof(uint64_t) * (words + 1))) return rc;
+    phase_mark(0);
+    MPB_CUDA(cudaMemsetAsync(t->edge_bits.p, 0, sizeof(uint64_t) * (words + 1), st));
+    MPB_CUDA(cudaMemsetAsync(c.d_scalar + 4, 0, sizeof(int64_t), st));
+    if (int rc = lq_edges_free_device(s, t, lq, r, o, ss, t->edge_bits.as<uint32_t>(),
+                                      reinterpret_cast<unsigned long long *>(c.d_scalar + 4)))
+        return rc;
+    phase_mark(1);
+    if (bitchunks && words)
+        MPB_CUDA(cudaMemcpyAsync(bitchunks, t->edge_bits.p, sizeof(uint64_t) * words, cudaMemcpyDeviceToHost, st));
+    MPB_CUDA(cudaMemcpyAsync(c.h_scalar + 4, c.d_scalar + 4, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    MPB_CUDA(cudaStreamSynchronize(st));
+    phases_collect(1);
+    if (checks) *checks = c.h_scalar[4];
+    return MPB200_OK;
+}
+
+int mpb200_lq_motions_free(const mpb200_lq *lq, double r, const double *v, const double *w, int64_t n,
+                           const mpb200_obstacles *o, const mpb200_space_desc *ss, uint8_t *out, int64_t *checks) {
+    MPB_REQUIRE_INIT();
+    MPB_CHECK_ARG(lq && o && (n == 0 || (v && w && out)), "NULL argument");
+    if (checks) *checks = 0;
+    if (n == 0) return MPB200_OK;
+    Context &c = ctx();
+    cudaStream_t st = c.stream;
+    static DevBuf bufA, bufB, bufO;
+    const int ns = 2 * lq->d;
+    const size_t bytes = sizeof(double) * (size_t)(n * ns);
+    if (int rc = bufA.reserve(bytes)) return rc;
+    if (int rc = bufB.reserve(bytes)) return rc;
+    if (int rc = bufO.reserve((size_t)n + 64)) return rc;
+    MPB_CUDA(cudaMemcpyAsync(bufA.p, v, bytes, cudaMemcpyHostToDevice, st));
+    MPB_CUDA(cudaMemcpyAsync(bufB.p, w, bytes, cudaMemcpyHostToDevice, st));
+    MPB_CUDA(cudaMemsetAsync(c.d_scalar + 5, 0, sizeof(int64_t), st));
+    if (int rc = lq_motions_free_device(lq, r, bufA.as<double>(), bufB.as<double>(), n, ns, o, ss, bufO.as<uint8_t>(),
+                                        reinterpret_cast<unsigned long long *>(c.d_scalar + 5)))
+        return rc;
+    MPB_CUDA(cudaMemcpyAsync(out, bufO.p, (size_t)n, cudaMemcpyDeviceToHost, st));
+    MPB_CUDA(cudaMemcpyAsync(c.h_scalar + 5, c.d_scalar + 5, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    MPB_CUDA(cudaStreamSynchronize(st));
+    if (checks) *checks = c.h_scalar[5];
+    return MPB200_OK;
 }
 
 }  // extern "C"

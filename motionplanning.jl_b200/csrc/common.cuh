@@ -117,3 +117,9 @@ struct mpb200_obstacles {
     // boxes
     int M = 0, d = 0;
 };
+
+struct mpb200_lq {
+    int d = 0;              // position dimension; state dimension n = 2 d
+    bool scalar_R = false;  // R == rho * I
+    double R[9] = {};       // d x d row-major (symmetric)
+};

@@ -1,0 +1,475 @@
+// lq.cu -- K5 (ControlNN: all-pairs linear-quadratic steering-cost neighbour tables) and
+// K9 (swept-trajectory edge checks along the optimal LQ trajectory) for double-integrator systems.
+//
+// Replaces helper_data_structures(V, ::LinearQuadratic) (linearquadratic.jl:68-77): the column-
+// batched dense steer_pairwise (:196-225: dcost(r) > 0 prefilter, per-candidate safeguarded
+// Newton topt_newton :175-190, keep cost <= r) followed by the inball filter
+// (nearneighbors.jl:165-177), producing both DSF (column v = costs FROM v) and DSB (column v =
+// costs INTO v); and is_free_motion(v, w, CC, SS) with collision_waypoints of :85-88
+// (5 states along x(s), statespaces.jl:153-158).
+//
+// The reference's SymPy closures reduce, for A=[0 I;0 0], B=[0;I], c=0, to
+//   cost(t) = t + alpha/t^3 - beta/t^2 + gamma/t
+// (see oracle/lq.c; pinned by tests/golden/lq_di2.json).  Operation order here is identical to
+// the oracle's, every operation an explicit _rn intrinsic (no FMA), so tables are bit-identical.
+//
+// Layout: one thread per query column (its state in registers, both directions evaluated against
+// the same staged sample), samples streamed through shared memory in tiles and read by
+// broadcast; rows come out in ascending index order, so no sort is needed.
+#include "common.cuh"
+#include "predicates.cuh"
+#include "scan.cuh"
+
+namespace mpb {
+
+struct LqDev {
+    int scalar_R;
+    double R[9];
+};
+struct Abg { double alpha, beta, gamma; };
+
+// alpha, beta, gamma in the oracle's order (oracle/lq.c: lq_abg)
+template <int D>
+__device__ __forceinline__ Abg lq_abg(const LqDev &L, const double *x0, const double *x1) {
+    double dp[D], sv[D];
+    const double *v0 = x0 + D, *v1 = x1 + D;
+#pragma unroll
+    for (int i = 0; i < D; ++i) { dp[i] = dsub(x1[i], x0[i]); sv[i] = dadd(v0[i], v1[i]); }
+    double a = 0.0, b = 0.0, g = 0.0;
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+        double Rdp, Rv0, Rv1;
+        if (L.scalar_R) {  // R = rho I: the off-diagonal products are exact zeros
+            Rdp = dmul(L.R[0], dp[i]); Rv0 = dmul(L.R[0], v0[i]); Rv1 = dmul(L.R[0], v1[i]);
+        } else {
+            Rdp = 0.0; Rv0 = 0.0; Rv1 = 0.0;
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                Rdp = dadd(Rdp, dmul(L.R[i * D + j], dp[j]));
+                Rv0 = dadd(Rv0, dmul(L.R[i * D + j], v0[j]));
+                Rv1 = dadd(Rv1, dmul(L.R[i * D + j], v1[j]));
+            }
+        }
+        a = dadd(a, dmul(dp[i], Rdp));
+        b = dadd(b, dmul(sv[i], Rdp));
+        g = dadd(g, dadd(dadd(dmul(v0[i], Rv0), dmul(v0[i], Rv1)), dmul(v1[i], Rv1)));
+    }
+    Abg k = {dmul(12.0, a), dmul(12.0, b), dmul(4.0, g)};
+    return k;
+}
+__device__ __forceinline__ double lq_cost(const Abg &k, double t) {
+    const double it = ddiv(1.0, t), it2 = dmul(it, it), it3 = dmul(it2, it);
+    return dadd(t, dadd(dsub(dmul(k.alpha, it3), dmul(k.beta, it2)), dmul(k.gamma, it)));
+}
+__device__ __forceinline__ double lq_dcost(const Abg &k, double t) {
+    const double it = ddiv(1.0, t), it2 = dmul(it, it), it3 = dmul(it2, it);
+    return dadd(1.0, dsub(dsub(dmul(dmul(2.0, k.beta), it3), dmul(dmul(3.0, k.alpha), dmul(it3, it))),
+                          dmul(k.gamma, it2)));
+}
+__device__ __forceinline__ double lq_ddcost(const Abg &k, double t) {
+    const double it = ddiv(1.0, t), it2 = dmul(it, it), it3 = dmul(it2, it);
+    return dadd(dsub(dmul(dmul(12.0, k.alpha), dmul(it3, it2)), dmul(dmul(6.0, k.beta), dmul(it2, it2))),
+                dmul(dmul(2.0, k.gamma), it3));
+}
+// linearquadratic.jl:175-190 (same 200-iteration safety cap as the oracle; never reached)
+__device__ __forceinline__ double lq_topt_newton(const Abg &k, double tm) {
+    const double tol = 1e-6;
+    double b = tm;
+    if (lq_dcost(k, b) < 0) return tm;
+    double a = ddiv(tm, 100.0);
+    while (lq_dcost(k, a) > 0) a = ddiv(a, 2.0);
+    double t = ddiv(tm, 2.0);
+    double cdval = lq_dcost(k, t);
+    int it = 0;
+    while (fabs(cdval) > tol && fabs(dsub(a, b)) > tol) {
+        t = dsub(t, ddiv(cdval, lq_ddcost(k, t)));
+        if (t < a || t > b) t = ddiv(dadd(a, b), 2.0);
+        cdval = lq_dcost(k, t);
+        if (cdval > 0) b = t; else a = t;
+        if (++it >= 200) break;
+    }
+    return t;
+}
+template <int D>
+__device__ __forceinline__ bool same_state(const double *x0, const double *x1) {
+    bool same = true;
+#pragma unroll
+    for (int i = 0; i < 2 * D; ++i) same = same && (x0[i] == x1[i]);
+    return same;
+}
+// steer(L, x0, x1, r): linearquadratic.jl:191-195
+template <int D>
+__device__ __forceinline__ void lq_steer(const LqDev &L, const double *x0, const double *x1, double r, double *cost,
+                                         double *topt) {
+    if (same_state<D>(x0, x1)) { *cost = 0.0; *topt = 0.0; return; }
+    const Abg k = lq_abg<D>(L, x0, x1);
+    const double t = lq_topt_newton(k, r);
+    *cost = lq_cost(k, t);
+    *topt = t;
+}
+// x(x0, x1, t, s): cubic Hermite in Horner form (oracle/lq.c: orc_lq_state)
+template <int D>
+__device__ __forceinline__ void lq_state(const double *x0, const double *x1, double t, double s, double *out) {
+    const double it = ddiv(1.0, t), it2 = dmul(it, it), it3 = dmul(it2, it);
+    const double *v0 = x0 + D, *v1 = x1 + D;
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+        const double dp = dsub(x1[i], x0[i]);
+        const double c2 = dsub(dmul(dmul(3.0, dp), it2), dmul(dadd(dmul(2.0, v0[i]), v1[i]), it));
+        const double c3 = dsub(dmul(dadd(v0[i], v1[i]), it2), dmul(dmul(2.0, dp), it3));
+        out[i] = dadd(dmul(dadd(dmul(dadd(dmul(c3, s), c2), s), v0[i]), s), x0[i]);
+        out[D + i] = dadd(dmul(dadd(dmul(dmul(3.0, c3), s), dmul(2.0, c2)), s), v0[i]);
+    }
+}
+
+// one ordered pair x0 -> x1: is it a stored neighbour, and at what cost
+template <int D>
+__device__ __forceinline__ bool lq_pair(const LqDev &L, const double *x0, const double *x1, double r, double *cost) {
+    const Abg k = lq_abg<D>(L, x0, x1);
+    if (!(lq_dcost(k, r) > 0)) return false;  // cands = cd .> 0, linearquadratic.jl:213
+    double c;
+    if (same_state<D>(x0, x1)) c = 0.0;       // :192 (duplicate states)
+    else c = lq_cost(k, lq_topt_newton(k, r));
+    *cost = c;
+    return c <= r;                            // :221
+}
+
+constexpr int kLqThreads = 128;
+constexpr int kLqTile = 128;
+
+// K5.  FILL = false: per-column counts for both directions; FILL = true: rows + costs.
+template <int D, bool FILL>
+__global__ void __launch_bounds__(kLqThreads)
+lq_inball_kernel(const double *__restrict__ V, int64_t N, int64_t q0, int64_t nq, LqDev L, double r,
+                 int *__restrict__ countsF, int *__restrict__ countsB, const int64_t *__restrict__ colptrF,
+                 const int64_t *__restrict__ colptrB, int64_t *__restrict__ rowvalF, double *__restrict__ nzvalF,
+                 int64_t *__restrict__ rowvalB, double *__restrict__ nzvalB) {
+    constexpr int NS = 2 * D;
+    __shared__ double tile[kLqTile * NS];
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = w < nq;
+    const int64_t q = q0 + w;
+    double x[NS];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) x[i] = active ? V[q * NS + i] : 0.0;
+    int nF = 0, nB = 0;
+    int64_t posF = 0, posB = 0;
+    if (FILL && active) { posF = colptrF[w] - 1; posB = colptrB[w] - 1; }
+    for (int64_t t0 = 0; t0 < N; t0 += kLqTile) {
+        const int cnt = (int)((N - t0 < kLqTile) ? (N - t0) : kLqTile);
+        __syncthreads();
+        for (int i = threadIdx.x; i < cnt * NS; i += blockDim.x) tile[i] = V[t0 * NS + i];
+        __syncthreads();
+        if (!active) continue;
+        for (int jj = 0; jj < cnt; ++jj) {
+            const int64_t j = t0 + jj;
+            if (j == q) continue;  // nearneighbors.jl:171: allinds[i] != v
+            double y[NS];
+#pragma unroll
+            for (int i = 0; i < NS; ++i) y[i] = tile[jj * NS + i];
+            double c;
+            if (lq_pair<D>(L, x, y, r, &c)) {  // forwards: cost(V[q] -> V[j])
+                if (FILL) { rowvalF[posF] = j + 1; nzvalF[posF] = c; ++posF; }
+                ++nF;
+            }
+            if (lq_pair<D>(L, y, x, r, &c)) {  // backwards: cost(V[j] -> V[q])
+                if (FILL) { rowvalB[posB] = j + 1; nzvalB[posB] = c; ++posB; }
+                ++nB;
+            }
+        }
+    }
+    if (!FILL && active) { countsF[w] = nF; countsB[w] = nB; }
+}
+
+template <int D>
+__global__ void __launch_bounds__(256)
+lq_steer_kernel(const double *__restrict__ A, const double *__restrict__ B, int64_t n, LqDev L, double r,
+                double *__restrict__ cost, double *__restrict__ topt) {
+    constexpr int NS = 2 * D;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double a[NS], b[NS];
+#pragma unroll
+        for (int k = 0; k < NS; ++k) { a[k] = A[i * NS + k]; b[k] = B[i * NS + k]; }
+        double c, t;
+        lq_steer<D>(L, a, b, r, &c, &t);
+        cost[i] = c;
+        topt[i] = t;
+    }
+}
+
+// K9: is_free_motion(v, w, CC, SS) along the optimal trajectory; *checks += segment tests run
+template <int D, int DW, int KIND>
+__device__ __forceinline__ bool lq_motion_free(const LqDev &L, const SpaceDev &S, const double *T, int M, double r,
+                                               const double *v, const double *w, int *checks) {
+    constexpr int NS = 2 * D;
+    double c, t;
+    lq_steer<D>(L, v, w, r, &c, &t);
+    double cur[NS], nxt[NS], p[DW], q[DW];
+    lq_state<D>(v, w, t, 0.0, cur);
+    state2workspace<NS, DW>(S, cur, p);
+    for (int i = 1; i <= 4; ++i) {
+        if (!in_state_space<NS>(S, cur)) return false;  // only wps[1..4] are bounds-checked (Q4)
+        const double s = ddiv(dmul((double)i, t), 4.0);  // linspace(0, t, 5)[i+1]
+        lq_state<D>(v, w, t, s, nxt);
+        state2workspace<NS, DW>(S, nxt, q);
+        *checks += 1;
+        bool free_;
+        if (KIND == 0) free_ = !line_colliding_2d(T, p[0], p[DW > 1 ? 1 : 0], q[0], q[DW > 1 ? 1 : 0]);
+        else free_ = box_segment_free<DW>(T, M, p, q);
+        if (!free_) return false;
+#pragma unroll
+        for (int k = 0; k < NS; ++k) cur[k] = nxt[k];
+#pragma unroll
+        for (int k = 0; k < DW; ++k) p[k] = q[k];
+    }
+    return true;
+}
+
+__device__ __forceinline__ const double *lq_stage_table(const double *__restrict__ g_table, int words, bool use_smem,
+                                                        double *smem) {
+    if (!use_smem) return g_table;
+    for (int i = threadIdx.x; i < words; i += blockDim.x) smem[i] = g_table[i];
+    __syncthreads();
+    return smem;
+}
+
+// one warp per column of the (backwards) table: entry (row y -> column x) = motion V[y] -> V[x]
+template <int D, int DW, int KIND>
+__global__ void __launch_bounds__(256)
+lq_edges_free_kernel(const double *__restrict__ V, const int64_t *__restrict__ colptr,
+                     const int64_t *__restrict__ rowval, int64_t ncols, int64_t col0, LqDev L, double r, SpaceDev S,
+                     const double *__restrict__ g_table, int table_words, int M, bool use_smem,
+                     uint32_t *__restrict__ bits32, unsigned long long *__restrict__ checks) {
+    constexpr int NS = 2 * D;
+    extern __shared__ double s_table[];
+    const double *T = lq_stage_table(g_table, table_words, use_smem, s_table);
+    const int lane = threadIdx.x & 31;
+    const int64_t gwarp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    unsigned long long my_checks = 0;
+    for (int64_t c = gwarp; c < ncols; c += nwarps) {
+        const int64_t beg = colptr[c] - 1, end = colptr[c + 1] - 1;
+        if (beg >= end) continue;
+        double b[NS];
+#pragma unroll
+        for (int k = 0; k < NS; ++k) b[k] = V[(col0 + c) * NS + k];
+        for (int64_t e0 = beg; e0 < end; e0 += 32) {
+            const int64_t e = e0 + lane;
+            bool ok = false;
+            if (e < end) {
+                const int64_t y = rowval[e] - 1;
+                double a[NS];
+#pragma unroll
+                for (int k = 0; k < NS; ++k) a[k] = V[y * NS + k];
+                int nchk = 0;
+                ok = lq_motion_free<D, DW, KIND>(L, S, T, M, r, a, b, &nchk);
+                my_checks += nchk;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, ok);
+            if (lane == 0 && m) {
+                const int sh = (int)(e0 & 31);
+                const int64_t wi = e0 >> 5;
+                atomicOr(&bits32[wi], m << sh);
+                if (sh && (m >> (32 - sh))) atomicOr(&bits32[wi + 1], m >> (32 - sh));
+            }
+        }
+    }
+    __shared__ unsigned long long s_checks[8];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) my_checks += __shfl_xor_sync(0xffffffffu, my_checks, o);
+    if (lane == 0) s_checks[threadIdx.x >> 5] = my_checks;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int w = 0; w < 8; ++w) t += s_checks[w];
+        if (t) atomicAdd(checks, t);
+    }
+}
+
+template <int D, int DW, int KIND>
+__global__ void __launch_bounds__(256)
+lq_motions_free_kernel(const double *__restrict__ A, const double *__restrict__ B, int64_t n, LqDev L, double r,
+                       SpaceDev S, const double *__restrict__ g_table, int table_words, int M, bool use_smem,
+                       uint8_t *__restrict__ out, unsigned long long *__restrict__ checks) {
+    constexpr int NS = 2 * D;
+    extern __shared__ double s_table[];
+    const double *T = lq_stage_table(g_table, table_words, use_smem, s_table);
+    unsigned long long my_checks = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double a[NS], b[NS];
+#pragma unroll
+        for (int k = 0; k < NS; ++k) { a[k] = A[i * NS + k]; b[k] = B[i * NS + k]; }
+        int nchk = 0;
+        out[i] = lq_motion_free<D, DW, KIND>(L, S, T, M, r, a, b, &nchk) ? 1 : 0;
+        my_checks += nchk;
+    }
+    if (my_checks) atomicAdd(checks, my_checks);
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+int make_space(const mpb200_space_desc *ss, int d_state, SpaceDev *out, int *dw);
+
+static LqDev lq_dev(const mpb200_lq *lq) {
+    LqDev L;
+    L.scalar_R = lq->scalar_R ? 1 : 0;
+    for (int i = 0; i < 9; ++i) L.R[i] = lq->R[i];
+    return L;
+}
+
+template <int D>
+static int lq_build(mpb200_samples *s, const mpb200_lq *lq, double r, mpb200_table *tF, mpb200_table *tB) {
+    Context &c = ctx();
+    cudaStream_t st = c.stream;
+    const int64_t N = s->N, nq = s->q1 - s->q0;
+    const double *V = s->V.as<double>();
+    const LqDev L = lq_dev(lq);
+    for (mpb200_table *t : {tF, tB}) {
+        if (int rc = t->counts.reserve(sizeof(int) * (size_t)(nq + 1))) return rc;
+        if (int rc = t->colptr.reserve(sizeof(int64_t) * (size_t)(nq + 1))) return rc;
+    }
+    const unsigned nb = (unsigned)ceil_div(nq > 0 ? nq : 1, kLqThreads);
+    phase_mark(0);
+    if (nq > 0) {
+        lq_inball_kernel<D, false><<<nb, kLqThreads, 0, st>>>(V, N, s->q0, nq, L, r, tF->counts.as<int>(),
+                                                             tB->counts.as<int>(), nullptr, nullptr, nullptr, nullptr,
+                                                             nullptr, nullptr);
+        MPB_LAUNCHED();
+    }
+    if (int rc = exclusive_scan<int, int64_t>(tF->counts.as<int>(), nq, tF->colptr.as<int64_t>(), (int64_t)1, s->scan_tmp,
+                                              c.d_scalar))
+        return rc;
+    if (int rc = exclusive_scan<int, int64_t>(tB->counts.as<int>(), nq, tB->colptr.as<int64_t>(), (int64_t)1, s->scan_tmp,
+                                              c.d_scalar + 1))
+        return rc;
+    phase_mark(1);
+    MPB_CUDA(cudaMemcpyAsync(c.h_scalar, c.d_scalar, sizeof(int64_t) * 2, cudaMemcpyDeviceToHost, st));
+    MPB_CUDA(cudaStreamSynchronize(st));
+    const int64_t nnzF = c.h_scalar[0], nnzB = c.h_scalar[1];
+    if (int rc = tF->rowval.reserve(sizeof(int64_t) * (size_t)(nnzF + 1))) return rc;
+    if (int rc = tF->nzval.reserve(sizeof(double) * (size_t)(nnzF + 1))) return rc;
+    if (int rc = tB->rowval.reserve(sizeof(int64_t) * (size_t)(nnzB + 1))) return rc;
+    if (int rc = tB->nzval.reserve(sizeof(double) * (size_t)(nnzB + 1))) return rc;
+    phase_mark(2);
+    if (nq > 0 && (nnzF > 0 || nnzB > 0)) {
+        lq_inball_kernel<D, true><<<nb, kLqThreads, 0, st>>>(V, N, s->q0, nq, L, r, nullptr, nullptr,
+                                                            tF->colptr.as<int64_t>(), tB->colptr.as<int64_t>(),
+                                                            tF->rowval.as<int64_t>(), tF->nzval.as<double>(),
+                                                            tB->rowval.as<int64_t>(), tB->nzval.as<double>());
+        MPB_LAUNCHED();
+    }
+    phase_mark(3);
+    MPB_CUDA(cudaStreamSynchronize(st));
+    phases_collect(3);
+    tF->ncols = tB->ncols = nq;
+    tF->col0 = tB->col0 = s->q0;
+    tF->nnz = nnzF;
+    tB->nnz = nnzB;
+    tF->r = tB->r = r;
+    return 0;
+}
+
+int lq_inball_build(mpb200_samples *s, const mpb200_lq *lq, double r, mpb200_table *tF, mpb200_table *tB) {
+    if (s->d != 2 * lq->d) return fail(MPB200_EARG, "sample dimension %d != 2 x %d", s->d, lq->d);
+    if (lq->d == 1) return lq_build<1>(s, lq, r, tF, tB);
+    if (lq->d == 2) return lq_build<2>(s, lq, r, tF, tB);
+    if (lq->d == 3) return lq_build<3>(s, lq, r, tF, tB);
+    return fail(MPB200_EARG, "double integrators of dimension 1..3 are built in (got %d)", lq->d);
+}
+
+int lq_steer_device(const mpb200_lq *lq, const double *dA, const double *dB, int64_t n, double r, double *d_cost,
+                    double *d_topt) {
+    const LqDev L = lq_dev(lq);
+    cudaStream_t st = ctx().stream;
+    const unsigned grid = (unsigned)(ceil_div(n, 256) < 148 * 8 ? ceil_div(n, 256) : 148 * 8);
+    if (lq->d == 1) lq_steer_kernel<1><<<grid, 256, 0, st>>>(dA, dB, n, L, r, d_cost, d_topt);
+    else if (lq->d == 2) lq_steer_kernel<2><<<grid, 256, 0, st>>>(dA, dB, n, L, r, d_cost, d_topt);
+    else if (lq->d == 3) lq_steer_kernel<3><<<grid, 256, 0, st>>>(dA, dB, n, L, r, d_cost, d_topt);
+    else return fail(MPB200_EARG, "double integrators of dimension 1..3 are built in (got %d)", lq->d);
+    MPB_LAUNCHED();
+    return 0;
+}
+
+struct LqLaunch {
+    const double *table;
+    int words, M;
+    bool use_smem;
+    size_t smem;
+};
+static LqLaunch lq_cfg(const mpb200_obstacles *o) {
+    LqLaunch C;
+    C.table = o->table.as<double>();
+    C.words = o->table_words;
+    C.M = o->M;
+    size_t bytes = sizeof(double) * (size_t)o->table_words;
+    C.use_smem = bytes <= 160 * 1024;
+    C.smem = C.use_smem ? bytes : 0;
+    return C;
+}
+
+// (D, DW, KIND) combinations: workspace = positions of the double integrator
+#define MPB_LQ_DISPATCH(D_, DW_, KIND_, CALL)                                                       \
+    do {                                                                                            \
+        if (KIND_ == 0 && DW_ != 2) return fail(MPB200_EARG, "2-D obstacles need a 2-D workspace"); \
+        if (D_ == 2 && DW_ == 2 && KIND_ == 0) { CALL(2, 2, 0); }                                   \
+        else if (D_ == 2 && DW_ == 2 && KIND_ == 1) { CALL(2, 2, 1); }                              \
+        else if (D_ == 3 && DW_ == 3 && KIND_ == 1) { CALL(3, 3, 1); }                              \
+        else if (D_ == 3 && DW_ == 2 && KIND_ == 0) { CALL(3, 2, 0); }                              \
+        else if (D_ == 1 && DW_ == 1 && KIND_ == 1) { CALL(1, 1, 1); }                              \
+        else return fail(MPB200_EARG, "unsupported LQ (d=%d, workspace=%d, checker=%d) combination", D_, DW_, KIND_); \
+    } while (0)
+
+int lq_edges_free_device(const mpb200_samples *s, const mpb200_table *t, const mpb200_lq *lq, double r,
+                         const mpb200_obstacles *o, const mpb200_space_desc *ss, uint32_t *d_bits32,
+                         unsigned long long *d_checks) {
+    SpaceDev S;
+    int dw;
+    if (int rc = make_space(ss, s->d, &S, &dw)) return rc;
+    if (s->d != 2 * lq->d) return fail(MPB200_EARG, "sample dimension %d != 2 x %d", s->d, lq->d);
+    if (o->kind == 1 && o->d != dw) return fail(MPB200_EARG, "box dimension %d != workspace dimension %d", o->d, dw);
+    const LqDev L = lq_dev(lq);
+    const LqLaunch C = lq_cfg(o);
+    cudaStream_t st = ctx().stream;
+    int64_t blocks = ceil_div(t->ncols > 0 ? t->ncols : 1, 8);
+    const unsigned grid = (unsigned)(blocks < (int64_t)ctx().sm_count * 8 ? blocks : (int64_t)ctx().sm_count * 8);
+#define CALL(D_, DW_, K_)                                                                                          \
+    do {                                                                                                           \
+        if (C.smem > 48 * 1024)                                                                                    \
+            MPB_CUDA(cudaFuncSetAttribute(lq_edges_free_kernel<D_, DW_, K_>,                                       \
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C.smem));              \
+        lq_edges_free_kernel<D_, DW_, K_><<<grid, 256, C.smem, st>>>(                                              \
+            s->V.as<double>(), t->colptr.as<int64_t>(), t->rowval.as<int64_t>(), t->ncols, t->col0, L, r, S, C.table, \
+            C.words, C.M, C.use_smem, d_bits32, d_checks);                                                         \
+    } while (0)
+    MPB_LQ_DISPATCH(lq->d, dw, o->kind, CALL);
+#undef CALL
+    MPB_LAUNCHED();
+    return 0;
+}
+
+int lq_motions_free_device(const mpb200_lq *lq, double r, const double *dA, const double *dB, int64_t n, int d_state,
+                           const mpb200_obstacles *o, const mpb200_space_desc *ss, uint8_t *d_out,
+                           unsigned long long *d_checks) {
+    SpaceDev S;
+    int dw;
+    if (int rc = make_space(ss, d_state, &S, &dw)) return rc;
+    if (d_state != 2 * lq->d) return fail(MPB200_EARG, "state dimension %d != 2 x %d", d_state, lq->d);
+    if (o->kind == 1 && o->d != dw) return fail(MPB200_EARG, "box dimension %d != workspace dimension %d", o->d, dw);
+    const LqDev L = lq_dev(lq);
+    const LqLaunch C = lq_cfg(o);
+    cudaStream_t st = ctx().stream;
+    const unsigned grid = (unsigned)(ceil_div(n, 256) < 148 * 8 ? ceil_div(n, 256) : 148 * 8);
+#define CALL(D_, DW_, K_)                                                                                       \
+    do {                                                                                                        \
+        if (C.smem > 48 * 1024)                                                                                 \
+            MPB_CUDA(cudaFuncSetAttribute(lq_motions_free_kernel<D_, DW_, K_>,                                  \
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C.smem));           \
+        lq_motions_free_kernel<D_, DW_, K_><<<grid, 256, C.smem, st>>>(dA, dB, n, L, r, S, C.table, C.words, C.M, \
+                                                                       C.use_smem, d_out, d_checks);            \
+    } while (0)
+    MPB_LQ_DISPATCH(lq->d, dw, o->kind, CALL);
+#undef CALL
+    MPB_LAUNCHED();
+    return 0;
+}
+
+}  // namespace mpb

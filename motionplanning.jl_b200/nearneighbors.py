@@ -203,6 +203,51 @@ class MetricNN(SampleSet):
         super().close()
 
 
+class QuasiMetricNN(SampleSet):
+    """nearneighbors.jl:76-92 for asymmetric distances (LinearQuadratic): separate forward and
+    backward tables.  `precompute(r)` replaces helper_data_structures(V, ::LinearQuadratic)
+    (linearquadratic.jl:68-77) and every inballF!/inballB!."""
+
+    def __init__(self, V, dist, init=None):
+        V = np.ascontiguousarray(V, dtype=np.float64)
+        super().__init__(V, dist, init if init is not None else V[0])
+        self.cacheF = self.cacheB = None
+        self.tableF, self.tableB = DeviceTable(), DeviceTable()
+
+    def build_tables(self, r):
+        nF, nB = _lib.c_i64(0), _lib.c_i64(0)
+        _lib.check(_lib.lib().mpb200_lq_inball_build(self.handle(), self.dist.handle(), float(r),
+                                                     ctypes.byref(self.tableF.h), ctypes.byref(self.tableB.h),
+                                                     ctypes.byref(nF), ctypes.byref(nB)))
+        for t, n in ((self.tableF, nF), (self.tableB, nB)):
+            t.nnz, t.ncols = n.value, self.q1 - self.q0
+        self.r = float(r)
+        return nF.value, nB.value
+
+    def precompute(self, r):
+        self.build_tables(r)
+        self.cacheF = ImmutableNNC(self.fetch_table(self.tableF, "nnF"), float(r))
+        self.cacheB = ImmutableNNC(self.fetch_table(self.tableB, "nnB"), float(r))
+        return self.cacheF, self.cacheB
+
+    def lq_edges_free(self, CC, SS, fetch=True):
+        """validity per stored entry (row y -> column x) of the BACKWARD table: the motion
+        V[y] -> V[x] that fmt.jl:75 asks about; returns (chunks, checks)"""
+        d = SS.desc()
+        t = self.tableB
+        bits = self.pool.array(("lq_edge_bits",), (t.nnz + 63) // 64, np.uint64) if fetch else None
+        checks = _lib.c_i64(0)
+        _lib.check(_lib.lib().mpb200_lq_edges_free(self.handle(), t.h, self.dist.handle(), self.r, CC.handle(),
+                                                   ctypes.byref(d), _lib.ptr(bits), ctypes.byref(checks)))
+        CC.count += checks.value
+        return bits, checks.value
+
+    def close(self):
+        self.tableF.close()
+        self.tableB.close()
+        super().close()
+
+
 def addpoints(NN, W):
     """nearneighbors.jl:108-109 -- rebuilds the sample set from scratch, as the reference does."""
     return type(NN)(np.vstack([NN.V, np.atleast_2d(W)]), NN.dist, NN.init)
@@ -217,5 +262,21 @@ def inball(NN, v, r, f=None):
     return filter_neighborhood(col, f) if f is not None else col
 
 
-inballF = inball  # nearneighbors.jl:200-203: for a MetricNN forwards == backwards
-inballB = inball
+def inballF(NN, v, r, f=None):
+    """inballF!(NN, v, r[, f]): nearneighbors.jl:121,128,200-203"""
+    if isinstance(NN, MetricNN):
+        return inball(NN, v, r, f)
+    if NN.cacheF is None:
+        NN.precompute(r)
+    col = viewcol(NN.cacheF.D, v - NN.q0)
+    return filter_neighborhood(col, f) if f is not None else col
+
+
+def inballB(NN, v, r, f=None):
+    """inballB!(NN, v, r[, f]): nearneighbors.jl:122,128,200-203"""
+    if isinstance(NN, MetricNN):
+        return inball(NN, v, r, f)
+    if NN.cacheB is None:
+        NN.precompute(r)
+    col = viewcol(NN.cacheB.D, v - NN.q0)
+    return filter_neighborhood(col, f) if f is not None else col

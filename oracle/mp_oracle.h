@@ -106,6 +106,18 @@ int64_t orc_kdtree_inball(const orc_kdtree *T, int64_t v, double r, int64_t **in
 void orc_rball_kdtree(const orc_kdtree *T, double r, int64_t q0, int64_t q1,
                       int64_t *colptr, int64_t *rowval, double *nzval);
 
+/* lq.c : double-integrator linear-quadratic steering (linearquadratic.jl:46-53,68-88,126-225) */
+void orc_lq_steer(int d, const double *R, const double *x0, const double *x1, double r, double *cost, double *topt);
+void orc_lq_cost_terms(int d, const double *R, const double *x0, const double *x1, double t, double *out3);
+void orc_lq_state(int d, const double *x0, const double *x1, double t, double s, double *out);
+void orc_lq_inball(const double *V, int64_t N, int d, const double *R, double r, int forwards, int64_t q0, int64_t q1,
+                   int64_t *colptr, int64_t *rowval, double *nzval);
+int orc_lq_is_free_motion(const orc_checker *CC, const orc_space *S, int d, const double *R, double r,
+                          const double *v, const double *w, int64_t *count);
+void orc_lq_edges_free_csc(const orc_checker *CC, const orc_space *S, int d, const double *R, double r,
+                           const double *V, const int64_t *colptr, const int64_t *rowval, int64_t c0, int64_t c1,
+                           uint8_t *out, int64_t *count);
+
 #ifdef __cplusplus
 }
 #endif

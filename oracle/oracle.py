@@ -61,6 +61,13 @@ def lib():
         L.orc_kdtree_build.argtypes = [c_vp, c_i64, ctypes.c_int, ctypes.c_int]
         L.orc_kdtree_free.argtypes = [c_vp]
         L.orc_rball_kdtree.argtypes = [c_vp, c_dbl, c_i64, c_i64, c_vp, c_vp, c_vp]
+        L.orc_lq_steer.argtypes = [ctypes.c_int, c_vp, c_vp, c_vp, c_dbl, P(c_dbl), P(c_dbl)]
+        L.orc_lq_cost_terms.argtypes = [ctypes.c_int, c_vp, c_vp, c_vp, c_dbl, c_vp]
+        L.orc_lq_state.argtypes = [ctypes.c_int, c_vp, c_vp, c_dbl, c_dbl, c_vp]
+        L.orc_lq_inball.argtypes = [c_vp, c_i64, ctypes.c_int, c_vp, c_dbl, ctypes.c_int, c_i64, c_i64, c_vp, c_vp, c_vp]
+        L.orc_lq_is_free_motion.argtypes = [P(Checker), P(Space), ctypes.c_int, c_vp, c_dbl, c_vp, c_vp, P(c_i64)]
+        L.orc_lq_edges_free_csc.argtypes = [P(Checker), P(Space), ctypes.c_int, c_vp, c_dbl, c_vp, c_vp, c_vp, c_i64,
+                                            c_i64, c_vp, P(c_i64)]
     return _lib
 
 
@@ -280,3 +287,61 @@ class KDTree:
         nzval = np.zeros(nnz, dtype=np.float64)
         lib().orc_rball_kdtree(self.h, float(r), q0, q1, _p(colptr), _p(rowval), _p(nzval))
         return colptr, rowval, nzval
+
+
+# ---- linear-quadratic (double integrator) ----------------------------------------------------------
+class DoubleIntegratorLQ:
+    """d-dimensional double integrator with control penalty R (d x d SPD, default identity)."""
+
+    def __init__(self, d, R=None):
+        self.d = d
+        self.R = _f64(np.eye(d) if R is None else R)
+
+    def steer(self, x0, x1, r):
+        x0, x1 = _f64(x0), _f64(x1)
+        c, t = c_dbl(0), c_dbl(0)
+        lib().orc_lq_steer(self.d, _p(self.R), _p(x0), _p(x1), float(r), ctypes.byref(c), ctypes.byref(t))
+        return c.value, t.value
+
+    def cost_terms(self, x0, x1, t):
+        x0, x1 = _f64(x0), _f64(x1)
+        out = np.zeros(3)
+        lib().orc_lq_cost_terms(self.d, _p(self.R), _p(x0), _p(x1), float(t), _p(out))
+        return out
+
+    def state(self, x0, x1, t, s):
+        x0, x1 = _f64(x0), _f64(x1)
+        out = np.zeros(2 * self.d)
+        lib().orc_lq_state(self.d, _p(x0), _p(x1), float(t), float(s), _p(out))
+        return out
+
+    def inball(self, V, r, forwards, q0=0, q1=None):
+        V = _f64(V)
+        N = V.shape[0]
+        q1 = N if q1 is None else q1
+        colptr = np.zeros(q1 - q0 + 1, dtype=np.int64)
+        lib().orc_lq_inball(_p(V), N, self.d, _p(self.R), float(r), int(forwards), q0, q1, _p(colptr), None, None)
+        nnz = int(colptr[-1] - 1)
+        rowval, nzval = np.zeros(nnz, dtype=np.int64), np.zeros(nnz)
+        lib().orc_lq_inball(_p(V), N, self.d, _p(self.R), float(r), int(forwards), q0, q1, _p(colptr), _p(rowval),
+                            _p(nzval))
+        return colptr, rowval, nzval
+
+    def is_free_motion(self, obs, space, r, v, w):
+        v, w = _f64(v), _f64(w)
+        cc = obs.checker()
+        cnt = c_i64(0)
+        ok = lib().orc_lq_is_free_motion(ctypes.byref(cc), ctypes.byref(space.c), self.d, _p(self.R), float(r), _p(v),
+                                         _p(w), ctypes.byref(cnt))
+        return bool(ok), cnt.value
+
+    def edges_free_csc(self, obs, space, r, V, colptr, rowval, c0=0):
+        V = _f64(V)
+        colptr = np.ascontiguousarray(colptr, dtype=np.int64)
+        rowval = np.ascontiguousarray(rowval, dtype=np.int64)
+        out = np.zeros(len(rowval), dtype=np.uint8)
+        cc = obs.checker()
+        cnt = c_i64(0)
+        lib().orc_lq_edges_free_csc(ctypes.byref(cc), ctypes.byref(space.c), self.d, _p(self.R), float(r), _p(V),
+                                    _p(colptr), _p(rowval), c0, c0 + len(colptr) - 1, _p(out), ctypes.byref(cnt))
+        return out, cnt.value
