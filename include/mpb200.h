@@ -169,6 +169,40 @@ int mpb200_lq_edges_free(const mpb200_samples *s, const mpb200_table *t, const m
 int mpb200_lq_motions_free(const mpb200_lq *lq, double r, const double *v_aos, const double *w_aos, int64_t n,
                            const mpb200_obstacles *o, const mpb200_space_desc *ss, uint8_t *out, int64_t *checks);
 
+/* ---- Monte-Carlo trajectory collision probability -----------------------------------
+ * NOT in the reference (only paper links, README.md:9-10, and the helper geometry
+ * closest/closeR, SAT2D.jl:208-285, boxesND.jl:61-86): specified in SURVEY.md section 11 /
+ * DESIGN.md.  Closed loop z' = F_t z + G_t eps_t (z_0 = 0), workspace w_t = wbar_t + Wz z_t,
+ * hit = some w_t (swept: some segment w_{t-1}->w_t) collides with the obstacle set, defensive
+ * mixture proposal over the stacked noise, Philox4x32-10 keyed by (seed, rollout id).
+ * All matrices row-major. */
+typedef struct {
+    int32_t T;           /* steps */
+    int32_t nz;          /* closed-loop state dimension */
+    int32_t q;           /* noise dimension per step */
+    int32_t dw;          /* workspace dimension */
+    const double *F;     /* T x nz x nz */
+    const double *G;     /* T x nz x q */
+    const double *Wz;    /* dw x nz */
+    const double *wbar;  /* (T+1) x dw nominal workspace points (index 0 = start, never tested as a point) */
+    int32_t K;           /* shifted mixture components (besides the nominal one) */
+    const double *alpha; /* K+1 mixture weights, alpha[0] = nominal, sum 1 */
+    const double *mu;    /* K x (T*q) mean shifts of the stacked noise */
+    int32_t swept;       /* 0: point test per step, 1: segment test between consecutive steps */
+} mpb200_mc_problem;
+typedef struct {
+    double s1;    /* sum of w * hit          */
+    double s2;    /* sum of (w * hit)^2      */
+    double s0;    /* sum of w (diagnostic: -> n) */
+    int64_t n;    /* rollouts                */
+    int64_t hits; /* unweighted hit count    */
+} mpb200_mc_result;
+/* Rollout ids [first, first + n): the shard of one GPU; sums of shards add up to the whole.
+ * hit_out (n bytes) / w_out (n doubles) are optional per-rollout outputs. */
+int mpb200_mc_collision_probability(const mpb200_mc_problem *p, const mpb200_obstacles *o, uint64_t seed,
+                                    int64_t first, int64_t n, mpb200_mc_result *out, uint8_t *hit_out,
+                                    double *w_out);
+
 #ifdef __cplusplus
 }
 #endif

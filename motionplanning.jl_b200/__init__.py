@@ -17,6 +17,8 @@ from .nearneighbors import (ImmutableNNC, MetricNN, QuasiMetricNN, SampleSet, Sp
                             nonzeros, viewcol)
 from .linearquadratic import (DoubleIntegrator, LinearQuadratic, LinearQuadraticQuasiMetricSpace,  # noqa: F401
                               lq_motions_free, setup_steering, steer, steer_batch)
+from . import montecarlo  # noqa: F401
+from .montecarlo import MCProblem, collision_probability  # noqa: F401
 from . import obstaclesets  # noqa: F401
 
 __version__ = "0.1.0"

@@ -38,6 +38,15 @@ class SpaceDesc(ctypes.Structure):
     ]
 
 
+class McProblem(ctypes.Structure):
+    _fields_ = [("T", c_i32), ("nz", c_i32), ("q", c_i32), ("dw", c_i32), ("F", c_vp), ("G", c_vp), ("Wz", c_vp),
+                ("wbar", c_vp), ("K", c_i32), ("alpha", c_vp), ("mu", c_vp), ("swept", c_i32)]
+
+
+class McResult(ctypes.Structure):
+    _fields_ = [("s1", c_dbl), ("s2", c_dbl), ("s0", c_dbl), ("n", c_i64), ("hits", c_i64)]
+
+
 # every symbol include/mpb200.h declares: name -> (restype, argtypes)
 SIGNATURES = {
     "mpb200_init": (ctypes.c_int, [ctypes.c_int]),
@@ -69,6 +78,8 @@ SIGNATURES = {
     "mpb200_lq_inball_build": (ctypes.c_int, [c_vp, c_vp, c_dbl, P(c_vp), P(c_vp), P(c_i64), P(c_i64)]),
     "mpb200_lq_steer": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_dbl, c_vp, c_vp]),
     "mpb200_lq_edges_free": (ctypes.c_int, [c_vp, c_vp, c_vp, c_dbl, c_vp, P(SpaceDesc), c_vp, P(c_i64)]),
+    "mpb200_mc_collision_probability": (ctypes.c_int, [P(McProblem), c_vp, ctypes.c_uint64, c_i64, c_i64, P(McResult),
+                                                       c_vp, c_vp]),
     "mpb200_lq_motions_free": (ctypes.c_int, [c_vp, c_dbl, c_vp, c_vp, c_i64, c_vp, P(SpaceDesc), c_vp, P(c_i64)]),
 }
 

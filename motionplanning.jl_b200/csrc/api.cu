@@ -94,6 +94,9 @@ int lq_motions_free_device(const mpb200_lq *lq, double r, const double *dA, cons
                            const mpb200_obstacles *o, const mpb200_space_desc *ss, uint8_t *d_out,
                            unsigned long long *d_checks);
 
+int mc_run_device(const mpb200_mc_problem *p, const mpb200_obstacles *o, unsigned long long seed, long long first,
+                  long long n, double *h_out4, uint8_t *h_hit, double *h_w);
+
 }  // namespace mpb
 
 using namespace mpb;
@@ -587,6 +590,27 @@ int mpb200_lq_motions_free(const mpb200_lq *lq, double r, const double *v, const
     MPB_CUDA(cudaMemcpyAsync(c.h_scalar + 5, c.d_scalar + 5, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     MPB_CUDA(cudaStreamSynchronize(st));
     if (checks) *checks = c.h_scalar[5];
+    return MPB200_OK;
+}
+
+// ---- Monte-Carlo collision probability ---------------------------------------------------------
+int mpb200_mc_collision_probability(const mpb200_mc_problem *p, const mpb200_obstacles *o, uint64_t seed, int64_t first,
+                                    int64_t n, mpb200_mc_result *out, uint8_t *hit_out, double *w_out) {
+    MPB_REQUIRE_INIT();
+    MPB_CHECK_ARG(p && o && out, "NULL argument");
+    MPB_CHECK_ARG(p->T >= 1 && p->nz >= 1 && p->q >= 1 && p->dw >= 1 && p->K >= 0, "bad problem dimensions");
+    MPB_CHECK_ARG(p->F && p->G && p->Wz && p->wbar && p->alpha && (p->K == 0 || p->mu), "NULL problem arrays");
+    MPB_CHECK_ARG(n >= 0 && first >= 0, "negative rollout range");
+    double sum = 0;
+    for (int k = 0; k <= p->K; ++k) {
+        MPB_CHECK_ARG(p->alpha[k] >= 0, "mixture weights must be non-negative");
+        sum += p->alpha[k];
+    }
+    MPB_CHECK_ARG(sum > 0.999999 && sum < 1.000001 && p->alpha[0] > 0, "mixture weights must sum to 1 with alpha[0] > 0");
+    double r4[4] = {0, 0, 0, 0};
+    if (n > 0)
+        if (int rc = mc_run_device(p, o, seed, first, n, r4, hit_out, w_out)) return rc;
+    out->s1 = r4[0]; out->s2 = r4[1]; out->s0 = r4[2]; out->n = n; out->hits = (int64_t)(r4[3] + 0.5);
     return MPB200_OK;
 }
 

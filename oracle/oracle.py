@@ -40,6 +40,11 @@ class Checker(ctypes.Structure):
     _fields_ = [("kind", c_i32), ("obs2d", P(Obs2D)), ("box_lo", c_vp), ("box_hi", c_vp), ("M", c_i32), ("d", c_i32)]
 
 
+class McProblem(ctypes.Structure):
+    _fields_ = [("T", c_i32), ("nz", c_i32), ("q", c_i32), ("dw", c_i32), ("F", c_vp), ("G", c_vp), ("Wz", c_vp),
+                ("wbar", c_vp), ("K", c_i32), ("alpha", c_vp), ("mu", c_vp), ("swept", c_i32)]
+
+
 def lib():
     global _lib
     if _lib is None:
@@ -61,6 +66,13 @@ def lib():
         L.orc_kdtree_build.argtypes = [c_vp, c_i64, ctypes.c_int, ctypes.c_int]
         L.orc_kdtree_free.argtypes = [c_vp]
         L.orc_rball_kdtree.argtypes = [c_vp, c_dbl, c_i64, c_i64, c_vp, c_vp, c_vp]
+        L.orc_philox4x32_10.argtypes = [c_vp, c_vp, c_vp]
+        L.orc_det_log.restype = c_dbl
+        L.orc_det_log.argtypes = [c_dbl]
+        L.orc_det_exp.restype = c_dbl
+        L.orc_det_exp.argtypes = [c_dbl]
+        L.orc_det_sincos2pi.argtypes = [c_dbl, P(c_dbl), P(c_dbl)]
+        L.orc_mc_run.argtypes = [P(McProblem), P(Checker), ctypes.c_uint64, c_i64, c_i64, c_vp, P(c_i64), c_vp, c_vp]
         L.orc_lq_steer.argtypes = [ctypes.c_int, c_vp, c_vp, c_vp, c_dbl, P(c_dbl), P(c_dbl)]
         L.orc_lq_cost_terms.argtypes = [ctypes.c_int, c_vp, c_vp, c_vp, c_dbl, c_vp]
         L.orc_lq_state.argtypes = [ctypes.c_int, c_vp, c_vp, c_dbl, c_dbl, c_vp]
@@ -345,3 +357,54 @@ class DoubleIntegratorLQ:
         lib().orc_lq_edges_free_csc(ctypes.byref(cc), ctypes.byref(space.c), self.d, _p(self.R), float(r), _p(V),
                                     _p(colptr), _p(rowval), c0, c0 + len(colptr) - 1, _p(out), ctypes.byref(cnt))
         return out, cnt.value
+
+
+# ---- Monte-Carlo collision probability (spec: oracle/mc.c header; parity unpinned) -------------------
+def philox4x32_10(ctr, key):
+    c = np.asarray(ctr, dtype=np.uint32)
+    k = np.asarray(key, dtype=np.uint32)
+    out = np.zeros(4, dtype=np.uint32)
+    lib().orc_philox4x32_10(_p(c), _p(k), _p(out))
+    return out
+
+
+def det_log(x):
+    return lib().orc_det_log(float(x))
+
+
+def det_exp(x):
+    return lib().orc_det_exp(float(x))
+
+
+def det_sincos2pi(u):
+    s, c = c_dbl(0), c_dbl(0)
+    lib().orc_det_sincos2pi(float(u), ctypes.byref(s), ctypes.byref(c))
+    return s.value, c.value
+
+
+class McSpec:
+    """Arrays of the estimator's problem statement (see oracle/mc.c)."""
+
+    def __init__(self, F, G, Wz, wbar, alpha, mu, swept=False):
+        self.F, self.G = _f64(F), _f64(G)                    # T x nz x nz, T x nz x q
+        self.Wz, self.wbar = _f64(Wz), _f64(wbar)            # dw x nz, (T+1) x dw
+        self.alpha = _f64(alpha)                             # K+1
+        T, nz, q = self.F.shape[0], self.F.shape[1], self.G.shape[2]
+        K = len(self.alpha) - 1
+        self.mu = _f64(np.asarray(mu, dtype=np.float64).reshape(K, T * q)) if K else np.zeros((0, T * q))
+        self.T, self.nz, self.q, self.dw, self.K, self.swept = T, nz, q, self.Wz.shape[0], K, bool(swept)
+        self.c = McProblem(T, nz, q, self.dw, _p(self.F), _p(self.G), _p(self.Wz), _p(self.wbar), K, _p(self.alpha),
+                           _p(self.mu), int(self.swept))
+
+
+def mc_run(spec, obs, seed, first, n, per_rollout=False):
+    sums = np.zeros(3)
+    hits = c_i64(0)
+    hit = np.zeros(n, dtype=np.uint8) if per_rollout else None
+    w = np.zeros(n) if per_rollout else None
+    cc = obs.checker()
+    lib().orc_mc_run(ctypes.byref(spec.c), ctypes.byref(cc), seed, first, n, _p(sums), ctypes.byref(hits), _p(hit), _p(w))
+    res = dict(S1=sums[0], S2=sums[1], S0=sums[2], n=n, hits=hits.value)
+    if per_rollout:
+        res["hit"], res["w"] = hit, w
+    return res
