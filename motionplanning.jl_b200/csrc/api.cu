@@ -77,6 +77,7 @@ int phases_collect(int n) {
 // implemented in the kernel translation units
 int compute_bbox(mpb200_samples *s);
 int grid_inball_build(mpb200_samples *s, double r, mpb200_table *t);
+int brute_inball_build(mpb200_samples *s, double r, mpb200_table *t);
 int points_free_device(const double *dV, int64_t n, int d, const mpb200_obstacles *o, const mpb200_space_desc *ss,
                        uint32_t *d_bits32, uint8_t *d_bytes);
 int edges_free_device(const double *dV, int d, const mpb200_table *t, const mpb200_obstacles *o,
@@ -244,7 +245,7 @@ int mpb200_inball_build(mpb200_samples *s, double r, mpb200_table **table, int64
     } else if (s->d <= 3 && s->d >= 2) {
         rc = grid_inball_build(s, r, t);
     } else {
-        rc = fail(MPB200_EARG, "Euclidean r-ball for d = %d is not built in this library version", s->d);
+        rc = brute_inball_build(s, r, t);
     }
     if (rc) {
         if (fresh) mpb200_table_destroy(t);

@@ -1,0 +1,179 @@
+// brute_rball.cu -- K3 + K4: Euclidean r-ball tables for d >= 4 (no useful spatial pruning: at the
+// FMT* radius the ball spans a large part of the cube), as an all-pairs FP32 prefilter followed
+// by the exact FP64 recheck of the few survivors.
+//
+// Replaces inball(V, dist, DS, v, r) over a KDTree / brute colwise distance
+// (nearneighbors.jl:138-150,179-183; geometric.jl:4-6,14) for every query column.  Membership
+// and stored distances are decided ONLY by the exact test  s = sum_i (V[v]_i - V[j]_i)^2 <= r*r
+// (index order, one rounding per operation); the FP32 pass merely discards pairs that provably
+// fail it: the threshold carries a rigorous bound on the FP32 conversion + accumulation error
+// (derivation in DESIGN.md), so there are no false negatives.
+//
+// Layout: a padded FP32 AoS copy of the samples (float4 granules) is streamed through shared
+// memory in tiles and read by broadcast; one thread owns one query column (its FP32 point in
+// registers) and walks the samples in index order, so rows come out ascending and need no sort.
+#include "common.cuh"
+#include "scan.cuh"
+
+namespace mpb {
+
+constexpr int kBrThreads = 256;
+constexpr int kBrTile = 256;
+
+template <int D>
+__global__ void __launch_bounds__(256) to_float_padded(const double *__restrict__ V, int64_t N, float *__restrict__ Vf) {
+    constexpr int DP = (D + 3) & ~3;
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= N) return;
+#pragma unroll
+    for (int i = 0; i < DP; ++i) Vf[j * DP + i] = (i < D) ? (float)V[j * D + i] : 0.0f;
+}
+
+template <int D>
+__device__ __forceinline__ double exact_sq(const double *__restrict__ a, const double *__restrict__ b) {
+    double t = __dsub_rn(a[0], b[0]);
+    double s = __dmul_rn(t, t);
+#pragma unroll
+    for (int i = 1; i < D; ++i) {
+        t = __dsub_rn(a[i], b[i]);
+        s = __dadd_rn(s, __dmul_rn(t, t));
+    }
+    return s;
+}
+
+template <int D, bool FILL>
+__global__ void __launch_bounds__(kBrThreads)
+brute_rball_kernel(const double *__restrict__ V, const float *__restrict__ Vf, int64_t N, int64_t q0, int64_t nq,
+                   double r2, float thr32, int *__restrict__ counts, const int64_t *__restrict__ colptr,
+                   int64_t *__restrict__ rowval, double *__restrict__ nzval) {
+    constexpr int DP = (D + 3) & ~3;
+    __shared__ float4 tile[kBrTile * DP / 4];
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = w < nq;
+    const int64_t q = q0 + w;
+    float xq[DP];
+#pragma unroll
+    for (int i = 0; i < DP; ++i) xq[i] = active ? Vf[q * DP + i] : 0.0f;
+    int cnt = 0;
+    int64_t pos = (FILL && active) ? colptr[w] - 1 : 0;
+    for (int64_t t0 = 0; t0 < N; t0 += kBrTile) {
+        const int n_t = (int)((N - t0 < kBrTile) ? (N - t0) : kBrTile);
+        __syncthreads();
+        {
+            const float4 *src = reinterpret_cast<const float4 *>(Vf + t0 * DP);
+            for (int i = threadIdx.x; i < n_t * DP / 4; i += blockDim.x) tile[i] = src[i];
+        }
+        __syncthreads();
+        if (!active) continue;
+#pragma unroll 4
+        for (int jj = 0; jj < n_t; ++jj) {
+            float s = 0.0f;
+#pragma unroll
+            for (int g = 0; g < DP / 4; ++g) {
+                const float4 b = tile[jj * (DP / 4) + g];
+                const float d0 = xq[4 * g] - b.x, d1 = xq[4 * g + 1] - b.y, d2 = xq[4 * g + 2] - b.z,
+                            d3 = xq[4 * g + 3] - b.w;
+                s = fmaf(d0, d0, s); s = fmaf(d1, d1, s); s = fmaf(d2, d2, s); s = fmaf(d3, d3, s);
+            }
+            if (s <= thr32) {  // survivor: exact FP64 recheck (K4)
+                const int64_t j = t0 + jj;
+                if (j != q) {
+                    const double s64 = exact_sq<D>(V + q * D, V + j * D);
+                    if (s64 <= r2) {
+                        if (FILL) { rowval[pos] = j + 1; nzval[pos] = sqrt(s64); ++pos; }
+                        ++cnt;
+                    }
+                }
+            }
+        }
+    }
+    if (!FILL && active) counts[w] = cnt;
+}
+
+// threshold for the FP32 pass: every pair with exact s <= r^2 satisfies s32 <= thr
+static float prefilter_threshold(double r, int D, double M) {
+    const double u = 5.9604644775390625e-08;  // 2^-24
+    const double e = 2.0 * u * M * (1.0 + u);
+    double thr = r * r + 2.0 * (2.0 * e * sqrt((double)D) * r + 2.0 * u * r * r + D * (e + u * r) * (e + u * r));
+    thr *= 1.0 + (D + 4) * 2.0 * u;
+    float f = (float)thr;
+    while ((double)f < thr) f = nextafterf(f, INFINITY);
+    return nextafterf(f, INFINITY);
+}
+
+template <int D>
+static int brute_build(mpb200_samples *s, double r, mpb200_table *t) {
+    constexpr int DP = (D + 3) & ~3;
+    Context &c = ctx();
+    cudaStream_t st = c.stream;
+    const int64_t N = s->N, nq = s->q1 - s->q0;
+    const double *V = s->V.as<double>();
+    double bb[2 * 16];
+    MPB_CUDA(cudaMemcpyAsync(bb, s->minmax.as<double>(), sizeof(double) * 2 * D, cudaMemcpyDeviceToHost, st));
+    MPB_CUDA(cudaStreamSynchronize(st));
+    double M = 0;
+    for (int i = 0; i < 2 * D; ++i) M = fmax(M, fabs(bb[i]));
+    const float thr32 = prefilter_threshold(r, D, M);
+    if (!(M < 1e18)) return fail(MPB200_EARG, "sample coordinates out of range for the FP32 prefilter");
+
+    phase_mark(0);
+    if (int rc = s->sorted_pos.reserve(sizeof(float) * (size_t)(N * DP + 4))) return rc;  // reused as the FP32 copy
+    float *Vf = s->sorted_pos.as<float>();
+    to_float_padded<D><<<(unsigned)ceil_div(N, 256), 256, 0, st>>>(V, N, Vf);
+    MPB_LAUNCHED();
+    if (int rc = t->counts.reserve(sizeof(int) * (size_t)(nq + 1))) return rc;
+    if (int rc = t->colptr.reserve(sizeof(int64_t) * (size_t)(nq + 1))) return rc;
+    const unsigned nb = (unsigned)ceil_div(nq > 0 ? nq : 1, kBrThreads);
+    phase_mark(1);
+    if (nq > 0) {
+        brute_rball_kernel<D, false><<<nb, kBrThreads, 0, st>>>(V, Vf, N, s->q0, nq, r * r, thr32, t->counts.as<int>(),
+                                                               nullptr, nullptr, nullptr);
+        MPB_LAUNCHED();
+    }
+    if (int rc = exclusive_scan<int, int64_t>(t->counts.as<int>(), nq, t->colptr.as<int64_t>(), (int64_t)1, s->scan_tmp,
+                                              c.d_scalar))
+        return rc;
+    phase_mark(2);
+    MPB_CUDA(cudaMemcpyAsync(c.h_scalar, c.d_scalar, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    MPB_CUDA(cudaStreamSynchronize(st));
+    const int64_t nnz = c.h_scalar[0];
+    if (int rc = t->rowval.reserve(sizeof(int64_t) * (size_t)(nnz + 1))) return rc;
+    if (int rc = t->nzval.reserve(sizeof(double) * (size_t)(nnz + 1))) return rc;
+    phase_mark(3);
+    if (nq > 0 && nnz > 0) {
+        brute_rball_kernel<D, true><<<nb, kBrThreads, 0, st>>>(V, Vf, N, s->q0, nq, r * r, thr32, nullptr,
+                                                              t->colptr.as<int64_t>(), t->rowval.as<int64_t>(),
+                                                              t->nzval.as<double>());
+        MPB_LAUNCHED();
+    }
+    phase_mark(4);
+    MPB_CUDA(cudaStreamSynchronize(st));
+    phases_collect(4);
+    t->ncols = nq;
+    t->col0 = s->q0;
+    t->nnz = nnz;
+    t->r = r;
+    return 0;
+}
+
+int brute_inball_build(mpb200_samples *s, double r, mpb200_table *t) {
+    switch (s->d) {
+    case 4: return brute_build<4>(s, r, t);
+    case 5: return brute_build<5>(s, r, t);
+    case 6: return brute_build<6>(s, r, t);
+    case 7: return brute_build<7>(s, r, t);
+    case 8: return brute_build<8>(s, r, t);
+    case 9: return brute_build<9>(s, r, t);
+    case 10: return brute_build<10>(s, r, t);
+    case 11: return brute_build<11>(s, r, t);
+    case 12: return brute_build<12>(s, r, t);
+    case 13: return brute_build<13>(s, r, t);
+    case 14: return brute_build<14>(s, r, t);
+    case 15: return brute_build<15>(s, r, t);
+    case 16: return brute_build<16>(s, r, t);
+    case 1: return brute_build<1>(s, r, t);
+    default: return fail(MPB200_EARG, "all-pairs r-ball supports d = 1 and 4..16 (got %d)", s->d);
+    }
+}
+
+}  // namespace mpb

@@ -133,6 +133,42 @@ def test_k1_k2_rball_matches_oracle(gpu, orc, d, N, r):
     NN.close()
 
 
+@pytest.mark.parametrize("d,N", [(4, 4000), (6, 3000), (10, 5000), (16, 1500), (1, 2000)])
+def test_k3_k4_high_dim_rball_matches_oracle(gpu, orc, d, N):
+    """all-pairs FP32 prefilter + exact FP64 recheck: same sets, bit-identical distances"""
+    mp = gpu
+    V = fx.uniform_samples(N, d, 20240603 + d)
+    r = fx.fmt_radius(N, d) if d > 1 else 0.01
+    NN = mp.MetricNN(V)
+    D = NN.precompute(r).D
+    ref = orc.rball_brute(V, r)
+    assert np.array_equal(D.colptr, ref[0]) and np.array_equal(D.rowval, ref[1])
+    assert D.nzval.tobytes() == ref[2].tobytes()
+    assert D.nnz > N
+    NN.close()
+
+
+def test_k3_prefilter_band_has_no_false_negatives(gpu, orc):
+    """adversarial for the FP32 prefilter: pairs EXACTLY at the radius, large coordinate offsets
+    (FP32 conversion error >> the gap to the radius), shard ranges"""
+    mp = gpu
+    rng = np.random.Generator(np.random.PCG64(17))
+    d = 5
+    base = rng.integers(-40, 40, size=(600, d)).astype(np.float64)
+    V = np.vstack([base, base + [3, 4, 0, 0, 0], base + [0, 0, 5, 0, 0], base + [3, 0, 4, 0, 1e-9]]) / 8.0
+    for off, r in ((0.0, 5.0 / 8.0), (1000.0, 5.0 / 8.0), (-3.0e4, 0.7)):
+        W = V + off
+        NN = mp.MetricNN(W)
+        NN.set_query_range(100, 1900)
+        D = NN.precompute(r).D
+        ref = orc.rball_brute(W, r, 0, 100, 1900)
+        assert np.array_equal(D.colptr, ref[0]) and np.array_equal(D.rowval, ref[1])
+        assert D.nzval.tobytes() == ref[2].tobytes()
+        if r == 5.0 / 8.0:
+            assert (D.nzval == r).sum() > 500        # the exactly-at-radius pairs are members
+        NN.close()
+
+
 def test_k2_duplicates_clusters_and_big_columns(gpu, orc):
     """ragged inputs: coincident points, a dense cluster whose columns exceed the per-warp stage
     (spill path), points outside the unit square, an isolated point"""
