@@ -17,6 +17,9 @@ from .nearneighbors import (ImmutableNNC, MetricNN, QuasiMetricNN, SampleSet, Sp
                             nonzeros, viewcol)
 from .linearquadratic import (DoubleIntegrator, LinearQuadratic, LinearQuadraticQuasiMetricSpace,  # noqa: F401
                               lq_motions_free, setup_steering, steer, steer_batch)
+from .problems import (BallGoal, MPProblem, MPSolution, PointGoal, RectangleGoal, StateGoal, is_goal_pt,  # noqa: F401
+                       sample_free, sample_free_goal, sample_goal)
+from .planners import fmtstar  # noqa: F401
 from . import montecarlo  # noqa: F401
 from .montecarlo import MCProblem, collision_probability  # noqa: F401
 from . import obstaclesets  # noqa: F401

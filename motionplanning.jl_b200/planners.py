@@ -1,0 +1,144 @@
+"""FMT* over GPU-precomputed neighbour and validity tables.
+
+Host restatement of src/planners/fmt.jl:4-119 (`fmtstar!`): the heap-ordered wavefront and the
+tree bookkeeping stay on the host exactly as north_star prescribes; what changes is where its
+three hot calls are served from:
+  nearF / nearB (fmt.jl:70,72)    -> column views of the ImmutableNNC tables built by K1/K2 or K5
+  F[i] = is_free_state (:31-36)   -> one batched K6 call
+  is_free_motion(V[y], V[x]) (:75)-> a bit lookup in the edge-validity table built by K7/K8/K9,
+                                     aligned with the backward table (row y, column x)
+The neighbour iteration order (ascending index), findmin's first-minimum tie-break and the
+"collision_checks" metadata (lookups actually consumed, one per segment test the lazy reference
+would have run) are preserved.
+"""
+import heapq
+import math
+import time
+
+import numpy as np
+
+from .linearquadratic import LinearQuadratic, setup_steering
+from .nearneighbors import MetricNN
+from .problems import MPSolution, goal_mask, sample_free
+from .statespaces import Euclidean, states_free, volume
+
+
+def fmt_radius(N, d, rm, free_volume_ub):
+    """fmt.jl:37-41"""
+    return rm * 2 * (1 / d * free_volume_ub / (math.pi ** (d / 2) / math.gamma(d / 2 + 1)) * math.log(N) / N) ** (1 / d)
+
+
+def _bits_to_bool(chunks, n):
+    return np.unpackbits(np.ascontiguousarray(chunks).view(np.uint8), bitorder="little")[:n].astype(bool)
+
+
+def fmtstar(P, N=None, rm=1.0, connections="R", r=0.0, ensure_goal_ct=1, init_idx=1, checkpts=True, seed=0):
+    """fmtstar!(P, N; rm, connections, r, ensure_goal_ct, init_idx, checkpts) -> (status, cost, elapsed)"""
+    t_start = time.perf_counter()
+    N = len(P.V) if N is None else N
+    P.CC.count = 0
+    if connections == "K":
+        # knn*/mutualknn* are exported but never defined in the reference (nearneighbors.jl:9-11,
+        # fmt.jl:17-19): connections = :K throws there as well
+        raise NotImplementedError("k-nearest connections are undefined in the reference (mutualknnF!, knnB!)")
+    if connections != "R":
+        raise ValueError("Connection type must be radial (:R) or k-nearest (:K)")
+    SS, CC = P.SS, P.CC
+    if r > 0:
+        setup_steering(SS, r)
+    if not states_free(P.init, CC, SS)[0]:
+        P.status = "failed"                               # fmt.jl:24-29
+        P.solution = MPSolution(P.status, math.inf, time.perf_counter() - t_start, {})
+        return math.inf
+    free_volume_ub = sample_free(P, N - len(P.V), ensure_goal_ct=ensure_goal_ct, seed=seed) if N > len(P.V) else volume(SS)
+    NN = P.V
+    V = NN.V
+    if r == 0:
+        r = fmt_radius(N, SS.dim, rm, free_volume_ub)
+        setup_steering(SS, r)
+
+    # ---- the batched precompute that replaces the lazy per-call hot path -----------------------
+    lq = isinstance(SS.dist, LinearQuadratic)
+    if lq:
+        cF, cB = NN.precompute(r)
+        DF, DB = cF.D, cB.D
+        ebits, _ = NN.lq_edges_free(CC, SS)
+    else:
+        DF = DB = NN.precompute(r).D
+        ebits, _ = NN.edges_free(NN.table, CC, SS)
+    lookups_before = CC.count
+    CC.count = 0                                          # the table build is not what FMT* "asked"
+    evalid = _bits_to_bool(ebits, DB.nnz)
+    F = _bits_to_bool(NN.points_free(CC, SS), N) if checkpts else np.ones(N, dtype=bool)
+    is_goal = goal_mask(V, P.goal, SS)
+
+    # per-edge number of segment tests the lazy checker would have run (CC.count parity):
+    # Euclidean edges: 1 if the first endpoint is inside the state bounds, else 0
+    inb = np.all((SS.lo <= V) & (V <= SS.hi), axis=1)
+
+    A = np.zeros(N, dtype=np.int64)
+    Wm = np.ones(N, dtype=bool)
+    H = np.zeros(N, dtype=bool)
+    C = np.zeros(N)
+    if not np.all(V[init_idx - 1] == P.init):
+        raise RuntimeError("P.V[init_idx] must be the init state (fmt.jl:48-66)")
+    Wm[init_idx - 1] = False
+    H[init_idx - 1] = True
+    heap = []
+    z = init_idx
+    fcp, frv, fnz = DF.colptr, DF.rowval, DF.nzval
+    bcp, brv, bnz = DB.colptr, DB.rowval, DB.nzval
+    checks = 0
+    while not is_goal[z - 1]:
+        H_new = []
+        fs = frv[fcp[z - 1] - 1:fcp[z] - 1]
+        for x in fs[Wm[fs - 1]]:                           # nearF(V, z, r, W): unvisited, ascending
+            x = int(x)
+            if checkpts and not F[x - 1]:
+                continue
+            lo, hi = bcp[x - 1] - 1, bcp[x] - 1
+            ys = brv[lo:hi]
+            keep = H[ys - 1]                               # nearB(V, x, r, H): open neighbours
+            cand = ys[keep]
+            if cand.size == 0:                             # cannot happen for consistent F/B tables
+                continue
+            costs = C[cand - 1] + bnz[lo:hi][keep]
+            j = int(np.argmin(costs))                      # findmin: first minimum
+            c_min, y_min = float(costs[j]), int(cand[j])
+            e = lo + int(np.flatnonzero(keep)[j])          # stored entry (row y_min, column x)
+            if lq:
+                checks += 1                                # counted per motion; segments in metadata below
+            else:
+                checks += int(inb[y_min - 1])
+            if evalid[e]:                                  # is_free_motion(V[y_min], V[x], CC, SS)
+                A[x - 1] = y_min
+                C[x - 1] = c_min
+                heapq.heappush(heap, (c_min, x))
+                H_new.append(x)
+                Wm[x - 1] = False
+        if H_new:
+            H[np.asarray(H_new) - 1] = True
+        H[z - 1] = False
+        if heap:
+            _, z = heapq.heappop(heap)
+        else:
+            break
+
+    sol = [z]
+    costs = [C[z - 1]]
+    while sol[0] != 1:                                     # fmt.jl:92-101 (assumes init_idx == 1)
+        sol.insert(0, int(A[sol[0] - 1]))
+        if sol[0] == 0:
+            costs.insert(0, 0.0)
+            break
+        costs.insert(0, C[sol[0] - 1])
+    solved = bool(is_goal[z - 1])
+    P.status = "solved" if solved else "failed"
+    CC.count = checks
+    meta = {
+        "radius_multiplier": rm, "collision_checks": checks, "num_samples": N, "cost": float(C[z - 1]),
+        "cumcost": costs, "planner": "FMTstar", "solved": solved, "tree": A, "path": sol, "r": r,
+        "precomputed_edge_checks": int(lookups_before),
+    }
+    P.solution = MPSolution(P.status, float(C[z - 1]), time.perf_counter() - t_start, meta)
+    return P.status, P.solution.cost, P.solution.elapsed

@@ -1,0 +1,114 @@
+"""End-to-end: FMT* over the GPU-built tables (product planner) against FMT* over the oracle's lazy
+predicates -- identical trees, path costs equal to 1e-12 relative (SURVEY 8c policy 4)."""
+import numpy as np
+import pytest
+
+import fixtures as fx
+from oracle_fmt import fmt_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _c1_samples(mp, orc, N, seed, spec, fixed=False):
+    """config C1 inputs: sample 1 = init (.1,.1), last = goal (.9,.9), the rest uniform, rejection-
+    filtered by the oracle's is_free_state"""
+    O = orc.Obstacles2D(spec, fixed_point_test=fixed)
+    So = orc.StateSpace([0, 0], [1, 1])
+    cand = fx.uniform_samples(3 * N, 2, seed)
+    cand = cand[orc.states_free(O, So, cand)][:N - 2]
+    return np.vstack([[0.1, 0.1], cand, [0.9, 0.9]])
+
+
+@pytest.mark.parametrize("obst,checker,rm", [("ISRR_2H", "sat2d", 1.0), ("ISRR_2H", "boxes", 1.0),
+                                             ("ISRR_POLY_WITH_SPIKE", "sat2d", 1.5), ("TRI_BALLS", "sat2d", 1.2)])
+def test_fmt_config_c1_matches_oracle(gpu, orc, obst, checker, rm):
+    mp = gpu
+    N = 1000
+    # seed 1 finds the narrow corridor of ISRR_POLY_WITH_SPIKE at N=1000, like the notebook's run did
+    V = _c1_samples(mp, orc, N, 1 if obst == "ISRR_POLY_WITH_SPIKE" else 20240601, fx.ALL_2D[obst])
+    SS = mp.UnitHypercube(2)
+    So = orc.StateSpace([0, 0], [1, 1])
+    if checker == "sat2d":
+        CC, O = mp.PointRobot2D(fx.product_shape(mp, fx.ALL_2D[obst])), orc.Obstacles2D(fx.ALL_2D[obst])
+    else:
+        CC, O = mp.PointRobotNDBoxes([mp.BoxBounds(b) for b in fx.BOXES2D]), orc.Boxes(fx.BOXES2D)
+    P = mp.MPProblem(SS, [0.1, 0.1], mp.PointGoal([0.9, 0.9]), CC, V=mp.MetricNN(V, SS.dist, V[0]))
+    status, cost, _ = mp.fmtstar(P, rm=rm)
+    r = P.solution.metadata["r"]
+    assert abs(r - fx.fmt_radius(N, 2, rm)) < 1e-15
+
+    tree = orc.KDTree(V)
+    cache = {}
+
+    def nbrs(v):
+        if v not in cache:
+            c = tree.rball(r, v - 1, v)
+            cache[v] = (c[1], c[2])
+        return cache[v]
+
+    def edge(y0, x0):
+        ok, n = orc.motions_free_straight(O, So, V[y0:y0 + 1], V[x0:x0 + 1])
+        return bool(ok[0]), n
+
+    ref = fmt_oracle(V, np.all(V == [0.9, 0.9], axis=1), nbrs, nbrs, lambda i: bool(orc.states_free(O, So, V[i:i + 1])[0]), edge)
+    assert ref["solved"] and status == "solved"
+    assert P.solution.metadata["path"] == ref["path"]
+    assert np.array_equal(P.solution.metadata["tree"], ref["tree"])
+    assert abs(cost - ref["cost"]) <= 1e-12 * ref["cost"]
+    assert P.solution.metadata["collision_checks"] == ref["checks"] == CC.count
+    assert 1.0 < cost < 2.2
+    if obst == "ISRR_POLY_WITH_SPIKE":
+        # soft anchor: docs/MotionPlanning.ipynb cell 5 prints cost 1.2346 for this set-up (unseeded)
+        assert abs(cost - 1.2346) < 0.05
+    P.V.close()
+
+
+def test_fmt_sample_free_and_failure_modes(gpu, orc):
+    mp = gpu
+    SS = mp.UnitHypercube(2)
+    CC = mp.PointRobotNDBoxes([mp.BoxBounds(b) for b in fx.BOXES2D])
+    P = mp.MPProblem(SS, [0.1, 0.1], mp.BallGoal([0.9, 0.9], 0.05), CC)
+    status, cost, _ = mp.fmtstar(P, 2000, rm=1.2, ensure_goal_ct=3, seed=5)
+    V = P.V.V
+    assert len(V) == 2000 and np.all(V[0] == [0.1, 0.1])
+    B = orc.Boxes(fx.BOXES2D)
+    assert orc.states_free(B, orc.StateSpace([0, 0], [1, 1]), V).all()          # every sample is free (boxes: correct test)
+    assert all(mp.is_goal_pt(v, P.goal, SS) for v in V[-3:])                    # goal samples in the last slots
+    assert status == "solved" and 1.0 < cost < 2.2
+    # infeasible start -> :failed, cost Inf (fmt.jl:24-29)
+    P2 = mp.MPProblem(SS, [0.08, 0.43], mp.PointGoal([0.9, 0.9]), CC)
+    assert mp.fmtstar(P2, 100) == float("inf") and P2.status == "failed"
+    with pytest.raises(NotImplementedError):                                     # :K is undefined in the reference too
+        mp.fmtstar(P, connections="K")
+
+
+def test_fmt_double_integrator_matches_oracle(gpu, orc):
+    """drift case (config C4 at small N): ControlNN tables + swept LQ edges"""
+    mp = gpu
+    N, r = 1500, 1.0
+    SS = mp.DoubleIntegrator(2, vmax=0.5)
+    rng = np.random.Generator(np.random.PCG64(20240604))
+    lo, hi = SS.lo, SS.hi
+    cand = lo + rng.random((4 * N, 4)) * (hi - lo)
+    B = orc.Boxes(fx.BOXES2D)
+    C = np.hstack([np.eye(2), np.zeros((2, 2))])
+    So = orc.StateSpace(lo, hi, ("matrix", C))
+    cand = cand[orc.states_free(B, So, cand)][:N - 2]
+    init, goal = np.array([0.1, 0.1, 0.0, 0.0]), np.array([0.9, 0.9, 0.0, 0.0])
+    V = np.vstack([init, cand, goal])
+    CC = mp.PointRobotNDBoxes([mp.BoxBounds(b) for b in fx.BOXES2D])
+    P = mp.MPProblem(SS, init, mp.StateGoal(goal), CC, V=mp.QuasiMetricNN(V, SS.dist, init))
+    status, cost, _ = mp.fmtstar(P, r=r)
+    L = orc.DoubleIntegratorLQ(2)
+    TF, TB = L.inball(V, r, True), L.inball(V, r, False)
+    nF = lambda v: (TF[1][TF[0][v - 1] - 1:TF[0][v] - 1], TF[2][TF[0][v - 1] - 1:TF[0][v] - 1])
+    nB = lambda v: (TB[1][TB[0][v - 1] - 1:TB[0][v] - 1], TB[2][TB[0][v - 1] - 1:TB[0][v] - 1])
+    ref = fmt_oracle(V, np.all(V == goal, axis=1), nF, nB, lambda i: bool(orc.states_free(B, So, V[i:i + 1])[0]),
+                     lambda y0, x0: L.is_free_motion(B, So, r, V[y0], V[x0]))
+    assert ref["solved"] and status == "solved"
+    assert P.solution.metadata["path"] == ref["path"]
+    assert np.array_equal(P.solution.metadata["tree"], ref["tree"])
+    assert abs(cost - ref["cost"]) <= 1e-12 * ref["cost"]
+    # soft anchor: the notebook's double-integrator run (vmax=.5, r=1, N=1000) printed 5.72
+    assert 3.5 < cost < 8.5
+    P.V.close()
