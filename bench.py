@@ -9,8 +9,9 @@ point validity (K6) + validity of every stored edge (K7).  metric = collision-ch
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
 N > 1: launched by torch.distributed.run, one rank per GPU; weak scaling -- the sample set grows
-to N x 1M (replicated on every GPU), rank g owns the query columns [g*1M, (g+1)*1M), no data-path
-collective (the per-rank CSC shards concatenate; only the timing is reduced, max over ranks).
+to N x 1M (replicated on every GPU), rank g owns the query columns [g*1M, (g+1)*1M); the per-rank
+CSC shards concatenate, and every step ends with the one exchange the host planner needs: an
+NCCL all-gather of the shard colptrs and edge-validity words (no other data-path collective).
 """
 import argparse
 import json
@@ -237,6 +238,13 @@ def main():
     NN.set_query_range(q0, q1)
     NN.handle()  # inputs resident in HBM before the timed region
     flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    exchange = None
+    if world > 1:
+        from mpb200 import sharding
+        nnz0 = NN.build_table(r)
+        cap = torch.tensor([nnz0], dtype=torch.int64, device="cuda")
+        dist.all_reduce(cap, op=dist.ReduceOp.MAX)
+        exchange = sharding.ValidityExchange(SAMPLES_PER_GPU, (int(cap) * 21 // 20 + 63) // 64)
 
     def device_step():
         nnz = NN.build_table(r)
@@ -269,6 +277,9 @@ def main():
         NN.edges_free(NN.table, CC, SS, fetch=False)
         if it >= args.warmup:
             edge_ms.append(lib.mpb200_last_ms(1))
+        if exchange is not None:
+            exchange.run(NN.table)          # NCCL all-gather of shard colptrs + validity words
+        if it >= args.warmup:
             ev[it - args.warmup][1].record(stream)
     torch.cuda.synchronize()
     if world > 1:
@@ -331,7 +342,8 @@ def main():
             "config": {"workload": "C2: FMT* 2-D unit square, ISRR_2H, N=%d uniform samples (%d query columns per GPU), r=%.7f"
                                    % (n_total, SAMPLES_PER_GPU, r),
                        "l2": "512 MiB flush between timed iterations", "index_type": "int64 (reference ABI)",
-                       "parallelism": "query-range shards x%d, samples+obstacles replicated" % world},
+                       "parallelism": "query-range shards x%d, samples+obstacles replicated%s"
+                                      % (world, ", NCCL all-gather of colptr + validity words per step" if world > 1 else "")},
             "nn_queries_per_sec": queries_all / (ms_per_step / 1e3),
             "edges_per_step": edges_all, "mean_degree": deg,
             "phase_ms": {"grid_build": phases[1] / args.steps, "count_scan": phases[2] / args.steps,

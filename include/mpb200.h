@@ -82,6 +82,11 @@ int mpb200_inball_build(mpb200_samples *s, double r, mpb200_table **table, int64
  * colptr has (q1-q0)+1 entries, relative to the shard (colptr[0] == 1). */
 int mpb200_table_fetch(const mpb200_table *t, int64_t *colptr, int64_t *rowval, double *nzval);
 int mpb200_table_nnz(const mpb200_table *t, int64_t *nnz, int64_t *ncols);
+/* Device pointers of a table's arrays (colptr int64[ncols+1], rowval int64[nnz], nzval f64[nnz],
+ * edge_bits uint64[ceil(nnz/64)] = last mpb200_edges_free / mpb200_lq_edges_free result or NULL),
+ * valid until the next build on / destroy of the handle: lets the caller hand shards to NCCL
+ * (all-gather across the GPUs of a box) without a host round trip. */
+int mpb200_table_device_view(const mpb200_table *t, void **colptr, void **rowval, void **nzval, void **edge_bits);
 int mpb200_table_destroy(mpb200_table *t);
 
 /* ---- obstacle sets ------------------------------------------------------------ */

@@ -65,6 +65,7 @@ SIGNATURES = {
     "mpb200_inball_build": (ctypes.c_int, [c_vp, c_dbl, P(c_vp), P(c_i64)]),
     "mpb200_table_fetch": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp]),
     "mpb200_table_nnz": (ctypes.c_int, [c_vp, P(c_i64), P(c_i64)]),
+    "mpb200_table_device_view": (ctypes.c_int, [c_vp, P(c_vp), P(c_vp), P(c_vp), P(c_vp)]),
     "mpb200_table_destroy": (ctypes.c_int, [c_vp]),
     "mpb200_obstacles2d_create": (ctypes.c_int, [P(ObstaclesDesc), P(c_vp)]),
     "mpb200_boxes_create": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, ctypes.c_int, P(c_vp)]),

@@ -261,6 +261,14 @@ int mpb200_table_nnz(const mpb200_table *t, int64_t *nnz, int64_t *ncols) {
     if (ncols) *ncols = t->ncols;
     return MPB200_OK;
 }
+int mpb200_table_device_view(const mpb200_table *t, void **colptr, void **rowval, void **nzval, void **edge_bits) {
+    MPB_CHECK_ARG(t != nullptr, "table handle is NULL");
+    if (colptr) *colptr = t->colptr.p;
+    if (rowval) *rowval = t->rowval.p;
+    if (nzval) *nzval = t->nzval.p;
+    if (edge_bits) *edge_bits = t->edge_bits.p;
+    return MPB200_OK;
+}
 int mpb200_table_fetch(const mpb200_table *t, int64_t *colptr, int64_t *rowval, double *nzval) {
     MPB_REQUIRE_INIT();
     MPB_CHECK_ARG(t != nullptr, "table handle is NULL");

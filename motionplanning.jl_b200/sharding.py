@@ -1,0 +1,172 @@
+"""Multi-GPU sharding of the precompute: one process per GPU, query-range shards, replicated
+samples and obstacles, and the exchange steps the host planner needs.
+
+The reference has no distributed layer at all (single Julia thread); this is the B200-native
+analogue of its only scaling axis, the sample count N.  Rank g owns the contiguous query
+(column) range shard_range(N, g, G) of every table; the per-rank CSC shards concatenate in rank
+order.  Collectives (torch.distributed: NCCL over NVLink on the GPUs, gloo in the CPU tests):
+  * all-gather of per-column counts            -> the global colptr
+  * all-gather of edge-validity words          -> the global BitVector (shards re-aligned by shift)
+  * all-gather of rowval / nzval (optional)    -> the full table on every rank
+  * all-gather + fixed-order sum of the MC sums (deterministic, unlike a tree all-reduce)
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def shard_range(N, rank, world):
+    """contiguous, balanced column range of `rank` (0-based half-open)"""
+    base, rem = divmod(int(N), int(world))
+    q0 = rank * base + min(rank, rem)
+    return q0, q0 + base + (1 if rank < rem else 0)
+
+
+def _dev():
+    return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+
+
+def _gather_var(x, group=None):
+    """all-gather of 1-D tensors of different lengths: sizes first, then padded payloads"""
+    world = dist.get_world_size(group)
+    n = torch.tensor([x.numel()], dtype=torch.int64, device=x.device)
+    sizes = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n, group=group)
+    sizes = [int(s) for s in sizes]
+    mx = max(max(sizes), 1)
+    pad = torch.zeros(mx, dtype=x.dtype, device=x.device)
+    pad[:x.numel()] = x
+    outs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(outs, pad, group=group)
+    return [o[:s] for o, s in zip(outs, sizes)]
+
+
+def allgather_colptr(local_colptr, group=None):
+    """local 1-based colptr (ncols_g + 1) of every rank -> global 1-based colptr (N + 1), and the
+    0-based entry offset of every rank's shard"""
+    t = torch.as_tensor(np.diff(np.asarray(local_colptr)), dtype=torch.int64).to(_dev())
+    parts = [p.cpu().numpy() for p in _gather_var(t, group)]
+    counts = np.concatenate(parts) if parts else np.zeros(0, dtype=np.int64)
+    colptr = np.empty(len(counts) + 1, dtype=np.int64)
+    colptr[0] = 1
+    np.cumsum(counts, out=colptr[1:])
+    colptr[1:] += 1
+    offs = np.concatenate([[0], np.cumsum([int(p.sum()) for p in parts])])
+    return colptr, offs
+
+
+def concat_bitvectors(parts):
+    """[(uint64 chunks, nbits), ...] -> chunks of the concatenated BitVector (Julia layout)."""
+    total = sum(n for _, n in parts)
+    out = np.zeros((total + 63) // 64, dtype=np.uint64)
+    pos = 0
+    for chunks, n in parts:
+        if n == 0:
+            continue
+        w = np.ascontiguousarray(chunks[:(n + 63) // 64], dtype=np.uint64).copy()
+        if n % 64:
+            w[-1] &= np.uint64((1 << (n % 64)) - 1)
+        word, sh = divmod(pos, 64)
+        if sh == 0:
+            out[word:word + len(w)] |= w
+        else:
+            out[word:word + len(w)] |= w << np.uint64(sh)
+            hi = w >> np.uint64(64 - sh)
+            k = min(len(hi), len(out) - word - 1)
+            out[word + 1:word + 1 + k] |= hi[:k]
+        pos += n
+    return out
+
+
+def allgather_bits(local_chunks, nbits, group=None):
+    """edge-validity words of every rank -> the global BitVector chunks (on every rank)"""
+    x = torch.as_tensor(np.ascontiguousarray(local_chunks[:(nbits + 63) // 64]).view(np.int64)).to(_dev())
+    words = _gather_var(x, group)
+    n = torch.tensor([nbits], dtype=torch.int64, device=x.device)
+    ns = [torch.zeros_like(n) for _ in range(dist.get_world_size(group))]
+    dist.all_gather(ns, n, group=group)
+    return concat_bitvectors([(w.cpu().numpy().view(np.uint64), int(k)) for w, k in zip(words, ns)])
+
+
+def allgather_table(rowval, nzval, group=None):
+    """variable-size all-gather of the shard's rowval / nzval -> full arrays on every rank"""
+    rv = _gather_var(torch.as_tensor(np.asarray(rowval), dtype=torch.int64).to(_dev()), group)
+    nz = _gather_var(torch.as_tensor(np.asarray(nzval), dtype=torch.float64).to(_dev()), group)
+    return np.concatenate([p.cpu().numpy() for p in rv]), np.concatenate([p.cpu().numpy() for p in nz])
+
+
+def allreduce_mc(res, group=None):
+    """sum the Monte-Carlo shard sums in rank order (bit-reproducible for a fixed world size)"""
+    x = torch.tensor([res["S1"], res["S2"], res["S0"], float(res["n"]), float(res["hits"])], dtype=torch.float64,
+                     device=_dev())
+    outs = [torch.empty_like(x) for _ in range(dist.get_world_size(group))]
+    dist.all_gather(outs, x, group=group)
+    tot = dict(S1=0.0, S2=0.0, S0=0.0, n=0, hits=0)
+    for o in outs:                                     # fixed order
+        o = o.cpu().tolist()
+        tot["S1"] += o[0]; tot["S2"] += o[1]; tot["S0"] += o[2]; tot["n"] += int(o[3]); tot["hits"] += int(o[4])
+    n = max(tot["n"], 1)
+    p = tot["S1"] / n
+    tot["p"], tot["se"] = p, (max(tot["S2"] / n - p * p, 0.0) / n) ** 0.5
+    return tot
+
+
+# ---- device-resident exchange (NCCL): no host round trip ----------------------------------------
+class _CudaArray:
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+def device_tensor(ptr, n, typestr):
+    """torch view (no copy) of a device array owned by libmpb200: typestr "<i8", "<f8", "<u8" ..."""
+    return torch.as_tensor(_CudaArray(ptr, n, typestr), device=torch.device("cuda", torch.cuda.current_device()))
+
+
+def table_device_tensors(table):
+    """(colptr, rowval, nzval, edge_words) torch views of a DeviceTable's arrays"""
+    import ctypes
+    from . import _lib
+    cp, rv, nz, eb = _lib.c_vp(), _lib.c_vp(), _lib.c_vp(), _lib.c_vp()
+    _lib.check(_lib.lib().mpb200_table_device_view(table.h, ctypes.byref(cp), ctypes.byref(rv), ctypes.byref(nz),
+                                                   ctypes.byref(eb)))
+    words = (table.nnz + 63) // 64
+    return (device_tensor(cp.value, table.ncols + 1, "<i8"),
+            device_tensor(rv.value, table.nnz, "<i8") if table.nnz else None,
+            device_tensor(nz.value, table.nnz, "<f8") if table.nnz else None,
+            device_tensor(eb.value, words, "<i8") if (eb.value and words) else None)
+
+
+class ValidityExchange:
+    """Reusable buffers for the per-step exchange the host planner needs from every GPU: the
+    shard colptrs (equal size) and the edge-validity words (padded to a common capacity)."""
+
+    def __init__(self, ncols, word_capacity, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.cap = int(word_capacity)
+        self.col_all = torch.empty(self.world * (ncols + 1), dtype=torch.int64, device=dev)
+        self.bits_pad = torch.zeros(self.cap, dtype=torch.int64, device=dev)
+        self.bits_all = torch.empty(self.world * self.cap, dtype=torch.int64, device=dev)
+
+    def run(self, table):
+        colptr, _, _, words = table_device_tensors(table)
+        if words is not None:
+            if words.numel() > self.cap:
+                raise RuntimeError("validity exchange capacity exceeded")
+            self.bits_pad[:words.numel()].copy_(words)
+        dist.all_gather_into_tensor(self.col_all, colptr, group=self.group)
+        dist.all_gather_into_tensor(self.bits_all, self.bits_pad, group=self.group)
+
+    def assemble(self):
+        """host-side: global colptr + BitVector chunks from the gathered shards"""
+        ncol1 = self.col_all.numel() // self.world
+        cols = self.col_all.cpu().numpy().reshape(self.world, ncol1)
+        bits = self.bits_all.cpu().numpy().view(np.uint64).reshape(self.world, self.cap)
+        counts = np.concatenate([np.diff(c) for c in cols])
+        colptr = np.empty(len(counts) + 1, dtype=np.int64)
+        colptr[0] = 1
+        np.cumsum(counts, out=colptr[1:])
+        colptr[1:] += 1
+        parts = [(bits[g], int(cols[g][-1] - 1)) for g in range(self.world)]
+        return colptr, concat_bitvectors(parts)
