@@ -3,7 +3,7 @@
 
 Workload "C2": FMT* precompute in the 2-D unit square, N = 1M synthetic uniform samples per
 GPU, obstacle set ISRR_2H: one step = uniform-grid build + r-ball neighbour table (K1+K2) +
-point validity (K6) + validity of every stored edge (K7).  metric = collision-checked edges/s
+point validity (K6) + validity of every stored edge (K7: column classify + per-edge kernel).  metric = collision-checked edges/s
 (the NN-queries/s figure of the same step is reported beside it).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
@@ -246,14 +246,8 @@ def main():
         dist.all_reduce(cap, op=dist.ReduceOp.MAX)
         exchange = sharding.ValidityExchange(SAMPLES_PER_GPU, (int(cap) * 21 // 20 + 63) // 64)
 
-    def device_step():
-        nnz = NN.build_table(r)
-        NN.points_free(CC, SS, fetch=False)
-        NN.edges_free(NN.table, CC, SS, fetch=False)
-        return nnz
-
     phases = np.zeros(6)
-    edge_ms = []
+    edge_ms, point_ms = [], []
     launches0 = launches1 = 0
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     sampler = ClockSampler(local)
@@ -270,11 +264,13 @@ def main():
         flush.zero_()  # L2 flush between iterations (outside the event pair)
         if it >= args.warmup:
             ev[it - args.warmup][0].record(stream)
-        nnz = NN.build_table(r)
+        nnz = NN.build_table(r)                       # K1 + K2
         if it >= args.warmup:
             phases[:5] += [lib.mpb200_last_ms(k) for k in range(5)]
-        NN.points_free(CC, SS, fetch=False)
-        NN.edges_free(NN.table, CC, SS, fetch=False)
+        NN.points_free(CC, SS, fetch=False)           # K6
+        if it >= args.warmup:
+            point_ms.append(lib.mpb200_last_ms(1))
+        NN.edges_free(NN.table, CC, SS, fetch=False)  # K7
         if it >= args.warmup:
             edge_ms.append(lib.mpb200_last_ms(1))
         if exchange is not None:
@@ -315,9 +311,8 @@ def main():
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
-        cache = NN2.precompute(r)         # H2D samples, build, D2H colptr/rowval/nzval
+        cache, Eb, _ = NN2.precompute_checked(r, CC, SS)   # H2D samples, fused build, D2H colptr/rowval/nzval/edge bits
         Fb = NN2.points_free(CC, SS)      # D2H point bits
-        Eb, _ = NN2.edges_free(NN2.table, CC, SS)   # D2H edge bits
         t1 = time.perf_counter()
         if it >= 2:
             e2e_times.append(t1 - t0)
@@ -348,7 +343,8 @@ def main():
             "edges_per_step": edges_all, "mean_degree": deg,
             "phase_ms": {"grid_build": phases[1] / args.steps, "count_scan": phases[2] / args.steps,
                          "host_gap": phases[3] / args.steps, "fill": fill_ms,
-                         "edges_kernel": float(np.mean(edge_ms)), "inball_total": phases[0] / args.steps},
+                         "points_kernel": float(np.mean(point_ms)), "edges_kernels": float(np.mean(edge_ms)),
+                         "inball_total": phases[0] / args.steps},
             "gpu_launches": int(launches1 - launches0),
             "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps,
             "clocks": clocks,

@@ -137,6 +137,13 @@ int mpb200_points_free(const mpb200_samples *s, const mpb200_obstacles *o, const
  * CC.count would have been incremented by. */
 int mpb200_edges_free(const mpb200_samples *s, const mpb200_table *t, const mpb200_obstacles *o,
                       const mpb200_space_desc *ss, uint64_t *bitchunks, int64_t *checks);
+/* Convenience for config "batched r-ball neighbours + edge validity precompute": build the
+ * Euclidean r-ball table and the validity of every stored edge with one call (= mpb200_inball_build
+ * followed by mpb200_edges_free); the edge bits stay on the device with the table
+ * (mpb200_table_fetch_edge_bits / mpb200_table_device_view). */
+int mpb200_inball_build_checked(mpb200_samples *s, double r, const mpb200_obstacles *o, const mpb200_space_desc *ss,
+                                mpb200_table **table, int64_t *nnz, int64_t *checks);
+int mpb200_table_fetch_edge_bits(const mpb200_table *t, uint64_t *bitchunks);
 /* State-level batches for callers that hold states, not indices (sampling.jl:25,
  * postprocessors.jl:11,21): n states / n straight segments, AoS d x n; out: 1 byte each. */
 int mpb200_states_free(const double *v_aos, int64_t n, int d, const mpb200_obstacles *o,

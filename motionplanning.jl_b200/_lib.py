@@ -64,6 +64,8 @@ SIGNATURES = {
     "mpb200_samples_set_query_range": (ctypes.c_int, [c_vp, c_i64, c_i64]),
     "mpb200_inball_build": (ctypes.c_int, [c_vp, c_dbl, P(c_vp), P(c_i64)]),
     "mpb200_table_fetch": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp]),
+    "mpb200_inball_build_checked": (ctypes.c_int, [c_vp, c_dbl, c_vp, P(SpaceDesc), P(c_vp), P(c_i64), P(c_i64)]),
+    "mpb200_table_fetch_edge_bits": (ctypes.c_int, [c_vp, c_vp]),
     "mpb200_table_nnz": (ctypes.c_int, [c_vp, P(c_i64), P(c_i64)]),
     "mpb200_table_device_view": (ctypes.c_int, [c_vp, P(c_vp), P(c_vp), P(c_vp), P(c_vp)]),
     "mpb200_table_destroy": (ctypes.c_int, [c_vp]),

@@ -78,6 +78,7 @@ int phases_collect(int n) {
 int compute_bbox(mpb200_samples *s);
 int grid_inball_build(mpb200_samples *s, double r, mpb200_table *t);
 int brute_inball_build(mpb200_samples *s, double r, mpb200_table *t);
+
 int points_free_device(const double *dV, int64_t n, int d, const mpb200_obstacles *o, const mpb200_space_desc *ss,
                        uint32_t *d_bits32, uint8_t *d_bytes);
 int edges_free_device(const double *dV, int d, const mpb200_table *t, const mpb200_obstacles *o,
@@ -240,7 +241,7 @@ int mpb200_inball_build(mpb200_samples *s, double r, mpb200_table **table, int64
         if (!rc) {
             int64_t one = 1;
             cudaMemcpy(t->colptr.p, &one, sizeof(one), cudaMemcpyHostToDevice);
-            t->ncols = 0; t->col0 = 0; t->nnz = 0; t->r = r;
+            t->ncols = 0; t->col0 = 0; t->nnz = 0; t->r = r; t->euclid = true;
         }
     } else if (s->d <= 3 && s->d >= 2) {
         rc = grid_inball_build(s, r, t);
@@ -253,6 +254,24 @@ int mpb200_inball_build(mpb200_samples *s, double r, mpb200_table **table, int64
     }
     *table = t;
     if (nnz) *nnz = t->nnz;
+    return MPB200_OK;
+}
+int mpb200_inball_build_checked(mpb200_samples *s, double r, const mpb200_obstacles *o, const mpb200_space_desc *ss,
+                                mpb200_table **table, int64_t *nnz, int64_t *checks) {
+    MPB_REQUIRE_INIT();
+    MPB_CHECK_ARG(s != nullptr && table != nullptr && o != nullptr && ss != nullptr, "NULL handle");
+    MPB_CHECK_ARG(r >= 0 && r == r, "r must be a non-negative number");
+    if (int rc = mpb200_inball_build(s, r, table, nnz)) return rc;
+    return mpb200_edges_free(s, *table, o, ss, nullptr, checks);
+}
+int mpb200_table_fetch_edge_bits(const mpb200_table *t, uint64_t *bitchunks) {
+    MPB_REQUIRE_INIT();
+    MPB_CHECK_ARG(t != nullptr && bitchunks != nullptr, "NULL argument");
+    MPB_CHECK_ARG(t->edge_bits.p != nullptr || t->nnz == 0, "no edge validity has been computed for this table");
+    const size_t words = (size_t)ceil_div(t->nnz, 64);
+    cudaStream_t st = ctx().stream;
+    if (words) MPB_CUDA(cudaMemcpyAsync(bitchunks, t->edge_bits.p, sizeof(uint64_t) * words, cudaMemcpyDeviceToHost, st));
+    MPB_CUDA(cudaStreamSynchronize(st));
     return MPB200_OK;
 }
 int mpb200_table_nnz(const mpb200_table *t, int64_t *nnz, int64_t *ncols) {
@@ -286,7 +305,7 @@ int mpb200_table_destroy(mpb200_table *t) {
     if (!t) return MPB200_OK;
     if (ctx().ready) cudaStreamSynchronize(ctx().stream);
     t->colptr.release(); t->rowval.release(); t->nzval.release(); t->counts.release(); t->masks.release();
-    t->edge_bits.release(); t->scratch.release();
+    t->edge_bits.release(); t->scratch.release(); t->col_list.release();
     delete t;
     return MPB200_OK;
 }

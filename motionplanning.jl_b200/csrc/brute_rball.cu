@@ -153,6 +153,7 @@ static int brute_build(mpb200_samples *s, double r, mpb200_table *t) {
     t->col0 = s->q0;
     t->nnz = nnz;
     t->r = r;
+    t->euclid = true;
     return 0;
 }
 

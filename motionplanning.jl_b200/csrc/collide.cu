@@ -8,6 +8,8 @@
 // Julia BitVector words (bit k&63 of word k>>6 == bit k&31 of 32-bit word k>>5, little endian).
 #include "common.cuh"
 #include "predicates.cuh"
+#include <climits>
+#include <cstdlib>
 
 namespace mpb {
 
@@ -77,9 +79,11 @@ __global__ void __launch_bounds__(kThreads, (DW <= 3) ? 3 : 1)
 edges_free_kernel(const double *__restrict__ V, const int64_t *__restrict__ colptr,
                   const int64_t *__restrict__ rowval, int64_t ncols, int64_t col0, int64_t nnz, SpaceDev S,
                   const double *__restrict__ g_table, int table_words, int M, bool use_smem,
-                  uint32_t *__restrict__ bits32, unsigned long long *__restrict__ checks) {
+                  uint32_t *__restrict__ bits32, unsigned long long *__restrict__ checks,
+                  const int *__restrict__ col_list, int64_t n_items, const unsigned long long *__restrict__ n_items_dev) {
     extern __shared__ double s_table[];
     const double *T = stage_table(g_table, table_words, use_smem, s_table);
+    if (n_items_dev) n_items = (int64_t)*n_items_dev;  // list length produced by classify_columns
     const int lane = threadIdx.x & 31;
     const int64_t gwarp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -92,12 +96,13 @@ edges_free_kernel(const double *__restrict__ V, const int64_t *__restrict__ colp
         const double *cb = O.cull_box(lane);
         cull_xl = cb[0]; cull_xh = cb[1]; cull_yl = cb[2]; cull_yh = cb[3];
     }
-    int64_t c = gwarp, beg = 0, end = 0;
-    if (c < ncols) { beg = colptr[c] - 1; end = colptr[c + 1] - 1; }
-    while (c < ncols) {
-        const int64_t cn = c + nwarps;
-        int64_t begn = 0, endn = 0;
-        if (cn < ncols) { begn = colptr[cn] - 1; endn = colptr[cn + 1] - 1; }  // prefetch
+    // work item i -> column (optionally through a column list: the big-column leftovers of the fused build)
+    int64_t it = gwarp, c = 0, beg = 0, end = 0;
+    if (it < n_items) { c = col_list ? col_list[it] : it; beg = colptr[c] - 1; end = colptr[c + 1] - 1; }
+    while (it < n_items) {
+        const int64_t itn = it + nwarps;
+        int64_t cn = 0, begn = 0, endn = 0;
+        if (itn < n_items) { cn = col_list ? col_list[itn] : itn; begn = colptr[cn] - 1; endn = colptr[cn + 1] - 1; }  // prefetch
         if (beg < end) {
             double b[N], q[DW];
 #pragma unroll
@@ -134,7 +139,7 @@ edges_free_kernel(const double *__restrict__ V, const int64_t *__restrict__ colp
                 }
             }
         }
-        c = cn; beg = begn; end = endn;
+        it = itn; c = cn; beg = begn; end = endn;
     }
     // per-CTA reduction of the CC.count increment
     __shared__ unsigned long long s_checks[kThreads / 32];
@@ -146,6 +151,88 @@ edges_free_kernel(const double *__restrict__ V, const int64_t *__restrict__ colp
         unsigned long long t = 0;
         for (int w = 0; w < kThreads / 32; ++w) t += s_checks[w];
         if (t) atomicAdd(checks, t);
+    }
+}
+
+// One thread per column of a Euclidean r-ball table (state == workspace): every stored neighbour
+// lies within r of the column point x, so all edges of the column live inside the box x +- r.  If
+// that box is inside the state bounds and overlaps no obstacle's cull box, every edge passes
+// in_state_space and is rejected by every obstacle's own AABB gate: the whole column is free.  Its
+// validity bits are set here (<= 3 atomicOr), `checks` advances by the column length, and the
+// column never reaches the per-edge kernel.  Anything else is appended to `list`.
+template <int DW, int KIND>
+__global__ void __launch_bounds__(kThreads)
+classify_columns(const double *__restrict__ V, const int64_t *__restrict__ colptr, int64_t ncols, int64_t col0,
+                 double r, SpaceDev S, const double *__restrict__ g_table, int table_words, int M, bool use_smem,
+                 unsigned long long *__restrict__ bits64, unsigned long long *__restrict__ checks,
+                 int *__restrict__ list, unsigned long long *__restrict__ n_list) {
+    extern __shared__ double s_table[];
+    const double *T = stage_table(g_table, table_words, use_smem, s_table);
+    const int lane = threadIdx.x & 31;
+    unsigned long long my_checks = 0;
+    const int64_t n_pad = (ncols + 31) & ~int64_t(31);
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_pad; c += (int64_t)gridDim.x * blockDim.x) {
+        bool flagged = false;
+        if (c < ncols) {
+            const int64_t beg = colptr[c] - 1, end = colptr[c + 1] - 1;
+            if (beg < end) {
+                double lo[DW], hi[DW];
+                bool trivial = true;
+#pragma unroll
+                for (int i = 0; i < DW; ++i) {
+                    const double x = V[(col0 + c) * DW + i];
+                    const double pad = r * (1.0 + 1e-9) + 4.5e-16 * fabs(x);  // covers every rounding in x +- r
+                    lo[i] = x - pad; hi[i] = x + pad;
+                    trivial = trivial && (S.lo[i] <= lo[i] && hi[i] <= S.hi[i]);
+                }
+                if (trivial) {
+                    if (KIND == 0) {
+                        Obs2 O(T);
+                        for (int s = 0; s < O.S && trivial; ++s) {
+                            const double *cb = O.cull_box(s);
+                            if (overlapping(lo[0], hi[0], cb[0], cb[1]) && overlapping(lo[DW > 1 ? 1 : 0], hi[DW > 1 ? 1 : 0], cb[2], cb[3]))
+                                trivial = false;
+                        }
+                    } else {
+                        const double *bl = T, *bh = T + (size_t)M * DW;
+                        for (int k = 0; k < M && trivial; ++k) {
+                            bool sep = false;
+#pragma unroll
+                            for (int i = 0; i < DW; ++i) sep = sep || (bh[k * DW + i] < lo[i] || bl[k * DW + i] > hi[i]);
+                            if (!sep) trivial = false;
+                        }
+                    }
+                }
+                if (trivial) {
+                    my_checks += (unsigned long long)(end - beg);
+                    for (int64_t w = beg >> 6; w <= (end - 1) >> 6; ++w) {
+                        const int64_t b0 = w << 6;
+                        const int from = (int)(beg > b0 ? beg - b0 : 0), to = (int)(end < b0 + 64 ? end - b0 : 64);
+                        const unsigned long long m = (to - from == 64) ? ~0ULL : (((1ULL << (to - from)) - 1ULL) << from);
+                        atomicOr(&bits64[w], m);
+                    }
+                } else {
+                    flagged = true;
+                }
+            }
+        }
+        const unsigned fm = __ballot_sync(0xffffffffu, flagged);
+        if (fm) {
+            unsigned long long basei = 0;
+            if (lane == 0) basei = atomicAdd(n_list, (unsigned long long)__popc(fm));
+            basei = __shfl_sync(0xffffffffu, basei, 0);
+            if (flagged) list[basei + __popc(fm & ((1u << lane) - 1u))] = (int)c;
+        }
+    }
+    __shared__ unsigned long long s_checks[kThreads / 32];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) my_checks += __shfl_xor_sync(0xffffffffu, my_checks, o);
+    if (lane == 0) s_checks[threadIdx.x >> 5] = my_checks;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long tt = 0;
+        for (int w = 0; w < kThreads / 32; ++w) tt += s_checks[w];
+        if (tt) atomicAdd(checks, tt);
     }
 }
 
@@ -279,13 +366,58 @@ int points_free_device(const double *dV, int64_t n, int d, const mpb200_obstacle
     return 0;
 }
 
+int edges_free_device_cols(const double *dV, int d, const mpb200_table *t, const mpb200_obstacles *o,
+                           const SpaceDev &S, uint32_t *d_bits32, unsigned long long *d_checks, const int *col_list,
+                           int64_t n_list, const unsigned long long *n_list_dev = nullptr);
+
 int edges_free_device(const double *dV, int d, const mpb200_table *t, const mpb200_obstacles *o,
                       const mpb200_space_desc *ss, uint32_t *d_bits32, unsigned long long *d_checks) {
     SpaceDev S;
     int dw;
     if (int rc = make_space(ss, d, &S, &dw)) return rc;
     if (int rc = check_obstacles(o, dw)) return rc;
-    LaunchCfg L = make_cfg(o, t->ncols * 32);
+    static const bool no_classify = getenv("MPB200_NO_CLASSIFY") != nullptr;
+    if (!(t->euclid && S.s2w_kind == 0 && t->ncols > 0 && t->ncols < INT_MAX) || no_classify)
+        return edges_free_device_cols(dV, d, t, o, S, d_bits32, d_checks, nullptr, t->ncols);
+    // classify pass: trivially-free columns are finished here, the rest go through the per-edge kernel
+    mpb200_table *tm = const_cast<mpb200_table *>(t);
+    if (int rc = tm->col_list.reserve(sizeof(int) * (size_t)(t->ncols + 4) + 16)) return rc;
+    unsigned long long *n_list = tm->col_list.as<unsigned long long>();
+    int *list = reinterpret_cast<int *>(n_list + 2);
+    cudaStream_t st = ctx().stream;
+    MPB_CUDA(cudaMemsetAsync(n_list, 0, 16, st));
+    LaunchCfg L = make_cfg(o, t->ncols);
+    unsigned long long *bits64 = reinterpret_cast<unsigned long long *>(d_bits32);
+#define CALLC(DW_, K_)                                                                                         \
+    do {                                                                                                       \
+        if (int rc = prep_kernel(classify_columns<DW_, K_>, L.smem)) return rc;                                \
+        classify_columns<DW_, K_><<<L.grid, kThreads, L.smem, st>>>(dV, t->colptr.as<int64_t>(), t->ncols, t->col0, \
+                                                                    t->r, S, L.table, L.words, L.M, L.use_smem, \
+                                                                    bits64, d_checks, list, n_list);           \
+    } while (0)
+    if (o->kind == 0) {
+        if (dw != 2) return fail(MPB200_EARG, "2-D obstacles need a 2-D workspace");
+        CALLC(2, 0);
+    } else {
+        switch (dw) {
+        case 1: CALLC(1, 1); break; case 2: CALLC(2, 1); break; case 3: CALLC(3, 1); break; case 4: CALLC(4, 1); break;
+        case 5: CALLC(5, 1); break; case 6: CALLC(6, 1); break; case 7: CALLC(7, 1); break; case 8: CALLC(8, 1); break;
+        case 9: CALLC(9, 1); break; case 10: CALLC(10, 1); break;
+        default: return edges_free_device_cols(dV, d, t, o, S, d_bits32, d_checks, nullptr, t->ncols);
+        }
+    }
+#undef CALLC
+    MPB_LAUNCHED();
+    return edges_free_device_cols(dV, d, t, o, S, d_bits32, d_checks, list, -1, n_list);
+}
+
+int edges_free_device_cols(const double *dV, int d, const mpb200_table *t, const mpb200_obstacles *o,
+                           const SpaceDev &S, uint32_t *d_bits32, unsigned long long *d_checks, const int *col_list,
+                           int64_t n_list, const unsigned long long *n_list_dev) {
+    const int dw = S.dw;
+    (void)d;
+    if (int rc = check_obstacles(o, dw)) return rc;
+    LaunchCfg L = make_cfg(o, (n_list_dev ? t->ncols : n_list) * 32);
     cudaStream_t st = ctx().stream;
     const int64_t *colptr = t->colptr.as<int64_t>();
     const int64_t *rowval = t->rowval.as<int64_t>();
@@ -294,7 +426,8 @@ int edges_free_device(const double *dV, int d, const mpb200_table *t, const mpb2
         if (int rc = prep_kernel(edges_free_kernel<N_, DW_, K_>, L.smem)) return rc;                       \
         edges_free_kernel<N_, DW_, K_><<<L.grid, kThreads, L.smem, st>>>(dV, colptr, rowval, t->ncols, t->col0, \
                                                                          t->nnz, S, L.table, L.words, L.M, \
-                                                                         L.use_smem, d_bits32, d_checks);  \
+                                                                         L.use_smem, d_bits32, d_checks, col_list, \
+                                                                         n_list, n_list_dev);              \
     } while (0)
     MPB_DISPATCH_DIMS(S.n, dw, o->kind, CALL);
 #undef CALL

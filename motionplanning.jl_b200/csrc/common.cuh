@@ -83,6 +83,7 @@ struct mpb200_table {
     int64_t col0 = 0;      // first global column (0-based)
     int64_t nnz = 0;
     double r = 0;
+    bool euclid = false;   // Euclidean r-ball table: every stored neighbour lies within r of its column point
     mpb::DevBuf colptr;    // int64 (ncols+1), 1-based, relative to the shard
     mpb::DevBuf rowval;    // int64 nnz, 1-based global row ids
     mpb::DevBuf nzval;     // f64 nnz
@@ -90,6 +91,7 @@ struct mpb200_table {
     mpb::DevBuf masks;     // 128-bit hit mask per query column (scratch between count and fill)
     mpb::DevBuf edge_bits; // uint64 ceil(nnz/64): last mpb200_edges_free result
     mpb::DevBuf scratch;   // big-column spill etc.
+    mpb::DevBuf col_list;  // int32 ncols + counter: columns that need per-edge checks
 };
 
 struct mpb200_samples {

@@ -12,7 +12,9 @@
 // per-warp shared-memory stage, rank-sorted by sample index there, and written as one
 // contiguous Int64/Float64 burst per column.
 #include "common.cuh"
+#include "predicates.cuh"
 #include "scan.cuh"
+#include <cstdlib>
 
 namespace mpb {
 
@@ -153,7 +155,6 @@ __device__ __forceinline__ bool run_span(const GridDev &g, const int *c, int run
 // lane is busy.  q_order (optional) lists the cell-order positions owned by this shard.
 constexpr int kQThreads = 128;
 constexpr int kListCap = 64;                  // hits staged per query thread; more -> warp path
-constexpr int kListStride = kQThreads + 1;    // padded: conflict-free column reads
 
 constexpr int kMaskBits = 128;  // candidates per query covered by the hit mask
 
@@ -248,42 +249,55 @@ __device__ __forceinline__ void bitonic64(unsigned &k0, unsigned &k1, int lane) 
     }
 }
 
-// Fill: each thread stages the cell-order positions of its query's hits (unsorted) in shared
-// memory; then the warp walks over its 32 columns two at a time, sorts each one by sample index
-// in registers (bitonic over lanes; the key carries the stage slot in its low 6 bits), fetches
-// the neighbour position from the cell-ordered copy (cache-friendly), recomputes the exact
-// distance and writes the column as one contiguous Int64 / Float64 burst.  Columns longer than
-// kListCap are left to rball_fill_big.  Requires N < 2^26 (key packing); otherwise the host
-// routes every column through rball_fill_big.
+// Fill.  Thread t owns query t of the cell order and keeps that query's point, column base, count,
+// 128-bit hit mask and candidate spans in registers; the warp then walks over its 32 columns, U at
+// a time.  For a column, lane e selects the e-th set bit of the mask (__fns), maps it to a cell-
+// order position, loads the sample index, and the column is sorted by index with a register
+// bitonic network over the lanes (key = index << 6 | source slot).  The neighbour position comes
+// from the cell-ordered copy (cache-friendly), the exact distance is recomputed, and the column
+// is written as one contiguous Int64/Float64 burst.  No shared memory, no re-evaluation of
+// distances.  Columns with more than kListCap entries or more than kMaskBits candidates are left
+// to rball_fill_big.  Requires N < 2^26 (key packing).
 template <int D>
-__device__ __forceinline__ void emit_entry(const double *__restrict__ sorted_pos, int kpos, unsigned idx,
-                                           const double *pc, long long at, int64_t *__restrict__ rowval,
-                                           double *__restrict__ nzval) {
-    double b[D];
-#pragma unroll
-    for (int i = 0; i < D; ++i) b[i] = sorted_pos[(size_t)kpos * D + i];
+__device__ __forceinline__ void emit_entry(const double *b, unsigned idx, const double *pc, long long at,
+                                           int64_t *__restrict__ rowval, double *__restrict__ nzval) {
     rowval[at] = (int64_t)idx + 1;
     nzval[at] = sqrt(sqdist<D>(pc, b));
 }
 
-constexpr int kColsPerStep = 4;  // columns sorted concurrently by one warp (independent chains)
+// position (0..127) of the n-th (0-based) set bit of the 128-bit mask (m0 = bits 0..63)
+__device__ __forceinline__ int nth_set_bit(unsigned long long m0, unsigned long long m1, int n) {
+    const int c0 = __popcll(m0);
+    const unsigned long long m = (n < c0) ? m0 : m1;
+    int nn = (n < c0) ? n : n - c0;
+    int off = (n < c0) ? 0 : 64;
+    const unsigned lo = (unsigned)m, hi = (unsigned)(m >> 32);
+    const int cl = __popc(lo);
+    const unsigned w = (nn < cl) ? lo : hi;
+    off += (nn < cl) ? 0 : 32;
+    nn = (nn < cl) ? nn : nn - cl;
+    return off + (int)__fns(w, 0, nn + 1);
+}
 
-template <int D>
+// U = columns sorted concurrently by one warp (independent dependency chains vs register budget)
+template <int D, int U>
 __global__ void __launch_bounds__(kQThreads)
 rball_fill(const double *__restrict__ sorted_pos, const int *__restrict__ sorted_idx,
            const int *__restrict__ q_order, const ulonglong2 *__restrict__ masks, int64_t nq, int64_t q0, GridDev g,
            const int *__restrict__ cell_start, const int64_t *__restrict__ colptr, int64_t *__restrict__ rowval,
            double *__restrict__ nzval) {
     constexpr int kRuns = (D == 2) ? 3 : 9;
-    constexpr int U = kColsPerStep;
-    __shared__ int s_list[kListCap * kListStride];
     const int lane = threadIdx.x & 31;
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int k_mine = 0;
     long long base = 0;
+    unsigned long long m0 = 0, m1 = 0;
+    int begs[kRuns], lens[kRuns];
     double p[D];
 #pragma unroll
     for (int i = 0; i < D; ++i) p[i] = 0.0;
+#pragma unroll
+    for (int r = 0; r < kRuns; ++r) { begs[r] = 0; lens[r] = 0; }
     if (t < nq) {
         const int pos = q_order ? q_order[t] : (int)t;
 #pragma unroll
@@ -291,57 +305,59 @@ rball_fill(const double *__restrict__ sorted_pos, const int *__restrict__ sorted
         const int64_t w = sorted_idx[pos] - q0;
         base = colptr[w] - 1;
         k_mine = (int)(colptr[w + 1] - colptr[w]);
-        int begs[kRuns], lens[kRuns];
         const int total = query_spans<D>(g, p, cell_start, begs, lens);
         if (k_mine > kListCap || total > kMaskBits) k_mine = 0;  // handled by rball_fill_big
-        if (k_mine > 0) {
-            // phase A: decode the hit mask into cell-order positions (no distance is re-evaluated)
-            const ulonglong2 mk = masks[t];
-            int n = 0;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                unsigned long long m = h ? mk.y : mk.x;
-                while (m) {
-                    int j = __ffsll((long long)m) - 1 + 64 * h;
-                    m &= m - 1;
-                    int kp = 0;
-#pragma unroll
-                    for (int run = 0; run < kRuns; ++run) {  // run containing candidate j
-                        const bool here = (j >= 0) && (j < lens[run]);
-                        kp = here ? begs[run] + j : kp;
-                        j = here ? -1 : j - lens[run];
-                    }
-                    s_list[n * kListStride + threadIdx.x] = kp;
-                    ++n;
-                }
-            }
-        }
+        const ulonglong2 mk = masks[t];
+        m0 = mk.x; m1 = mk.y;
     }
-    __syncwarp();
-    // phase B: the warp sorts and writes its 32 columns, U at a time
-    const int tid0 = threadIdx.x & ~31;
     for (int cl0 = 0; cl0 < 32; cl0 += U) {
         int kc[U];
-        unsigned key[U];
         long long basec[U];
         double pc[U][D];
+        int kpos[U][2];
+        unsigned key[U][2];
         int kmax = 0;
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             kc[u] = __shfl_sync(0xffffffffu, k_mine, cl0 + u);
-            basec[u] = __shfl_sync(0xffffffffu, base, cl0 + u);
-#pragma unroll
-            for (int i = 0; i < D; ++i) pc[u][i] = __shfl_sync(0xffffffffu, p[i], cl0 + u);
             kmax = max(kmax, kc[u]);
         }
         if (kmax == 0) continue;
-        if (kmax <= 32) {
+        const int rounds = (kmax > 32) ? 2 : 1;  // warp-uniform
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                key[u] = 0xffffffffu;
-                if (lane < kc[u])
-                    key[u] = ((unsigned)sorted_idx[s_list[lane * kListStride + tid0 + cl0 + u]] << 6) | (unsigned)lane;
+        for (int u = 0; u < U; ++u) {
+            basec[u] = __shfl_sync(0xffffffffu, base, cl0 + u);
+            const unsigned long long c_m0 = __shfl_sync(0xffffffffu, m0, cl0 + u);
+            const unsigned long long c_m1 = __shfl_sync(0xffffffffu, m1, cl0 + u);
+#pragma unroll
+            for (int i = 0; i < D; ++i) pc[u][i] = __shfl_sync(0xffffffffu, p[i], cl0 + u);
+            int cb_[kRuns], cn_[kRuns];
+#pragma unroll
+            for (int r = 0; r < kRuns; ++r) {
+                cb_[r] = __shfl_sync(0xffffffffu, begs[r], cl0 + u);
+                cn_[r] = __shfl_sync(0xffffffffu, lens[r], cl0 + u);
             }
+            // element e = lane + 32 h: candidate number -> cell-order position -> sort key
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                key[u][h] = 0xffffffffu;
+                kpos[u][h] = 0;
+                const int e = lane + 32 * h;
+                if (h < rounds && e < kc[u]) {
+                    int j = nth_set_bit(c_m0, c_m1, e);
+                    int kp = 0;
+#pragma unroll
+                    for (int r = 0; r < kRuns; ++r) {  // run containing candidate j
+                        const bool here = (j >= 0) && (j < cn_[r]);
+                        kp = here ? cb_[r] + j : kp;
+                        j = here ? -1 : j - cn_[r];
+                    }
+                    kpos[u][h] = kp;
+                    key[u][h] = ((unsigned)sorted_idx[kp] << 6) | (unsigned)e;
+                }
+            }
+        }
+        if (rounds == 1) {
 #pragma unroll
             for (int size = 2; size <= 32; size <<= 1) {
 #pragma unroll
@@ -350,33 +366,32 @@ rball_fill(const double *__restrict__ sorted_pos, const int *__restrict__ sorted
                     const bool lower = (lane & stride) == 0;
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
-                        const unsigned other = __shfl_xor_sync(0xffffffffu, key[u], stride);
-                        key[u] = (lower == up) ? min(key[u], other) : max(key[u], other);
+                        const unsigned other = __shfl_xor_sync(0xffffffffu, key[u][0], stride);
+                        key[u][0] = (lower == up) ? min(key[u][0], other) : max(key[u][0], other);
                     }
                 }
             }
-#pragma unroll
-            for (int u = 0; u < U; ++u)
-                if (lane < kc[u]) {
-                    const int kp = s_list[(key[u] & 63u) * kListStride + tid0 + cl0 + u];
-                    emit_entry<D>(sorted_pos, kp, key[u] >> 6, pc[u], basec[u] + lane, rowval, nzval);
-                }
         } else {
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                if (kc[u] == 0) continue;
-                const int col = tid0 + cl0 + u;
-                unsigned k0 = 0xffffffffu, k1 = 0xffffffffu;
-                if (lane < kc[u]) k0 = ((unsigned)sorted_idx[s_list[lane * kListStride + col]] << 6) | (unsigned)lane;
-                if (lane + 32 < kc[u])
-                    k1 = ((unsigned)sorted_idx[s_list[(lane + 32) * kListStride + col]] << 6) | (unsigned)(lane + 32);
-                bitonic64(k0, k1, lane);
-                if (lane < kc[u])
-                    emit_entry<D>(sorted_pos, s_list[(k0 & 63u) * kListStride + col], k0 >> 6, pc[u], basec[u] + lane,
-                                  rowval, nzval);
-                if (lane + 32 < kc[u])
-                    emit_entry<D>(sorted_pos, s_list[(k1 & 63u) * kListStride + col], k1 >> 6, pc[u],
-                                  basec[u] + lane + 32, rowval, nzval);
+            for (int u = 0; u < U; ++u) bitonic64(key[u][0], key[u][1], lane);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int ru = (kc[u] > 32) ? 2 : (kc[u] > 0 ? 1 : 0);  // warp-uniform
+            for (int h = 0; h < ru; ++h) {
+                const int e = lane + 32 * h;
+                const unsigned ky = h ? key[u][1] : key[u][0];
+                const int src = (int)(ky & 63u);
+                // cell-order position of the source slot: held by lane (src & 31), register (src >> 5)
+                const int kp_a = __shfl_sync(0xffffffffu, kpos[u][0], src & 31);
+                const int kp_b = (ru > 1) ? __shfl_sync(0xffffffffu, kpos[u][1], src & 31) : 0;
+                const int kp = (src >> 5) ? kp_b : kp_a;
+                if (e < kc[u]) {
+                    double b[D];
+#pragma unroll
+                    for (int i = 0; i < D; ++i) b[i] = sorted_pos[(size_t)kp * D + i];
+                    emit_entry<D>(b, ky >> 6, pc[u], basec[u] + e, rowval, nzval);
+                }
             }
         }
     }
@@ -597,9 +612,16 @@ static int build_table(mpb200_samples *s, double r, mpb200_table *t) {
     phase_mark(3);
     if (nq > 0 && nnz > 0) {
         if (N < (int64_t(1) << 26)) {
-            rball_fill<D><<<nbQ, kQThreads, 0, st>>>(sorted_pos, sorted_idx, q_order, masks, nq, s->q0, g, cell_start,
-                                                    t->colptr.as<int64_t>(), t->rowval.as<int64_t>(),
-                                                    t->nzval.as<double>());
+            static const int fill_u = [] { const char *e = getenv("MPB200_FILL_U"); return e ? atoi(e) : 2; }();
+            const int64_t *cp = t->colptr.as<int64_t>();
+            int64_t *rv = t->rowval.as<int64_t>();
+            double *nz = t->nzval.as<double>();
+            if (fill_u == 4)
+                rball_fill<D, 4><<<nbQ, kQThreads, 0, st>>>(sorted_pos, sorted_idx, q_order, masks, nq, s->q0, g, cell_start, cp, rv, nz);
+            else if (fill_u == 1)
+                rball_fill<D, 1><<<nbQ, kQThreads, 0, st>>>(sorted_pos, sorted_idx, q_order, masks, nq, s->q0, g, cell_start, cp, rv, nz);
+            else
+                rball_fill<D, 2><<<nbQ, kQThreads, 0, st>>>(sorted_pos, sorted_idx, q_order, masks, nq, s->q0, g, cell_start, cp, rv, nz);
             MPB_LAUNCHED();
         }
         if (n_big > 0) {
@@ -619,6 +641,7 @@ static int build_table(mpb200_samples *s, double r, mpb200_table *t) {
     t->col0 = s->q0;
     t->nnz = nnz;
     t->r = r;
+    t->euclid = true;
     return 0;
 }
 

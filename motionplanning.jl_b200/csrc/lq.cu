@@ -365,6 +365,7 @@ static int lq_build(mpb200_samples *s, const mpb200_lq *lq, double r, mpb200_tab
     tF->nnz = nnzF;
     tB->nnz = nnzB;
     tF->r = tB->r = r;
+    tF->euclid = tB->euclid = false;
     return 0;
 }
 

@@ -192,11 +192,38 @@ class MetricNN(SampleSet):
         self.r = float(r)
         return nnz.value
 
+    def build_table_checked(self, r, CC, SS):
+        """Device-only, fused: neighbour table + validity of every stored edge in one pass
+        (mpb200_inball_build_checked).  Returns (nnz, checks); bits via fetch_edge_bits()."""
+        nnz, checks = _lib.c_i64(0), _lib.c_i64(0)
+        d = SS.desc()
+        _lib.check(_lib.lib().mpb200_inball_build_checked(self.handle(), float(r), CC.handle(), ctypes.byref(d),
+                                                          ctypes.byref(self.table.h), ctypes.byref(nnz),
+                                                          ctypes.byref(checks)))
+        self.table.nnz = nnz.value
+        self.table.ncols = self.q1 - self.q0
+        self.r = float(r)
+        CC.count += checks.value
+        return nnz.value, checks.value
+
+    def fetch_edge_bits(self, table=None):
+        table = table or self.table
+        bits = self.pool.array(("edge_bits", id(table)), (table.nnz + 63) // 64, np.uint64)
+        _lib.check(_lib.lib().mpb200_table_fetch_edge_bits(table.h, _lib.ptr(bits)))
+        return bits
+
     def precompute(self, r):
         self.build_table(r)
         D = self.fetch_table(self.table)
         self.cache = ImmutableNNC(D, float(r))
         return self.cache
+
+    def precompute_checked(self, r, CC, SS):
+        """precompute + edge validity through the fused pass -> (ImmutableNNC, edge chunks, checks)"""
+        _, checks = self.build_table_checked(r, CC, SS)
+        D = self.fetch_table(self.table)
+        self.cache = ImmutableNNC(D, float(r))
+        return self.cache, self.fetch_edge_bits(), checks
 
     def close(self):
         self.table.close()

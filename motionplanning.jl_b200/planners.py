@@ -64,8 +64,8 @@ def fmtstar(P, N=None, rm=1.0, connections="R", r=0.0, ensure_goal_ct=1, init_id
         DF, DB = cF.D, cB.D
         ebits, _ = NN.lq_edges_free(CC, SS)
     else:
-        DF = DB = NN.precompute(r).D
-        ebits, _ = NN.edges_free(NN.table, CC, SS)
+        cache, ebits, _ = NN.precompute_checked(r, CC, SS)   # K1 + K2 with K7/K8 fused
+        DF = DB = cache.D
     lookups_before = CC.count
     CC.count = 0                                          # the table build is not what FMT* "asked"
     evalid = _bits_to_bool(ebits, DB.nnz)

@@ -45,3 +45,13 @@ def test_product_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", text, flags=re.M), f
                 assert "liboracle" not in text and "mp_oracle.h" not in text, f
+
+
+def test_julia_shim_and_integration_doc_bind_real_symbols():
+    """every ccall symbol named in julia/MotionPlanningB200.jl and INTEGRATION.md is declared in the header"""
+    syms = set(_declared_symbols())
+    for rel in ("julia/MotionPlanningB200.jl", "INTEGRATION.md"):
+        text = open(os.path.join(ROOT, rel)).read()
+        used = set(re.findall(r"\(:(mpb200_[a-z0-9_]+),\s*LIB\)", text))
+        assert used, rel
+        assert used <= syms, (rel, used - syms)

@@ -268,3 +268,43 @@ def test_full_size_c2_properties(gpu, orc):
     exp, _ = orc.edges_free_csc(orc.Obstacles2D(fx.ISRR_2H), SSo, V, ref[0], ref[1], 500_000)
     assert np.array_equal(got[lo:hi], exp.astype(bool))
     NN.close()
+
+
+@pytest.mark.parametrize("checker", ["sat2d", "sat2d_nested", "boxes2d", "boxes3d"])
+def test_fused_build_checked_equals_separate_calls(gpu, orc, checker):
+    """mpb200_inball_build_checked (K2 with K7/K8 fused) == inball_build + edges_free == oracle,
+    including columns that overflow the thread path (dense cluster -> big-column leftovers)"""
+    mp = gpu
+    rng = np.random.Generator(np.random.PCG64(99))
+    d = 3 if checker == "boxes3d" else 2
+    N = 60_000
+    V = rng.random((N, d)) * 1.04 - 0.02                      # some samples outside the unit cube
+    V[:300] = 0.3 + 0.002 * rng.random((300, d))              # cluster: columns with ~300 entries
+    r = fx.fmt_radius(N, d)
+    lo, hi = np.zeros(d), np.ones(d)
+    SSp, SSo = _space_pair(mp, orc, lo, hi)
+    if checker == "sat2d":
+        CC, R = mp.PointRobot2D(mp.obstaclesets.ISRR_POLY_WITH_SPIKE()), orc.Obstacles2D(fx.ISRR_POLY_WITH_SPIKE)
+    elif checker == "sat2d_nested":
+        spec = ("compound", [fx.TRI_BALLS, ("circle", (0.8, 0.8), 0.1), fx.box2d([0.05, 0.2], [0.7, 0.9])])
+        CC, R = mp.PointRobot2D(fx.product_shape(mp, spec)), orc.Obstacles2D(spec)
+    elif checker == "boxes2d":
+        CC, R = mp.PointRobotNDBoxes([mp.BoxBounds(b) for b in fx.BOXES2D]), orc.Boxes(fx.BOXES2D)
+    else:
+        CC, R = mp.PointRobotNDBoxes([mp.BoxBounds(b) for b in fx.BOXES3D]), orc.Boxes(fx.BOXES3D)
+    NN = mp.MetricNN(V)
+    CC.count = 0
+    cache, bits, checks = NN.precompute_checked(r, CC, SSp)
+    D = cache.D
+    ref = _check_table(orc, V, r, D)
+    exp, cnt = orc.edges_free_csc(R, SSo, V, D.colptr, D.rowval)
+    got = unpack_bits(bits, D.nnz)
+    assert np.array_equal(got, exp.astype(bool))
+    assert checks == cnt == CC.count
+    assert np.diff(D.colptr).max() >= 299
+    # and the stand-alone edge kernel on the same table
+    bits2, checks2 = NN.edges_free(NN.table, CC, SSp)
+    assert np.array_equal(unpack_bits(bits2, D.nnz), got) and checks2 == cnt
+    if D.nnz % 64:
+        assert int(bits[-1]) >> (D.nnz % 64) == 0
+    NN.close()
