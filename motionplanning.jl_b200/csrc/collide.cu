@@ -185,13 +185,32 @@ classify_columns(const double *__restrict__ V, const int64_t *__restrict__ colpt
                     lo[i] = x - pad; hi[i] = x + pad;
                     trivial = trivial && (S.lo[i] <= lo[i] && hi[i] <= S.hi[i]);
                 }
+                bool all_colliding = false;  // 2-D only: the whole r-box sits inside one convex polygon
                 if (trivial) {
                     if (KIND == 0) {
                         Obs2 O(T);
-                        for (int s = 0; s < O.S && trivial; ++s) {
+                        const double ylo = lo[DW > 1 ? 1 : 0], yhi = hi[DW > 1 ? 1 : 0];
+                        for (int s = 0; s < O.S; ++s) {
                             const double *cb = O.cull_box(s);
-                            if (overlapping(lo[0], hi[0], cb[0], cb[1]) && overlapping(lo[DW > 1 ? 1 : 0], hi[DW > 1 ? 1 : 0], cb[2], cb[3]))
-                                trivial = false;
+                            if (!(overlapping(lo[0], hi[0], cb[0], cb[1]) && overlapping(ylo, yhi, cb[2], cb[3]))) continue;
+                            trivial = false;
+                            // Both endpoints of every edge of the column lie in the box; if the box is inside
+                            // polygon s by a margin far above rounding, no axis of the SAT test separates
+                            // (SAT2D.jl:172-176), so every edge collides -- given the gate chain passes, which
+                            // holds for consistent gates because they contain the polygon's AABB.
+                            if (O.kind(s) == 1 && O.consistent()) {
+                                const double *P = O.data(s);
+                                const int K = O.K(s);
+                                const double *nrm = P + 4 + 2 * K, *ext = P + 4 + 4 * K;
+                                const double m = 1e-9 * (1.0 + fabs(lo[0]) + fabs(hi[0]) + fabs(ylo) + fabs(yhi));
+                                bool inside = true;
+                                for (int i = 0; i < K && inside; ++i) {
+                                    const double n1 = nrm[2 * i], n2 = nrm[2 * i + 1];
+                                    const double dmax = fmax(lo[0] * n1, hi[0] * n1) + fmax(ylo * n2, yhi * n2);
+                                    inside = dmax <= ext[2 * i + 1] - m;  // support of the box along the outward normal
+                                }
+                                if (inside) { all_colliding = true; break; }
+                            }
                         }
                     } else {
                         const double *bl = T, *bh = T + (size_t)M * DW;
@@ -203,7 +222,9 @@ classify_columns(const double *__restrict__ V, const int64_t *__restrict__ colpt
                         }
                     }
                 }
-                if (trivial) {
+                if (all_colliding) {
+                    my_checks += (unsigned long long)(end - beg);  // every segment test runs and fails: bits stay 0
+                } else if (trivial) {
                     my_checks += (unsigned long long)(end - beg);
                     for (int64_t w = beg >> 6; w <= (end - 1) >> 6; ++w) {
                         const int64_t b0 = w << 6;

@@ -88,7 +88,7 @@ struct mpb200_table {
     mpb::DevBuf rowval;    // int64 nnz, 1-based global row ids
     mpb::DevBuf nzval;     // f64 nnz
     mpb::DevBuf counts;    // int32 ncols (scratch)
-    mpb::DevBuf masks;     // 128-bit hit mask per query column (scratch between count and fill)
+    mpb::DevBuf masks;     // per-query hit lists (one byte per hit, 64 B/query; scratch between count and fill)
     mpb::DevBuf edge_bits; // uint64 ceil(nnz/64): last mpb200_edges_free result
     mpb::DevBuf scratch;   // big-column spill etc.
     mpb::DevBuf col_list;  // int32 ncols + counter: columns that need per-edge checks

@@ -156,7 +156,7 @@ __device__ __forceinline__ bool run_span(const GridDev &g, const int *c, int run
 constexpr int kQThreads = 128;
 constexpr int kListCap = 64;                  // hits staged per query thread; more -> warp path
 
-constexpr int kMaskBits = 128;  // candidates per query covered by the hit mask
+constexpr int kMaxCand = 255;  // candidates per query addressable by the one-byte hit list
 
 // candidate spans of a query: begs[r], lens[r] for the 3^(D-1) x-runs (len 0 = outside the grid)
 template <int D>
@@ -177,46 +177,61 @@ __device__ __forceinline__ int query_spans(const GridDev &g, const double *p, co
     return total;
 }
 
-// Count pass.  Besides the per-column count it records WHICH candidates hit as a 128-bit mask
-// (bit j = j-th candidate in run order), so the fill pass never re-evaluates a distance.
+// Count pass.  Besides the per-column count it records WHICH candidates hit: one byte per hit
+// (the candidate's number in run order), staged per thread in shared memory and written out by
+// the warp as a [tile = 32 queries][slot][lane] byte array (one 32-byte sector per slot), so the
+// fill pass never re-evaluates a distance and reads its column's list with coalesced byte loads.
 template <int D>
 __global__ void __launch_bounds__(kQThreads)
 rball_count(const double *__restrict__ sorted_pos, const int *__restrict__ sorted_idx,
             const int *__restrict__ q_order, int64_t nq, int64_t q0, GridDev g, double r2,
             const int *__restrict__ cell_start, int list_cap, int *__restrict__ counts,
-            ulonglong2 *__restrict__ masks, int *__restrict__ big_list, unsigned long long *__restrict__ n_big) {
+            uint32_t *__restrict__ hit_lists, int *__restrict__ big_list, unsigned long long *__restrict__ n_big) {
     constexpr int kRuns = (D == 2) ? 3 : 9;
+    __shared__ __align__(16) unsigned char s_hits[kListCap][kQThreads];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nq) return;
-    const int pos = q_order ? q_order[t] : (int)t;
-    double p[D];
+    int cnt = 0;
+    if (t < nq) {
+        const int pos = q_order ? q_order[t] : (int)t;
+        double p[D];
 #pragma unroll
-    for (int i = 0; i < D; ++i) p[i] = sorted_pos[(size_t)pos * D + i];
-    int begs[kRuns], lens[kRuns];
-    const int total = query_spans<D>(g, p, cell_start, begs, lens);
-    int cnt = 0, j = 0;
-    unsigned long long m0 = 0, m1 = 0;
+        for (int i = 0; i < D; ++i) p[i] = sorted_pos[(size_t)pos * D + i];
+        int begs[kRuns], lens[kRuns];
+        const int total = query_spans<D>(g, p, cell_start, begs, lens);
+        int j = 0;
 #pragma unroll
-    for (int run = 0; run < kRuns; ++run) {
-        const int beg = begs[run], end = begs[run] + lens[run];
-        for (int k = beg; k < end; ++k, ++j) {
-            double b[D];
+        for (int run = 0; run < kRuns; ++run) {
+            const int beg = begs[run], end = begs[run] + lens[run];
+            for (int k = beg; k < end; ++k, ++j) {
+                double b[D];
 #pragma unroll
-            for (int i = 0; i < D; ++i) b[i] = sorted_pos[(size_t)k * D + i];
-            const bool hit = (k != pos) && (sqdist<D>(p, b) <= r2);
-            cnt += hit ? 1 : 0;
-            if (hit) {
-                if (j < 64) m0 |= 1ULL << j;
-                else if (j < 128) m1 |= 1ULL << (j - 64);
+                for (int i = 0; i < D; ++i) b[i] = sorted_pos[(size_t)k * D + i];
+                if ((k != pos) && (sqdist<D>(p, b) <= r2)) {
+                    if (cnt < kListCap) s_hits[cnt][threadIdx.x] = (unsigned char)j;
+                    ++cnt;
+                }
             }
         }
+        const int w = (int)(sorted_idx[pos] - q0);
+        counts[w] = cnt;
+        if (cnt > 0 && (cnt > list_cap || total > kMaxCand)) {
+            unsigned long long slot = atomicAdd(n_big, 1ULL);
+            big_list[slot] = w;
+        }
     }
-    const int w = (int)(sorted_idx[pos] - q0);
-    counts[w] = cnt;
-    masks[t] = make_ulonglong2(m0, m1);
-    if (cnt > 0 && (cnt > list_cap || total > kMaskBits)) {
-        unsigned long long slot = atomicAdd(n_big, 1ULL);
-        big_list[slot] = w;
+    // warp writes its tile: slot rows 0 .. max(cnt)-1, four rows (8 words each) per step
+    int kmax = min(cnt, kListCap);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+    __syncwarp();
+    const int64_t tile = (int64_t)blockIdx.x * (kQThreads / 32) + wid;
+    for (int n0 = 0; n0 < kmax; n0 += 4) {
+        const int n = n0 + (lane >> 3);
+        if (n < kmax) {
+            const uint32_t word = reinterpret_cast<const uint32_t *>(&s_hits[n][wid * 32])[lane & 7];
+            hit_lists[(tile * kListCap + n) * 8 + (lane & 7)] = word;
+        }
     }
 }
 
@@ -249,14 +264,14 @@ __device__ __forceinline__ void bitonic64(unsigned &k0, unsigned &k1, int lane) 
     }
 }
 
-// Fill.  Thread t owns query t of the cell order and keeps that query's point, column base, count,
-// 128-bit hit mask and candidate spans in registers; the warp then walks over its 32 columns, U at
-// a time.  For a column, lane e selects the e-th set bit of the mask (__fns), maps it to a cell-
-// order position, loads the sample index, and the column is sorted by index with a register
-// bitonic network over the lanes (key = index << 6 | source slot).  The neighbour position comes
+// Fill.  Thread t owns query t of the cell order and keeps that query's point, column base, count
+// and candidate spans in registers; the warp then walks over its 32 columns, U at a time.  For a
+// column, lane e reads the e-th byte of the column's hit list (written by rball_count), maps the
+// candidate number to a cell-order position, loads the sample index, and the column is sorted by
+// index with a register bitonic network over the lanes (key = index << 6 | source slot).  The neighbour position comes
 // from the cell-ordered copy (cache-friendly), the exact distance is recomputed, and the column
 // is written as one contiguous Int64/Float64 burst.  No shared memory, no re-evaluation of
-// distances.  Columns with more than kListCap entries or more than kMaskBits candidates are left
+// distances.  Columns with more than kListCap entries or more than kMaxCand candidates are left
 // to rball_fill_big.  Requires N < 2^26 (key packing).
 template <int D>
 __device__ __forceinline__ void emit_entry(const double *b, unsigned idx, const double *pc, long long at,
@@ -265,33 +280,19 @@ __device__ __forceinline__ void emit_entry(const double *b, unsigned idx, const 
     nzval[at] = sqrt(sqdist<D>(pc, b));
 }
 
-// position (0..127) of the n-th (0-based) set bit of the 128-bit mask (m0 = bits 0..63)
-__device__ __forceinline__ int nth_set_bit(unsigned long long m0, unsigned long long m1, int n) {
-    const int c0 = __popcll(m0);
-    const unsigned long long m = (n < c0) ? m0 : m1;
-    int nn = (n < c0) ? n : n - c0;
-    int off = (n < c0) ? 0 : 64;
-    const unsigned lo = (unsigned)m, hi = (unsigned)(m >> 32);
-    const int cl = __popc(lo);
-    const unsigned w = (nn < cl) ? lo : hi;
-    off += (nn < cl) ? 0 : 32;
-    nn = (nn < cl) ? nn : nn - cl;
-    return off + (int)__fns(w, 0, nn + 1);
-}
-
 // U = columns sorted concurrently by one warp (independent dependency chains vs register budget)
 template <int D, int U>
 __global__ void __launch_bounds__(kQThreads)
 rball_fill(const double *__restrict__ sorted_pos, const int *__restrict__ sorted_idx,
-           const int *__restrict__ q_order, const ulonglong2 *__restrict__ masks, int64_t nq, int64_t q0, GridDev g,
-           const int *__restrict__ cell_start, const int64_t *__restrict__ colptr, int64_t *__restrict__ rowval,
-           double *__restrict__ nzval) {
+           const int *__restrict__ q_order, const unsigned char *__restrict__ hit_lists, int64_t nq, int64_t q0,
+           GridDev g, const int *__restrict__ cell_start, const int64_t *__restrict__ colptr,
+           int64_t *__restrict__ rowval, double *__restrict__ nzval) {
     constexpr int kRuns = (D == 2) ? 3 : 9;
     const int lane = threadIdx.x & 31;
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned char *tile_list = hit_lists + (t >> 5) * (int64_t)(kListCap * 32);  // same tiling as rball_count
     int k_mine = 0;
     long long base = 0;
-    unsigned long long m0 = 0, m1 = 0;
     int begs[kRuns], lens[kRuns];
     double p[D];
 #pragma unroll
@@ -306,9 +307,7 @@ rball_fill(const double *__restrict__ sorted_pos, const int *__restrict__ sorted
         base = colptr[w] - 1;
         k_mine = (int)(colptr[w + 1] - colptr[w]);
         const int total = query_spans<D>(g, p, cell_start, begs, lens);
-        if (k_mine > kListCap || total > kMaskBits) k_mine = 0;  // handled by rball_fill_big
-        const ulonglong2 mk = masks[t];
-        m0 = mk.x; m1 = mk.y;
+        if (k_mine > kListCap || total > kMaxCand) k_mine = 0;  // handled by rball_fill_big
     }
     for (int cl0 = 0; cl0 < 32; cl0 += U) {
         int kc[U];
@@ -327,8 +326,6 @@ rball_fill(const double *__restrict__ sorted_pos, const int *__restrict__ sorted
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             basec[u] = __shfl_sync(0xffffffffu, base, cl0 + u);
-            const unsigned long long c_m0 = __shfl_sync(0xffffffffu, m0, cl0 + u);
-            const unsigned long long c_m1 = __shfl_sync(0xffffffffu, m1, cl0 + u);
 #pragma unroll
             for (int i = 0; i < D; ++i) pc[u][i] = __shfl_sync(0xffffffffu, p[i], cl0 + u);
             int cb_[kRuns], cn_[kRuns];
@@ -344,7 +341,7 @@ rball_fill(const double *__restrict__ sorted_pos, const int *__restrict__ sorted
                 kpos[u][h] = 0;
                 const int e = lane + 32 * h;
                 if (h < rounds && e < kc[u]) {
-                    int j = nth_set_bit(c_m0, c_m1, e);
+                    int j = tile_list[e * 32 + cl0 + u];  // candidate number of the e-th hit of this column
                     int kp = 0;
 #pragma unroll
                     for (int r = 0; r < kRuns; ++r) {  // run containing candidate j
@@ -576,8 +573,8 @@ static int build_table(mpb200_samples *s, double r, mpb200_table *t) {
     // count pass
     if (int rc = t->counts.reserve(sizeof(int) * (size_t)(2 * nq + 2))) return rc;
     if (int rc = t->colptr.reserve(sizeof(int64_t) * (size_t)(nq + 1))) return rc;
-    if (int rc = t->masks.reserve(sizeof(ulonglong2) * (size_t)(nq + 1))) return rc;
-    ulonglong2 *masks = t->masks.as<ulonglong2>();
+    if (int rc = t->masks.reserve((size_t)kListCap * 32 * (size_t)(ceil_div(nq, 32) + 1))) return rc;
+    uint32_t *hit_lists = t->masks.as<uint32_t>();
     int *counts = t->counts.as<int>();
     int *big_list = counts + nq;
     unsigned long long *d_nbig = reinterpret_cast<unsigned long long *>(c.d_scalar + 1);
@@ -588,7 +585,7 @@ static int build_table(mpb200_samples *s, double r, mpb200_table *t) {
         // key packing in rball_fill needs N < 2^26; beyond that every non-empty column is "big"
         const int list_cap = (N < (int64_t(1) << 26)) ? kListCap : 0;
         rball_count<D><<<nbQ, kQThreads, 0, st>>>(sorted_pos, sorted_idx, q_order, nq, s->q0, g, r2, cell_start,
-                                                 list_cap, counts, masks, big_list, d_nbig);
+                                                 list_cap, counts, hit_lists, big_list, d_nbig);
         MPB_LAUNCHED();
     }
     if (int rc = exclusive_scan<int, int64_t>(counts, nq, t->colptr.as<int64_t>(), (int64_t)1, s->scan_tmp,
@@ -616,12 +613,13 @@ static int build_table(mpb200_samples *s, double r, mpb200_table *t) {
             const int64_t *cp = t->colptr.as<int64_t>();
             int64_t *rv = t->rowval.as<int64_t>();
             double *nz = t->nzval.as<double>();
+            const unsigned char *hl = t->masks.as<unsigned char>();
             if (fill_u == 4)
-                rball_fill<D, 4><<<nbQ, kQThreads, 0, st>>>(sorted_pos, sorted_idx, q_order, masks, nq, s->q0, g, cell_start, cp, rv, nz);
+                rball_fill<D, 4><<<nbQ, kQThreads, 0, st>>>(sorted_pos, sorted_idx, q_order, hl, nq, s->q0, g, cell_start, cp, rv, nz);
             else if (fill_u == 1)
-                rball_fill<D, 1><<<nbQ, kQThreads, 0, st>>>(sorted_pos, sorted_idx, q_order, masks, nq, s->q0, g, cell_start, cp, rv, nz);
+                rball_fill<D, 1><<<nbQ, kQThreads, 0, st>>>(sorted_pos, sorted_idx, q_order, hl, nq, s->q0, g, cell_start, cp, rv, nz);
             else
-                rball_fill<D, 2><<<nbQ, kQThreads, 0, st>>>(sorted_pos, sorted_idx, q_order, masks, nq, s->q0, g, cell_start, cp, rv, nz);
+                rball_fill<D, 2><<<nbQ, kQThreads, 0, st>>>(sorted_pos, sorted_idx, q_order, hl, nq, s->q0, g, cell_start, cp, rv, nz);
             MPB_LAUNCHED();
         }
         if (n_big > 0) {
