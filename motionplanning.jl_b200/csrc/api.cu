@@ -202,6 +202,7 @@ int mpb200_samples_create(const double *V_aos, int64_t N, int d, mpb200_samples 
         if (e != cudaSuccess) { s->V.release(); delete s; return fail(MPB200_ECUDA, "H2D copy failed: %s", cudaGetErrorString(e)); }
         rc = compute_bbox(s);
         if (rc) { mpb200_samples_destroy(s); return rc; }
+        MPB_CUDA(cudaMemcpyAsync(s->h_bbox, s->minmax.p, sizeof(double) * 2 * d, cudaMemcpyDeviceToHost, st));
     }
     MPB_CUDA(cudaStreamSynchronize(st));
     *out = s;
@@ -210,6 +211,7 @@ int mpb200_samples_create(const double *V_aos, int64_t N, int d, mpb200_samples 
 int mpb200_samples_destroy(mpb200_samples *s) {
     if (!s) return MPB200_OK;
     if (ctx().ready) cudaStreamSynchronize(ctx().stream);
+    if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
     s->V.release(); s->cell_start.release(); s->cell_fill.release(); s->sorted_idx.release();
     s->sorted_pos.release(); s->minmax.release(); s->scan_tmp.release(); s->point_bits.release(); s->q_order.release();
     delete s;

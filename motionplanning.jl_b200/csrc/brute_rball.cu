@@ -108,9 +108,7 @@ static int brute_build(mpb200_samples *s, double r, mpb200_table *t) {
     cudaStream_t st = c.stream;
     const int64_t N = s->N, nq = s->q1 - s->q0;
     const double *V = s->V.as<double>();
-    double bb[2 * 16];
-    MPB_CUDA(cudaMemcpyAsync(bb, s->minmax.as<double>(), sizeof(double) * 2 * D, cudaMemcpyDeviceToHost, st));
-    MPB_CUDA(cudaStreamSynchronize(st));
+    const double *bb = s->h_bbox;
     double M = 0;
     for (int i = 0; i < 2 * D; ++i) M = fmax(M, fabs(bb[i]));
     const float thr32 = prefilter_threshold(r, D, M);

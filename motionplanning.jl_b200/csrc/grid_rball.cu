@@ -512,10 +512,8 @@ static int build_table(mpb200_samples *s, double r, mpb200_table *t) {
     const int64_t N = s->N, nq = s->q1 - s->q0;
     const double *V = s->V.as<double>();
 
-    // bounding box -> grid geometry (host reads 2*D doubles: one tiny sync per build)
-    double bb[6];
-    MPB_CUDA(cudaMemcpyAsync(bb, s->minmax.as<double>(), sizeof(double) * 2 * D, cudaMemcpyDeviceToHost, st));
-    MPB_CUDA(cudaStreamSynchronize(st));
+    // bounding box (host copy made at samples_create) -> grid geometry
+    const double *bb = s->h_bbox;
     GridDev g;
     const int max_per_dim = (D == 2) ? 4096 : 256;
     double ext_max = 0;
@@ -535,62 +533,94 @@ static int build_table(mpb200_samples *s, double r, mpb200_table *t) {
     for (int i = D; i < 3; ++i) { g.lo[i] = 0; g.n[i] = 1; }
     g.inv_h = 1.0 / h;
 
+    // ---- reserve every buffer of the front half up front (nothing may allocate during graph capture)
     if (int rc = s->cell_start.reserve(sizeof(int) * (size_t)(ncells + 1))) return rc;
     if (int rc = s->cell_fill.reserve(sizeof(int) * (size_t)(ncells + 1))) return rc;
     if (int rc = s->sorted_idx.reserve(sizeof(int) * (size_t)(2 * N + 2))) return rc;  // + cell_id scratch
     if (int rc = s->sorted_pos.reserve(sizeof(double) * (size_t)(D * N + 1))) return rc;
+    if (int rc = s->scan_tmp.reserve(sizeof(int64_t) * (size_t)(ceil_div(ncells > N ? ncells : N, kScanTile) + 2))) return rc;
+    if (nq != N)
+        if (int rc = s->q_order.reserve(sizeof(int) * (size_t)(3 * N + 4))) return rc;
+    if (int rc = t->counts.reserve(sizeof(int) * (size_t)(2 * nq + 2))) return rc;
+    if (int rc = t->colptr.reserve(sizeof(int64_t) * (size_t)(nq + 1))) return rc;
+    if (int rc = t->masks.reserve((size_t)kListCap * 32 * (size_t)(ceil_div(nq, 32) + 1))) return rc;
     int *hist = s->cell_fill.as<int>();
     int *cell_start = s->cell_start.as<int>();
     int *sorted_idx = s->sorted_idx.as<int>();
     int *cell_id = sorted_idx + N;
     double *sorted_pos = s->sorted_pos.as<double>();
-
-    phase_mark(0);
-    MPB_CUDA(cudaMemsetAsync(hist, 0, sizeof(int) * (size_t)(ncells + 1), st));
-    const unsigned nbN = (unsigned)ceil_div(N > 0 ? N : 1, 256);
-    cell_histogram<D><<<nbN, 256, 0, st>>>(V, N, g, hist, cell_id);
-    MPB_LAUNCHED();
-    if (int rc = exclusive_scan<int, int>(hist, ncells, cell_start, 0, s->scan_tmp, nullptr)) return rc;
-    MPB_CUDA(cudaMemsetAsync(hist, 0, sizeof(int) * (size_t)(ncells + 1), st));
-    cell_scatter<D><<<nbN, 256, 0, st>>>(V, N, cell_id, cell_start, hist, sorted_idx, sorted_pos);
-    MPB_LAUNCHED();
-
-    // shard: compact the cell-order positions this process owns
-    const int *q_order = nullptr;
-    if (nq != N) {
-        if (int rc = s->q_order.reserve(sizeof(int) * (size_t)(3 * N + 4))) return rc;
-        int *qo = s->q_order.as<int>();
-        int *flags = qo + N + 1, *offs = flags + N + 1;
-        range_flags<<<nbN, 256, 0, st>>>(sorted_idx, N, s->q0, s->q1, flags);
-        MPB_LAUNCHED();
-        if (int rc = exclusive_scan<int, int>(flags, N, offs, 0, s->scan_tmp, nullptr)) return rc;
-        range_scatter<<<nbN, 256, 0, st>>>(flags, offs, N, qo);
-        MPB_LAUNCHED();
-        q_order = qo;
-    }
-    phase_mark(1);
-
-    // count pass
-    if (int rc = t->counts.reserve(sizeof(int) * (size_t)(2 * nq + 2))) return rc;
-    if (int rc = t->colptr.reserve(sizeof(int64_t) * (size_t)(nq + 1))) return rc;
-    if (int rc = t->masks.reserve((size_t)kListCap * 32 * (size_t)(ceil_div(nq, 32) + 1))) return rc;
     uint32_t *hit_lists = t->masks.as<uint32_t>();
     int *counts = t->counts.as<int>();
     int *big_list = counts + nq;
     unsigned long long *d_nbig = reinterpret_cast<unsigned long long *>(c.d_scalar + 1);
-    MPB_CUDA(cudaMemsetAsync(c.d_scalar, 0, sizeof(int64_t) * 2, st));
+    const int *q_order = (nq != N) ? s->q_order.as<int>() : nullptr;
     const double r2 = r * r;
+    const unsigned nbN = (unsigned)ceil_div(N > 0 ? N : 1, 256);
     const unsigned nbQ = (unsigned)ceil_div(nq > 0 ? nq : 1, kQThreads);
-    if (nq > 0) {
-        // key packing in rball_fill needs N < 2^26; beyond that every non-empty column is "big"
-        const int list_cap = (N < (int64_t(1) << 26)) ? kListCap : 0;
-        rball_count<D><<<nbQ, kQThreads, 0, st>>>(sorted_pos, sorted_idx, q_order, nq, s->q0, g, r2, cell_start,
-                                                 list_cap, counts, hit_lists, big_list, d_nbig);
+    // key packing in rball_fill needs N < 2^26; beyond that every non-empty column is "big"
+    const int list_cap = (N < (int64_t(1) << 26)) ? kListCap : 0;
+
+    // the front half: K1 (histogram, scan, scatter) [+ shard compaction] + count pass + colptr scan
+    auto front = [&]() -> int {
+        MPB_CUDA(cudaMemsetAsync(hist, 0, sizeof(int) * (size_t)(ncells + 1), st));
+        cell_histogram<D><<<nbN, 256, 0, st>>>(V, N, g, hist, cell_id);
         MPB_LAUNCHED();
+        if (int rc = exclusive_scan<int, int>(hist, ncells, cell_start, 0, s->scan_tmp, nullptr)) return rc;
+        MPB_CUDA(cudaMemsetAsync(hist, 0, sizeof(int) * (size_t)(ncells + 1), st));
+        cell_scatter<D><<<nbN, 256, 0, st>>>(V, N, cell_id, cell_start, hist, sorted_idx, sorted_pos);
+        MPB_LAUNCHED();
+        if (nq != N) {  // shard: compact the cell-order positions this process owns
+            int *qo = s->q_order.as<int>();
+            int *flags = qo + N + 1, *offs = flags + N + 1;
+            range_flags<<<nbN, 256, 0, st>>>(sorted_idx, N, s->q0, s->q1, flags);
+            MPB_LAUNCHED();
+            if (int rc = exclusive_scan<int, int>(flags, N, offs, 0, s->scan_tmp, nullptr)) return rc;
+            range_scatter<<<nbN, 256, 0, st>>>(flags, offs, N, qo);
+            MPB_LAUNCHED();
+        }
+        MPB_CUDA(cudaMemsetAsync(c.d_scalar, 0, sizeof(int64_t) * 2, st));
+        if (nq > 0) {
+            rball_count<D><<<nbQ, kQThreads, 0, st>>>(sorted_pos, sorted_idx, q_order, nq, s->q0, g, r2, cell_start,
+                                                     list_cap, counts, hit_lists, big_list, d_nbig);
+            MPB_LAUNCHED();
+        }
+        return exclusive_scan<int, int64_t>(counts, nq, t->colptr.as<int64_t>(), (int64_t)1, s->scan_tmp, c.d_scalar);
+    };
+
+    static const bool use_graph = getenv("MPB200_NO_GRAPH") == nullptr;
+    phase_mark(0);
+    if (use_graph && nq > 0 && ncells > 0) {
+        uint64_t key[24] = {};
+        int kk = 0;
+        auto put = [&](const void *p, size_t n) { uint64_t v = 0; memcpy(&v, p, n); key[kk++] = v; };
+        const void *ptrs[] = {V, hist, cell_start, sorted_idx, sorted_pos, hit_lists, counts, t->colptr.p, s->scan_tmp.p,
+                              s->q_order.p, c.d_scalar, (const void *)st};
+        for (const void *p : ptrs) put(&p, sizeof(p));
+        put(&N, 8); put(&nq, 8); put(&s->q0, 8); put(&r, 8); put(&g.inv_h, 8); put(&g.lo[0], 8); put(&g.lo[1], 8);
+        put(&g.lo[2], 8); put(&g.n[0], 4); put(&g.n[1], 4); put(&g.n[2], 4);
+        key[kk++] = (uint64_t)D;
+        if (!(s->graph_exec && memcmp(key, s->graph_key, sizeof(key)) == 0)) {
+            if (s->graph_exec) { cudaGraphExecDestroy(s->graph_exec); s->graph_exec = nullptr; }
+            cudaGraph_t graph = nullptr;
+            MPB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            const int64_t launches_before = c.launches;
+            int rc = front();
+            cudaError_t e = cudaStreamEndCapture(st, &graph);
+            s->graph_launches = (int)(c.launches - launches_before);
+            c.launches = launches_before;
+            if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+            if (e != cudaSuccess) return fail(MPB200_ECUDA, "graph capture failed: %s", cudaGetErrorString(e));
+            e = cudaGraphInstantiate(&s->graph_exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (e != cudaSuccess) { s->graph_exec = nullptr; return fail(MPB200_ECUDA, "graph instantiate failed: %s", cudaGetErrorString(e)); }
+            memcpy(s->graph_key, key, sizeof(key));
+        }
+        MPB_CUDA(cudaGraphLaunch(s->graph_exec, st));
+        c.launches += s->graph_launches;  // the kernels inside the graph still run
+    } else {
+        if (int rc = front()) return rc;
     }
-    if (int rc = exclusive_scan<int, int64_t>(counts, nq, t->colptr.as<int64_t>(), (int64_t)1, s->scan_tmp,
-                                              c.d_scalar))
-        return rc;
+    phase_mark(1);
     phase_mark(2);
     MPB_CUDA(cudaMemcpyAsync(c.h_scalar, c.d_scalar, sizeof(int64_t) * 2, cudaMemcpyDeviceToHost, st));
     MPB_CUDA(cudaStreamSynchronize(st));
