@@ -1,0 +1,159 @@
+#!/usr/bin/env python
+"""Secondary measurements: BASELINE.json configs C1, C3, C4, C5 (bench.py is the headline C2 line).
+One JSON line per config: device-resident GPU throughput + the oracle port on a bounded sample of
+the same workload (single host thread, extrapolated and labelled as such).
+
+  python bench_configs.py [--configs C1,C3,C4,C5] [--scale 1.0]
+"""
+import argparse
+import json
+import math
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def timed(f, reps=1):
+    best = math.inf
+    out = None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        out = f()
+        best = min(best, time.perf_counter() - t0)
+    return best, out
+
+
+def c1(mp, orc, fx, args):
+    """FMT* 2-D, ISRR_2H, N=1000, end to end (planner included)"""
+    N = 1000
+    SS = mp.UnitHypercube(2)
+    CC = mp.PointRobot2D(mp.obstaclesets.ISRR_2H())
+    O = orc.Obstacles2D(fx.ISRR_2H)
+    So = orc.StateSpace([0, 0], [1, 1])
+    cand = fx.uniform_samples(3 * N, 2, 20240601)
+    V = np.vstack([[0.1, 0.1], cand[orc.states_free(O, So, cand)][:N - 2], [0.9, 0.9]])
+    def run():
+        P = mp.MPProblem(SS, [0.1, 0.1], mp.PointGoal([0.9, 0.9]), CC, V=mp.MetricNN(V, SS.dist, V[0]))
+        out = mp.fmtstar(P, rm=1.0)
+        P.V.close()
+        return out
+    run()
+    t, (status, cost, _) = timed(run, 3)
+    return dict(config="C1", N=N, status=status, cost=cost, gpu_s=t, note="host FMT* + GPU tables, N=1000 (latency-bound)")
+
+
+def c3(mp, orc, fx, args):
+    """10-D unit hypercube, random hyperboxes, N=2M: all-pairs r-ball + box edge checks"""
+    d = 10
+    N = int(2_000_000 * args.scale)
+    V = fx.uniform_samples(N, d, 20240603)
+    r = fx.fmt_radius(N, d)
+    boxes = fx.random_hyperboxes(64, d, 20240613)
+    CC = mp.PointRobotNDBoxes([mp.BoxBounds(*b) for b in boxes])
+    SS = mp.UnitHypercube(d)
+    NN = mp.MetricNN(V)
+    NN.handle()
+    lib = mp.load()
+    t_nn, nnz = timed(lambda: NN.build_table(r))
+    ph = [lib.mpb200_last_ms(k) for k in range(5)]
+    t_e, (_, checks) = timed(lambda: NN.edges_free(NN.table, CC, SS, fetch=False))
+    # oracle port on a bounded sample of query columns (brute-force truth; the kd-tree degenerates in 10-D)
+    q = 64
+    t_cpu, ref = timed(lambda: orc.rball_brute(V, r, 0, 0, q))
+    B = orc.Boxes(boxes)
+    So = orc.StateSpace(np.zeros(d), np.ones(d))
+    t_cpu_e, _ = timed(lambda: orc.edges_free_csc(B, So, V, ref[0], ref[1], 0))
+    out = dict(config="C3", N=N, d=d, r=r, nnz=int(nnz), mean_degree=nnz / N,
+               nn_gpu_s=t_nn, nn_queries_per_s=N / t_nn, pair_tests_per_s=float(N) * N * 2 / t_nn, phase_ms=ph,
+               edges_gpu_s=t_e, edges_per_s=nnz / t_e, checks=int(checks),
+               cpu_port=dict(sample_queries=q, nn_queries_per_s=q / t_cpu, edges_per_s=len(ref[1]) / max(t_cpu_e, 1e-9),
+                             cores=1, note="brute-force oracle on %d query columns, extrapolated" % q))
+    NN.close()
+    return out
+
+
+def c4(mp, orc, fx, args):
+    """double integrator, N=200k: ControlNN tables (both directions) + swept LQ edge checks"""
+    N = int(200_000 * args.scale)
+    rng = np.random.Generator(np.random.PCG64(20240604))
+    SS = mp.DoubleIntegrator(2)
+    V = SS.lo + rng.random((N, 4)) * (SS.hi - SS.lo)
+    # calibrate r to a mean out-degree of ~64 on a query subsample
+    L = orc.DoubleIntegratorLQ(2)
+    sub = V[:20000]
+    lo_r, hi_r = 0.3, 1.5
+    for _ in range(12):
+        r = 0.5 * (lo_r + hi_r)
+        cp, _, _ = L.inball(sub, r, True, 0, 48)
+        deg = (cp[-1] - 1) / 48 * (N / len(sub))
+        lo_r, hi_r = (r, hi_r) if deg < 64 else (lo_r, r)
+    CC = mp.PointRobot2D(mp.obstaclesets.ISRR_2H())
+    NN = mp.QuasiMetricNN(V, SS.dist)
+    NN.handle()
+    lib = mp.load()
+    t_nn, (nF, nB) = timed(lambda: NN.build_tables(r))
+    ph = [lib.mpb200_last_ms(k) for k in range(4)]
+    t_e, (_, checks) = timed(lambda: NN.lq_edges_free(CC, SS, fetch=False))
+    q = 8
+    t_cpu, ref = timed(lambda: L.inball(V, r, False, 0, q))
+    C = np.hstack([np.eye(2), np.zeros((2, 2))])
+    So = orc.StateSpace(SS.lo, SS.hi, ("matrix", C))
+    t_cpu_e, _ = timed(lambda: L.edges_free_csc(orc.Obstacles2D(fx.ISRR_2H), So, r, V, ref[0], ref[1], 0))
+    out = dict(config="C4", N=N, r=r, nnzF=int(nF), nnzB=int(nB), mean_degree=nB / N,
+               nn_gpu_s=t_nn, nn_queries_per_s=2 * N / t_nn, ordered_pairs_per_s=2.0 * N * N * 2 / t_nn, phase_ms=ph,
+               edges_gpu_s=t_e, edges_per_s=nB / t_e, segment_checks=int(checks),
+               cpu_port=dict(sample_queries=q, nn_queries_per_s=q / t_cpu, edges_per_s=len(ref[1]) / max(t_cpu_e, 1e-9),
+                             cores=1, note="oracle on %d backward columns (one direction), extrapolated" % q))
+    NN.close()
+    return out
+
+
+def c5(mp, orc, fx, args):
+    """Monte-Carlo collision probability, LQG-tracked double integrator past ISRR_2H, 1e8 rollouts"""
+    T, dt = 100, 0.05
+    A = np.block([[np.eye(2), dt * np.eye(2)], [np.zeros((2, 2)), np.eye(2)]])
+    B = np.vstack([0.5 * dt * dt * np.eye(2), dt * np.eye(2)])
+    C = np.hstack([np.eye(2), np.zeros((2, 2))])
+    F, G = mp.montecarlo.lqg_closed_loop(A, B, C, np.eye(4), 0.1 * np.eye(2), 1e-4 * np.eye(4), 1e-4 * np.eye(2), T)
+    Wz = np.hstack([np.eye(2), np.zeros((2, 6))])
+    # nominal path: along y = 0.165 under box 2, then up the corridor x = 0.6 between boxes 2 and 5
+    s = np.linspace(0, 1, T + 1)
+    wbar = np.stack([0.30 + 0.35 * s, 0.135 + 0.0 * s], axis=1)          # 0.055 below box 2
+    CC = mp.PointRobot2D(mp.obstaclesets.ISRR_2H(), fixed_point_test=True)
+    P = mp.montecarlo.with_proposal(mp.MCProblem(F, G, Wz, wbar), CC, r2=36.0, max_components=8)
+    n = int(1e8 * args.scale)
+    mp.collision_probability(P, CC, 100_000)
+    t, res = timed(lambda: mp.collision_probability(P, CC, n))
+    O = orc.Obstacles2D(fx.ISRR_2H, fixed_point_test=True)
+    spec = orc.McSpec(P.F, P.G, P.Wz, P.wbar, P.alpha, P.mu if P.K else None)
+    nq = 20000
+    t_cpu, ref = timed(lambda: orc.mc_run(spec, O, 20240605, 0, nq))
+    naive = mp.collision_probability(mp.MCProblem(F, G, Wz, wbar), CC, min(n, 10_000_000), seed=7)
+    return dict(config="C5", rollouts=n, T=T, K=P.K, p=res["p"], se=res["se"], hits=res["hits"],
+                naive_p=naive["p"], naive_se=naive["se"], gpu_s=t, rollouts_per_s=n / t,
+                cpu_port=dict(sample_rollouts=nq, rollouts_per_s=nq / t_cpu, cores=1))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--configs", default="C1,C3,C4,C5")
+    ap.add_argument("--scale", type=float, default=1.0)
+    args = ap.parse_args()
+    import mpb200
+    from oracle import oracle as orc
+    import fixtures as fx
+    mpb200.init(int(os.environ.get("LOCAL_RANK", "0")))
+    table = dict(C1=c1, C3=c3, C4=c4, C5=c5)
+    for name in args.configs.split(","):
+        out = table[name](mpb200, orc, fx, args)
+        print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -41,11 +41,16 @@ __device__ __forceinline__ double exact_sq(const double *__restrict__ a, const d
     return s;
 }
 
-template <int D, bool FILL>
+// MODE 0: count only; MODE 1: fill the CSC arrays (needs colptr); MODE 2: ONE sweep that counts and
+// appends every hit (index, exact squared distance) to the query's slab of `cap` entries, so the
+// all-pairs work is done once and a streaming compaction (slab_to_csc) finishes the table.
+template <int D, int MODE>
 __global__ void __launch_bounds__(kBrThreads)
 brute_rball_kernel(const double *__restrict__ V, const float *__restrict__ Vf, int64_t N, int64_t q0, int64_t nq,
                    double r2, float thr32, int *__restrict__ counts, const int64_t *__restrict__ colptr,
-                   int64_t *__restrict__ rowval, double *__restrict__ nzval) {
+                   int64_t *__restrict__ rowval, double *__restrict__ nzval, int cap, int *__restrict__ slab_j,
+                   double *__restrict__ slab_s) {
+    constexpr bool FILL = (MODE == 1);
     constexpr int DP = (D + 3) & ~3;
     __shared__ float4 tile[kBrTile * DP / 4];
     const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -81,6 +86,10 @@ brute_rball_kernel(const double *__restrict__ V, const float *__restrict__ Vf, i
                     const double s64 = exact_sq<D>(V + q * D, V + j * D);
                     if (s64 <= r2) {
                         if (FILL) { rowval[pos] = j + 1; nzval[pos] = sqrt(s64); ++pos; }
+                        if (MODE == 2 && cnt < cap) {
+                            slab_j[w * cap + cnt] = (int)j;
+                            slab_s[w * cap + cnt] = s64;
+                        }
                         ++cnt;
                     }
                 }
@@ -88,6 +97,28 @@ brute_rball_kernel(const double *__restrict__ V, const float *__restrict__ Vf, i
         }
     }
     if (!FILL && active) counts[w] = cnt;
+}
+
+// slab -> CSC: one warp per column, coalesced reads of the slab row, contiguous Int64/Float64 bursts
+__global__ void __launch_bounds__(256)
+slab_to_csc(const int *__restrict__ slab_j, const double *__restrict__ slab_s, int cap, int64_t nq,
+            const int64_t *__restrict__ colptr, int64_t *__restrict__ rowval, double *__restrict__ nzval) {
+    const int lane = threadIdx.x & 31;
+    const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t w = gw; w < nq; w += nw) {
+        const int64_t base = colptr[w] - 1;
+        const int k = (int)(colptr[w + 1] - colptr[w]);
+        for (int e = lane; e < k; e += 32) {
+            rowval[base + e] = (int64_t)slab_j[w * cap + e] + 1;
+            nzval[base + e] = sqrt(slab_s[w * cap + e]);
+        }
+    }
+}
+__global__ void max_count(const int *__restrict__ counts, int64_t n, int *__restrict__ out) {
+    int m = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) m = max(m, counts[i]);
+    for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, m);
 }
 
 // threshold for the FP32 pass: every pair with exact s <= r^2 satisfies s32 <= thr
@@ -119,29 +150,71 @@ static int brute_build(mpb200_samples *s, double r, mpb200_table *t) {
     float *Vf = s->sorted_pos.as<float>();
     to_float_padded<D><<<(unsigned)ceil_div(N, 256), 256, 0, st>>>(V, N, Vf);
     MPB_LAUNCHED();
-    if (int rc = t->counts.reserve(sizeof(int) * (size_t)(nq + 1))) return rc;
+    if (int rc = t->counts.reserve(sizeof(int) * (size_t)(nq + 2))) return rc;
     if (int rc = t->colptr.reserve(sizeof(int64_t) * (size_t)(nq + 1))) return rc;
     const unsigned nb = (unsigned)ceil_div(nq > 0 ? nq : 1, kBrThreads);
+    const double r2 = r * r;
+    int *counts = t->counts.as<int>();
+    int *d_max = reinterpret_cast<int *>(c.d_scalar + 2);
     phase_mark(1);
+    // ---- slab capacity from a probe of up to 2048 query columns (exact counts for those columns)
+    int cap = 0;
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
     if (nq > 0) {
-        brute_rball_kernel<D, false><<<nb, kBrThreads, 0, st>>>(V, Vf, N, s->q0, nq, r * r, thr32, t->counts.as<int>(),
-                                                               nullptr, nullptr, nullptr);
+        const int64_t probe = nq < 2048 ? nq : 2048;
+        MPB_CUDA(cudaMemsetAsync(d_max, 0, sizeof(int), st));
+        brute_rball_kernel<D, 0><<<(unsigned)ceil_div(probe, kBrThreads), kBrThreads, 0, st>>>(
+            V, Vf, N, s->q0, probe, r2, thr32, counts, nullptr, nullptr, nullptr, 0, nullptr, nullptr);
+        MPB_LAUNCHED();
+        max_count<<<8, 256, 0, st>>>(counts, probe, d_max);
+        MPB_LAUNCHED();
+        int h_max = 0;
+        MPB_CUDA(cudaMemcpyAsync(&h_max, d_max, sizeof(int), cudaMemcpyDeviceToHost, st));
+        MPB_CUDA(cudaStreamSynchronize(st));
+        cap = (probe == nq) ? h_max : (h_max + h_max / 2 + 64);
+        cap = (cap + 31) & ~31;
+        // slabs must leave room for the table itself; otherwise use the two-sweep path
+        const double need = 12.0 * (double)cap * (double)nq + 16.0 * 0.8 * (double)cap * (double)nq;
+        if (cap == 0 || need > 0.8 * (double)free_b) cap = 0;
+    }
+    bool single = cap > 0;
+    if (single) {
+        if (int rc = t->scratch.reserve(12 * (size_t)cap * (size_t)nq + 64)) return rc;
+        double *slab_s = t->scratch.as<double>();
+        int *slab_j = reinterpret_cast<int *>(slab_s + (size_t)cap * (size_t)nq);
+        brute_rball_kernel<D, 2><<<nb, kBrThreads, 0, st>>>(V, Vf, N, s->q0, nq, r2, thr32, counts, nullptr, nullptr,
+                                                           nullptr, cap, slab_j, slab_s);
+        MPB_LAUNCHED();
+        MPB_CUDA(cudaMemsetAsync(d_max, 0, sizeof(int), st));
+        max_count<<<64, 256, 0, st>>>(counts, nq, d_max);
+        MPB_LAUNCHED();
+    } else if (nq > 0) {
+        brute_rball_kernel<D, 0><<<nb, kBrThreads, 0, st>>>(V, Vf, N, s->q0, nq, r2, thr32, counts, nullptr, nullptr,
+                                                           nullptr, 0, nullptr, nullptr);
         MPB_LAUNCHED();
     }
-    if (int rc = exclusive_scan<int, int64_t>(t->counts.as<int>(), nq, t->colptr.as<int64_t>(), (int64_t)1, s->scan_tmp,
-                                              c.d_scalar))
+    if (int rc = exclusive_scan<int, int64_t>(counts, nq, t->colptr.as<int64_t>(), (int64_t)1, s->scan_tmp, c.d_scalar))
         return rc;
     phase_mark(2);
-    MPB_CUDA(cudaMemcpyAsync(c.h_scalar, c.d_scalar, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    MPB_CUDA(cudaMemcpyAsync(c.h_scalar, c.d_scalar, sizeof(int64_t) * 3, cudaMemcpyDeviceToHost, st));
     MPB_CUDA(cudaStreamSynchronize(st));
     const int64_t nnz = c.h_scalar[0];
+    if (single && *reinterpret_cast<int *>(c.h_scalar + 2) > cap) single = false;  // a slab overflowed: two-sweep fill
     if (int rc = t->rowval.reserve(sizeof(int64_t) * (size_t)(nnz + 1))) return rc;
     if (int rc = t->nzval.reserve(sizeof(double) * (size_t)(nnz + 1))) return rc;
     phase_mark(3);
     if (nq > 0 && nnz > 0) {
-        brute_rball_kernel<D, true><<<nb, kBrThreads, 0, st>>>(V, Vf, N, s->q0, nq, r * r, thr32, nullptr,
-                                                              t->colptr.as<int64_t>(), t->rowval.as<int64_t>(),
-                                                              t->nzval.as<double>());
+        if (single) {
+            const double *slab_s = t->scratch.as<double>();
+            const int *slab_j = reinterpret_cast<const int *>(slab_s + (size_t)cap * (size_t)nq);
+            slab_to_csc<<<(unsigned)(ctx().sm_count * 8), 256, 0, st>>>(slab_j, slab_s, cap, nq, t->colptr.as<int64_t>(),
+                                                                       t->rowval.as<int64_t>(), t->nzval.as<double>());
+        } else {
+            brute_rball_kernel<D, 1><<<nb, kBrThreads, 0, st>>>(V, Vf, N, s->q0, nq, r2, thr32, nullptr,
+                                                               t->colptr.as<int64_t>(), t->rowval.as<int64_t>(),
+                                                               t->nzval.as<double>(), 0, nullptr, nullptr);
+        }
         MPB_LAUNCHED();
     }
     phase_mark(4);

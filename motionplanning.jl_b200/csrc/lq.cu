@@ -137,14 +137,18 @@ __device__ __forceinline__ bool lq_pair(const LqDev &L, const double *x0, const 
 constexpr int kLqThreads = 128;
 constexpr int kLqTile = 128;
 
-// K5.  FILL = false: per-column counts for both directions; FILL = true: rows + costs.
-template <int D, bool FILL>
+// K5.  MODE 0: per-column counts for both directions; MODE 1: rows + costs into the CSC arrays;
+// MODE 2: ONE sweep that counts and appends every neighbour (index, cost) to the column's slab
+// (capacity `cap` per direction), finished by lq_slab_to_csc -- the all-pairs work runs once.
+template <int D, int MODE>
 __global__ void __launch_bounds__(kLqThreads)
 lq_inball_kernel(const double *__restrict__ V, int64_t N, int64_t q0, int64_t nq, LqDev L, double r,
                  int *__restrict__ countsF, int *__restrict__ countsB, const int64_t *__restrict__ colptrF,
                  const int64_t *__restrict__ colptrB, int64_t *__restrict__ rowvalF, double *__restrict__ nzvalF,
-                 int64_t *__restrict__ rowvalB, double *__restrict__ nzvalB) {
+                 int64_t *__restrict__ rowvalB, double *__restrict__ nzvalB, int cap, int *__restrict__ slabF_j,
+                 double *__restrict__ slabF_c, int *__restrict__ slabB_j, double *__restrict__ slabB_c) {
     constexpr int NS = 2 * D;
+    constexpr bool FILL = (MODE == 1);
     __shared__ double tile[kLqTile * NS];
     const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = w < nq;
@@ -170,15 +174,39 @@ lq_inball_kernel(const double *__restrict__ V, int64_t N, int64_t q0, int64_t nq
             double c;
             if (lq_pair<D>(L, x, y, r, &c)) {  // forwards: cost(V[q] -> V[j])
                 if (FILL) { rowvalF[posF] = j + 1; nzvalF[posF] = c; ++posF; }
+                if (MODE == 2 && nF < cap) { slabF_j[w * cap + nF] = (int)j; slabF_c[w * cap + nF] = c; }
                 ++nF;
             }
             if (lq_pair<D>(L, y, x, r, &c)) {  // backwards: cost(V[j] -> V[q])
                 if (FILL) { rowvalB[posB] = j + 1; nzvalB[posB] = c; ++posB; }
+                if (MODE == 2 && nB < cap) { slabB_j[w * cap + nB] = (int)j; slabB_c[w * cap + nB] = c; }
                 ++nB;
             }
         }
     }
     if (!FILL && active) { countsF[w] = nF; countsB[w] = nB; }
+}
+
+__global__ void __launch_bounds__(256)
+lq_slab_to_csc(const int *__restrict__ slab_j, const double *__restrict__ slab_c, int cap, int64_t nq,
+               const int64_t *__restrict__ colptr, int64_t *__restrict__ rowval, double *__restrict__ nzval) {
+    const int lane = threadIdx.x & 31;
+    const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t w = gw; w < nq; w += nw) {
+        const int64_t base = colptr[w] - 1;
+        const int k = (int)(colptr[w + 1] - colptr[w]);
+        for (int e = lane; e < k; e += 32) {
+            rowval[base + e] = (int64_t)slab_j[w * cap + e] + 1;
+            nzval[base + e] = slab_c[w * cap + e];
+        }
+    }
+}
+__global__ void lq_max_count(const int *__restrict__ a, const int *__restrict__ b, int64_t n, int *__restrict__ out) {
+    int m = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        m = max(m, max(a[i], b[i]));
+    for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, m);
 }
 
 template <int D>
@@ -328,11 +356,52 @@ static int lq_build(mpb200_samples *s, const mpb200_lq *lq, double r, mpb200_tab
         if (int rc = t->colptr.reserve(sizeof(int64_t) * (size_t)(nq + 1))) return rc;
     }
     const unsigned nb = (unsigned)ceil_div(nq > 0 ? nq : 1, kLqThreads);
+    int *d_max = reinterpret_cast<int *>(c.d_scalar + 2);
     phase_mark(0);
+    // slab capacity from a probe of up to 1024 query columns (exact counts for those columns)
+    int cap = 0;
     if (nq > 0) {
-        lq_inball_kernel<D, false><<<nb, kLqThreads, 0, st>>>(V, N, s->q0, nq, L, r, tF->counts.as<int>(),
+        const int64_t probe = nq < 1024 ? nq : 1024;
+        MPB_CUDA(cudaMemsetAsync(d_max, 0, sizeof(int), st));
+        lq_inball_kernel<D, 0><<<(unsigned)ceil_div(probe, kLqThreads), kLqThreads, 0, st>>>(
+            V, N, s->q0, probe, L, r, tF->counts.as<int>(), tB->counts.as<int>(), nullptr, nullptr, nullptr, nullptr,
+            nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr);
+        MPB_LAUNCHED();
+        lq_max_count<<<8, 256, 0, st>>>(tF->counts.as<int>(), tB->counts.as<int>(), probe, d_max);
+        MPB_LAUNCHED();
+        int h_max = 0;
+        MPB_CUDA(cudaMemcpyAsync(&h_max, d_max, sizeof(int), cudaMemcpyDeviceToHost, st));
+        MPB_CUDA(cudaStreamSynchronize(st));
+        cap = (probe == nq) ? h_max : (2 * h_max + 64);
+        cap = (cap + 31) & ~31;
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        if (cap == 0 || 56.0 * (double)cap * (double)nq > 0.8 * (double)free_b) cap = 0;
+    }
+    bool single = cap > 0;
+    int *slabF_j = nullptr, *slabB_j = nullptr;
+    double *slabF_c = nullptr, *slabB_c = nullptr;
+    if (single) {
+        const size_t per = (size_t)cap * (size_t)nq;
+        if (int rc = tF->scratch.reserve(24 * per + 64)) return rc;
+        slabF_c = tF->scratch.as<double>();
+        slabB_c = slabF_c + per;
+        slabF_j = reinterpret_cast<int *>(slabB_c + per);
+        slabB_j = slabF_j + per;
+    }
+    if (nq > 0) {
+        if (single) {
+            lq_inball_kernel<D, 2><<<nb, kLqThreads, 0, st>>>(V, N, s->q0, nq, L, r, tF->counts.as<int>(),
                                                              tB->counts.as<int>(), nullptr, nullptr, nullptr, nullptr,
-                                                             nullptr, nullptr);
+                                                             nullptr, nullptr, cap, slabF_j, slabF_c, slabB_j, slabB_c);
+            MPB_LAUNCHED();
+            MPB_CUDA(cudaMemsetAsync(d_max, 0, sizeof(int), st));
+            lq_max_count<<<64, 256, 0, st>>>(tF->counts.as<int>(), tB->counts.as<int>(), nq, d_max);
+        } else {
+            lq_inball_kernel<D, 0><<<nb, kLqThreads, 0, st>>>(V, N, s->q0, nq, L, r, tF->counts.as<int>(),
+                                                             tB->counts.as<int>(), nullptr, nullptr, nullptr, nullptr,
+                                                             nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr);
+        }
         MPB_LAUNCHED();
     }
     if (int rc = exclusive_scan<int, int64_t>(tF->counts.as<int>(), nq, tF->colptr.as<int64_t>(), (int64_t)1, s->scan_tmp,
@@ -342,19 +411,30 @@ static int lq_build(mpb200_samples *s, const mpb200_lq *lq, double r, mpb200_tab
                                               c.d_scalar + 1))
         return rc;
     phase_mark(1);
-    MPB_CUDA(cudaMemcpyAsync(c.h_scalar, c.d_scalar, sizeof(int64_t) * 2, cudaMemcpyDeviceToHost, st));
+    MPB_CUDA(cudaMemcpyAsync(c.h_scalar, c.d_scalar, sizeof(int64_t) * 3, cudaMemcpyDeviceToHost, st));
     MPB_CUDA(cudaStreamSynchronize(st));
     const int64_t nnzF = c.h_scalar[0], nnzB = c.h_scalar[1];
+    if (single && *reinterpret_cast<int *>(c.h_scalar + 2) > cap) single = false;  // a slab overflowed
     if (int rc = tF->rowval.reserve(sizeof(int64_t) * (size_t)(nnzF + 1))) return rc;
     if (int rc = tF->nzval.reserve(sizeof(double) * (size_t)(nnzF + 1))) return rc;
     if (int rc = tB->rowval.reserve(sizeof(int64_t) * (size_t)(nnzB + 1))) return rc;
     if (int rc = tB->nzval.reserve(sizeof(double) * (size_t)(nnzB + 1))) return rc;
     phase_mark(2);
     if (nq > 0 && (nnzF > 0 || nnzB > 0)) {
-        lq_inball_kernel<D, true><<<nb, kLqThreads, 0, st>>>(V, N, s->q0, nq, L, r, nullptr, nullptr,
-                                                            tF->colptr.as<int64_t>(), tB->colptr.as<int64_t>(),
-                                                            tF->rowval.as<int64_t>(), tF->nzval.as<double>(),
-                                                            tB->rowval.as<int64_t>(), tB->nzval.as<double>());
+        if (single) {
+            const unsigned g2 = (unsigned)(ctx().sm_count * 8);
+            lq_slab_to_csc<<<g2, 256, 0, st>>>(slabF_j, slabF_c, cap, nq, tF->colptr.as<int64_t>(), tF->rowval.as<int64_t>(),
+                                               tF->nzval.as<double>());
+            MPB_LAUNCHED();
+            lq_slab_to_csc<<<g2, 256, 0, st>>>(slabB_j, slabB_c, cap, nq, tB->colptr.as<int64_t>(), tB->rowval.as<int64_t>(),
+                                               tB->nzval.as<double>());
+        } else {
+            lq_inball_kernel<D, 1><<<nb, kLqThreads, 0, st>>>(V, N, s->q0, nq, L, r, nullptr, nullptr,
+                                                             tF->colptr.as<int64_t>(), tB->colptr.as<int64_t>(),
+                                                             tF->rowval.as<int64_t>(), tF->nzval.as<double>(),
+                                                             tB->rowval.as<int64_t>(), tB->nzval.as<double>(), 0, nullptr,
+                                                             nullptr, nullptr, nullptr);
+        }
         MPB_LAUNCHED();
     }
     phase_mark(3);

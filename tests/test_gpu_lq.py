@@ -116,3 +116,23 @@ def test_k9_lq_edges_match_oracle(gpu, orc, checker):
     mp.setup_steering(SS, r)                         # linearquadratic.jl:34
     assert mp.is_free_motion(V[cB.D.rowval[0] - 1], V[cols[0]], CC, SS) == bool(got[0])
     NN.close()
+
+
+def test_k5_single_sweep_slab_overflow_falls_back(gpu, orc):
+    mp = gpu
+    rng = np.random.Generator(np.random.PCG64(8))
+    spread = np.hstack([rng.random((1500, 2)), (rng.random((1500, 2)) * 2 - 1) * 1.5])
+    cluster = np.hstack([0.5 + 0.01 * rng.random((400, 2)), 0.05 * (rng.random((400, 2)) - 0.5)])
+    V = np.vstack([spread, cluster])
+    r = 0.6
+    SS = mp.DoubleIntegrator(2)
+    L = orc.DoubleIntegratorLQ(2)
+    NN = mp.QuasiMetricNN(V, SS.dist)
+    cF, cB = NN.precompute(r)
+    for cache, fwd in ((cF, True), (cB, False)):
+        ref = L.inball(V, r, fwd)
+        assert np.array_equal(cache.D.colptr, ref[0]) and np.array_equal(cache.D.rowval, ref[1])
+        assert cache.D.nzval.tobytes() == ref[2].tobytes()
+    deg = np.diff(cB.D.colptr)
+    assert 2 * deg[:1024].max() + 64 < deg.max()
+    NN.close()

@@ -308,3 +308,21 @@ def test_fused_build_checked_equals_separate_calls(gpu, orc, checker):
     if D.nnz % 64:
         assert int(bits[-1]) >> (D.nnz % 64) == 0
     NN.close()
+
+
+def test_k3_single_sweep_slab_overflow_falls_back(gpu, orc):
+    """the slab capacity is sized from a probe of the first 2048 columns; a dense cluster among
+    later indices overflows it and the build must fall back to the two-sweep fill"""
+    mp = gpu
+    rng = np.random.Generator(np.random.PCG64(5))
+    d = 5
+    V = np.vstack([rng.random((3000, d)), 3.0 + 0.01 * rng.random((700, d)), rng.random((300, d))])   # cluster far away
+    r = 0.12
+    NN = mp.MetricNN(V)
+    D = NN.precompute(r).D
+    ref = orc.rball_brute(V, r)
+    assert np.array_equal(D.colptr, ref[0]) and np.array_equal(D.rowval, ref[1])
+    assert D.nzval.tobytes() == ref[2].tobytes()
+    deg = np.diff(D.colptr)
+    assert deg[:2048].max() * 1.5 + 64 < deg.max()        # the probe really underestimates
+    NN.close()
