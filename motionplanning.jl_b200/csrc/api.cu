@@ -213,7 +213,7 @@ int mpb200_samples_destroy(mpb200_samples *s) {
     if (ctx().ready) cudaStreamSynchronize(ctx().stream);
     if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
     s->V.release(); s->cell_start.release(); s->cell_fill.release(); s->sorted_idx.release();
-    s->sorted_pos.release(); s->minmax.release(); s->scan_tmp.release(); s->point_bits.release(); s->q_order.release();
+    s->sorted_pos.release(); s->minmax.release(); s->scan_tmp.release(); s->point_bits.release(); s->q_order.release(); s->aux.release();
     delete s;
     return MPB200_OK;
 }

@@ -14,6 +14,8 @@
 // registers) and walks the samples in index order, so rows come out ascending and need no sort.
 #include "common.cuh"
 #include "scan.cuh"
+#include "tc_rball.cuh"
+#include <cstdlib>
 
 namespace mpb {
 
@@ -145,11 +147,23 @@ static int brute_build(mpb200_samples *s, double r, mpb200_table *t) {
     const float thr32 = prefilter_threshold(r, D, M);
     if (!(M < 1e18)) return fail(MPB200_EARG, "sample coordinates out of range for the FP32 prefilter");
 
+    // tensor-core prefilter (tc_rball.cu) for 4 <= d <= 14; MPB200_NO_TC=1 selects the FP32 CUDA-core sweep
+    static const bool no_tc = getenv("MPB200_NO_TC") != nullptr;
+    constexpr bool kTcDim = (D >= 4 && D <= 14);
+    const bool use_tc = kTcDim && !no_tc;
+    TcPlan plan = {nullptr, nullptr, 0, 0.0f};
     phase_mark(0);
-    if (int rc = s->sorted_pos.reserve(sizeof(float) * (size_t)(N * DP + 4))) return rc;  // reused as the FP32 copy
-    float *Vf = s->sorted_pos.as<float>();
-    to_float_padded<D><<<(unsigned)ceil_div(N, 256), 256, 0, st>>>(V, N, Vf);
-    MPB_LAUNCHED();
+    float *Vf = nullptr;
+    if (use_tc) {
+        if constexpr (kTcDim) {
+            if (int rc = tc_prepare_operands<D>(s, r, &plan)) return rc;
+        }
+    } else {
+        if (int rc = s->sorted_pos.reserve(sizeof(float) * (size_t)(N * DP + 4))) return rc;  // reused as the FP32 copy
+        Vf = s->sorted_pos.as<float>();
+        to_float_padded<D><<<(unsigned)ceil_div(N, 256), 256, 0, st>>>(V, N, Vf);
+        MPB_LAUNCHED();
+    }
     if (int rc = t->counts.reserve(sizeof(int) * (size_t)(nq + 2))) return rc;
     if (int rc = t->colptr.reserve(sizeof(int64_t) * (size_t)(nq + 1))) return rc;
     const unsigned nb = (unsigned)ceil_div(nq > 0 ? nq : 1, kBrThreads);
@@ -164,9 +178,15 @@ static int brute_build(mpb200_samples *s, double r, mpb200_table *t) {
     if (nq > 0) {
         const int64_t probe = nq < 2048 ? nq : 2048;
         MPB_CUDA(cudaMemsetAsync(d_max, 0, sizeof(int), st));
-        brute_rball_kernel<D, 0><<<(unsigned)ceil_div(probe, kBrThreads), kBrThreads, 0, st>>>(
-            V, Vf, N, s->q0, probe, r2, thr32, counts, nullptr, nullptr, nullptr, 0, nullptr, nullptr);
-        MPB_LAUNCHED();
+        if (use_tc) {
+            if constexpr (kTcDim) {
+                if (int rc = tc_sweep<D>(s, plan, r, probe, counts, 0, nullptr, nullptr)) return rc;
+            }
+        } else {
+            brute_rball_kernel<D, 0><<<(unsigned)ceil_div(probe, kBrThreads), kBrThreads, 0, st>>>(
+                V, Vf, N, s->q0, probe, r2, thr32, counts, nullptr, nullptr, nullptr, 0, nullptr, nullptr);
+            MPB_LAUNCHED();
+        }
         max_count<<<8, 256, 0, st>>>(counts, probe, d_max);
         MPB_LAUNCHED();
         int h_max = 0;
@@ -183,16 +203,28 @@ static int brute_build(mpb200_samples *s, double r, mpb200_table *t) {
         if (int rc = t->scratch.reserve(12 * (size_t)cap * (size_t)nq + 64)) return rc;
         double *slab_s = t->scratch.as<double>();
         int *slab_j = reinterpret_cast<int *>(slab_s + (size_t)cap * (size_t)nq);
-        brute_rball_kernel<D, 2><<<nb, kBrThreads, 0, st>>>(V, Vf, N, s->q0, nq, r2, thr32, counts, nullptr, nullptr,
-                                                           nullptr, cap, slab_j, slab_s);
-        MPB_LAUNCHED();
+        if (use_tc) {
+            if constexpr (kTcDim) {
+                if (int rc = tc_sweep<D>(s, plan, r, nq, counts, cap, slab_j, slab_s)) return rc;
+            }
+        } else {
+            brute_rball_kernel<D, 2><<<nb, kBrThreads, 0, st>>>(V, Vf, N, s->q0, nq, r2, thr32, counts, nullptr, nullptr,
+                                                               nullptr, cap, slab_j, slab_s);
+            MPB_LAUNCHED();
+        }
         MPB_CUDA(cudaMemsetAsync(d_max, 0, sizeof(int), st));
         max_count<<<64, 256, 0, st>>>(counts, nq, d_max);
         MPB_LAUNCHED();
     } else if (nq > 0) {
-        brute_rball_kernel<D, 0><<<nb, kBrThreads, 0, st>>>(V, Vf, N, s->q0, nq, r2, thr32, counts, nullptr, nullptr,
-                                                           nullptr, 0, nullptr, nullptr);
-        MPB_LAUNCHED();
+        if (use_tc) {
+            if constexpr (kTcDim) {
+                if (int rc = tc_sweep<D>(s, plan, r, nq, counts, 0, nullptr, nullptr)) return rc;
+            }
+        } else {
+            brute_rball_kernel<D, 0><<<nb, kBrThreads, 0, st>>>(V, Vf, N, s->q0, nq, r2, thr32, counts, nullptr, nullptr,
+                                                               nullptr, 0, nullptr, nullptr);
+            MPB_LAUNCHED();
+        }
     }
     if (int rc = exclusive_scan<int, int64_t>(counts, nq, t->colptr.as<int64_t>(), (int64_t)1, s->scan_tmp, c.d_scalar))
         return rc;
@@ -211,6 +243,12 @@ static int brute_build(mpb200_samples *s, double r, mpb200_table *t) {
             slab_to_csc<<<(unsigned)(ctx().sm_count * 8), 256, 0, st>>>(slab_j, slab_s, cap, nq, t->colptr.as<int64_t>(),
                                                                        t->rowval.as<int64_t>(), t->nzval.as<double>());
         } else {
+            if (!Vf) {  // two-sweep fill after a tensor-core count: the FP32 copy is built now (aux holds it)
+                if (int rc = s->q_order.reserve(sizeof(float) * (size_t)(N * DP + 4))) return rc;
+                Vf = s->q_order.as<float>();
+                to_float_padded<D><<<(unsigned)ceil_div(N, 256), 256, 0, st>>>(V, N, Vf);
+                MPB_LAUNCHED();
+            }
             brute_rball_kernel<D, 1><<<nb, kBrThreads, 0, st>>>(V, Vf, N, s->q0, nq, r2, thr32, nullptr,
                                                                t->colptr.as<int64_t>(), t->rowval.as<int64_t>(),
                                                                t->nzval.as<double>(), 0, nullptr, nullptr);

@@ -109,6 +109,7 @@ struct mpb200_samples {
     mpb::DevBuf scan_tmp;    // scan block sums
     mpb::DevBuf q_order;     // int32: cell-order positions owned by this shard (+ scratch)
     mpb::DevBuf point_bits;  // uint64 ceil(N/64): last mpb200_points_free result
+    mpb::DevBuf aux;         // small per-build constants (e.g. the centring vector of the tensor-core path)
     // CUDA graph of the launch-bound front half of a grid build (K1 + count + scans), replayed
     // while the launch parameters (sizes, radius, buffer addresses) stay the same
     cudaGraphExec_t graph_exec = nullptr;

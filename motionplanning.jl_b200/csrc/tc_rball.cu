@@ -1,0 +1,308 @@
+// tc_rball.cu -- K3 on the 5th-generation tensor cores: the all-pairs prefilter of the d >= 4
+// Euclidean r-ball as a TF32 tcgen05.mma with TMEM accumulators, K4 (exact FP64 recheck) unchanged.
+//
+// For centred points x~ = x - c the membership test  |x - y|^2 <= r^2  is
+//      x~.y~ + (r^2 - |y~|^2)/2  >=  |x~|^2 / 2 .
+// The left side is ONE dense contraction over K = 16: slots 0..d-1 hold the coordinates, two
+// more slots hold a hi/lo TF32 split of (r^2 - |y~|^2)/2 on the sample side against 1.0 on the
+// query side.  A CTA owns 128 query columns (operand A, 128 x 16, staged once) and sweeps the
+// samples in tiles of 128 (operand B): two tcgen05.mma.kind::tf32 (M=128, N=128, K=8) per tile
+// write a 128 x 128 FP32 accumulator into tensor memory; the four warps read their TMEM lanes
+// back with tcgen05.ld (one query row per thread) and keep a running max per 32 columns, so the
+// epilogue costs ~1 instruction per pair; only chunks whose max passes  |x~|^2/2 - delta  are
+// rescanned, and only survivors reach the exact FP64 test that decides membership and the stored
+// distance.  delta bounds the TF32 input rounding and FP32 accumulation error, so
+// the prefilter has no false negatives.  Up to four CTAs share an SM (4 x 128 TMEM columns), which
+// overlaps one CTA's MMA with the others' epilogues without an explicit pipeline.
+#include "common.cuh"
+#include "scan.cuh"
+#include "tc_rball.cuh"
+
+namespace mpb {
+
+constexpr int kTcM = 128;      // query rows per CTA (= threads: one TMEM lane per thread)
+constexpr int kTcN = 128;      // samples per MMA tile (= TMEM columns per CTA)
+constexpr int kTcK = 16;       // contraction length: d coordinates + 2 threshold slots, zero padded
+
+__device__ __forceinline__ float to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+// Operand arrays in the canonical K-major / no-swizzle UMMA layout, per tile of 128 rows:
+//   [chunk 0..3][row 0..127][4 x tf32]   (16-byte chunks; core matrix = 8 rows x 16 B contiguous)
+// B version: slots d, d+1 = hi/lo of (r^2 - |y~|^2)/2.   nrm_half[j] = |x~_j|^2 / 2 (FP32).
+template <int D>
+__global__ void __launch_bounds__(256)
+tc_prepare(const double *__restrict__ V, int64_t N, int64_t Npad, const double *__restrict__ center, double r2,
+           float *__restrict__ opB, float *__restrict__ nrm_half) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= Npad) return;
+    float slot[kTcK];
+#pragma unroll
+    for (int k = 0; k < kTcK; ++k) slot[k] = 0.0f;
+    float nh = __int_as_float(0x7f800000);  // padding rows: +inf norm -> never a candidate as a query
+    if (j < N) {
+        double n2 = 0.0;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            const double xc = V[j * D + k] - center[k];
+            n2 += xc * xc;
+            slot[k] = to_tf32((float)xc);
+        }
+        const float v = (float)(0.5 * (r2 - n2));
+        const float hi = to_tf32(v);
+        slot[D] = hi;
+        slot[D + 1] = to_tf32(v - hi);
+        nh = (float)(0.5 * n2);
+    } else {
+        slot[D] = -3.0e38f;  // padding samples: the contraction is hugely negative -> never a candidate
+    }
+    nrm_half[j] = nh;
+    const int64_t tile = j >> 7, row = j & 127;
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+        reinterpret_cast<float4 *>(opB)[(tile * 4 + c) * 128 + row] =
+            make_float4(slot[4 * c], slot[4 * c + 1], slot[4 * c + 2], slot[4 * c + 3]);
+}
+
+// ---- raw tcgen05 / mbarrier PTX ----------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+// start address >> 4 in [0,14), leading (K-chunk) byte offset >> 4 in [16,30), stride (8-row group)
+// byte offset >> 4 in [32,46), version 1 in [46,48), layout type 0 in [61,64)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32) | (1ULL << 46);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 (bits 4-5 = 1), A = B = TF32
+// (bits 7-9, 10-12 = 2), both K-major, N >> 3 in [17,23), M >> 4 in [24,29)
+__device__ __forceinline__ uint32_t umma_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+                 :: "r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    // bounded spin: a mis-programmed MMA must not hang the GPU -- trap after ~seconds instead
+    for (unsigned tries = 0; tries < (1u << 28); ++tries) {
+        uint32_t done;
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t *r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+template <int D>
+__device__ __forceinline__ double tc_exact_sq(const double *__restrict__ a, const double *__restrict__ b) {
+    double t = __dsub_rn(a[0], b[0]);
+    double s = __dmul_rn(t, t);
+#pragma unroll
+    for (int i = 1; i < D; ++i) {
+        t = __dsub_rn(a[i], b[i]);
+        s = __dadd_rn(s, __dmul_rn(t, t));
+    }
+    return s;
+}
+
+// MODE 0: count only, MODE 2: count + append (index, exact squared distance) to the column's slab
+template <int D, int MODE>
+__global__ void __launch_bounds__(kTcM, 4)
+tc_rball_kernel(const double *__restrict__ V, const float *__restrict__ opB, const float *__restrict__ nrm_half,
+                int64_t N, int64_t Npad, int64_t q0, int64_t nq, double r2, float delta, int *__restrict__ counts,
+                int cap, int *__restrict__ slab_j, double *__restrict__ slab_s) {
+    __shared__ __align__(128) float4 sA[4 * kTcM];   // 8 KB
+    __shared__ __align__(128) float4 sB[4 * kTcN];   // 8 KB
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ uint32_t s_tmem;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int64_t w = (int64_t)blockIdx.x * kTcM + tid;
+    const bool active = w < nq;
+    const int64_t q = q0 + w;
+
+    // operand A: this thread's query row, threshold slots replaced by 1.0 (exact in TF32)
+    {
+        const int64_t qq = active ? q : 0;
+        const int64_t tile = qq >> 7, row = qq & 127;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            float4 v = reinterpret_cast<const float4 *>(opB)[(tile * 4 + c) * 128 + row];
+            float f[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int k = 4 * c + e;
+                if (k == D || k == D + 1) f[e] = 1.0f;
+                if (!active) f[e] = 0.0f;
+            }
+            sA[c * kTcM + tid] = make_float4(f[0], f[1], f[2], f[3]);
+        }
+    }
+    // pass iff acc >= |x~|^2/2 - delta ; inactive rows never pass
+    const float pass_at = active ? (nrm_half[q] - delta) : __int_as_float(0x7f800000);
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&s_tmem)), "r"(kTcN));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    if (tid == 0) {
+        mbar_init(smem_u32(&s_bar), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = s_tmem;
+    const uint32_t idesc = umma_idesc_tf32(kTcM, kTcN);
+    // chunk stride (LBO) = 128 rows x 16 B, 8-row group stride (SBO) = 128 B; the second MMA (K slots
+    // 8..15) starts two chunks further
+    const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
+    const uint64_t a_desc0 = umma_desc(a0, kTcM * 16, 128), a_desc1 = umma_desc(a0 + 2 * kTcM * 16, kTcM * 16, 128);
+    const uint64_t b_desc0 = umma_desc(b0, kTcN * 16, 128), b_desc1 = umma_desc(b0 + 2 * kTcN * 16, kTcN * 16, 128);
+    const uint32_t bar = smem_u32(&s_bar);
+    const uint32_t my_tmem = tmem + ((uint32_t)(warp * 32) << 16);
+
+    int cnt = 0;
+    uint32_t phase = 0;
+    for (int64_t t0 = 0; t0 < Npad; t0 += kTcN) {
+        // stage operand B: the tile is one contiguous 8 KB block already in the smem layout
+        {
+            const float4 *src = reinterpret_cast<const float4 *>(opB) + (t0 >> 7) * (4 * 128);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) sB[i * kTcN + tid] = src[i * 128 + tid];
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> tensor core
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            umma_tf32(tmem, a_desc0, b_desc0, idesc, 0u);
+            umma_tf32(tmem, a_desc1, b_desc1, idesc, 1u);
+            umma_commit(bar);
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1u;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // epilogue: row `tid` of the 128 x 128 accumulator, 32 columns at a time
+#pragma unroll 1
+        for (int c0 = 0; c0 < kTcN; c0 += 32) {
+            uint32_t rr[32];
+            tmem_ld32(my_tmem + (uint32_t)c0, rr);
+            float m0 = __uint_as_float(rr[0]), m1 = __uint_as_float(rr[1]), m2 = __uint_as_float(rr[2]),
+                  m3 = __uint_as_float(rr[3]);
+#pragma unroll
+            for (int i = 4; i < 32; i += 4) {
+                m0 = fmaxf(m0, __uint_as_float(rr[i]));
+                m1 = fmaxf(m1, __uint_as_float(rr[i + 1]));
+                m2 = fmaxf(m2, __uint_as_float(rr[i + 2]));
+                m3 = fmaxf(m3, __uint_as_float(rr[i + 3]));
+            }
+            if (fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) >= pass_at) {
+                uint32_t mask = 0;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) mask |= (__uint_as_float(rr[i]) >= pass_at) ? (1u << i) : 0u;
+                while (mask) {  // K4: the exact FP64 test decides membership and the stored distance
+                    const int i = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const int64_t j = t0 + c0 + i;
+                    if (j < N && j != q) {
+                        const double s64 = tc_exact_sq<D>(V + q * D, V + j * D);
+                        if (s64 <= r2) {
+                            if (MODE == 2 && cnt < cap) {
+                                slab_j[w * cap + cnt] = (int)j;
+                                slab_s[w * cap + cnt] = s64;
+                            }
+                            ++cnt;
+                        }
+                    }
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();  // accumulator and sB are free for the next tile
+    }
+    if (active) counts[w] = cnt;
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(kTcN));
+}
+
+// ---- host side -------------------------------------------------------------------------------------
+// delta: half of the worst-case error of the computed test quantity (see header + DESIGN.md 10)
+static float tc_delta(double r, int D, double Rmax2) {
+    const double u_tf32 = 4.8828125e-4;                       // 2^-11, cvt.rna
+    const double e_dot = 2.0 * u_tf32 * (1.0 + u_tf32) * Rmax2;     // |x~.y~ - tf32(x~).tf32(y~)| <= 2u(1+u)|x~||y~|
+    const double e_acc = 64.0 * 1.1920929e-7 * (Rmax2 + 0.5 * (r * r + Rmax2));  // FP32 accumulation of 16 products
+    const double e_thr = 3.6e-7 * 0.5 * (r * r + Rmax2);     // hi/lo split + FP32 rounding of (r^2-|y~|^2)/2 and |x~|^2/2
+    return (float)(1.5 * (e_dot + e_acc + 2.0 * e_thr) + 1e-30);
+}
+
+
+template <int D>
+int tc_prepare_operands(mpb200_samples *s, double r, TcPlan *plan) {
+    Context &c = ctx();
+    cudaStream_t st = c.stream;
+    const int64_t N = s->N, Npad = (N + 127) & ~int64_t(127);
+    double center[16], Rmax2 = 0;
+    for (int k = 0; k < D; ++k) {
+        center[k] = 0.5 * (s->h_bbox[k] + s->h_bbox[D + k]);
+        const double h = fmax(fabs(s->h_bbox[k] - center[k]), fabs(s->h_bbox[D + k] - center[k]));
+        Rmax2 += h * h;
+    }
+    if (int rc = s->sorted_pos.reserve(sizeof(float) * (size_t)(kTcK + 1) * (size_t)Npad + 256)) return rc;
+    if (int rc = s->aux.reserve(sizeof(double) * 32)) return rc;
+    float *opB = s->sorted_pos.as<float>();
+    float *nrm_half = opB + (size_t)kTcK * (size_t)Npad;
+    double *d_center = s->aux.as<double>();
+    MPB_CUDA(cudaMemcpyAsync(d_center, center, sizeof(double) * D, cudaMemcpyHostToDevice, st));
+    tc_prepare<D><<<(unsigned)ceil_div(Npad, 256), 256, 0, st>>>(s->V.as<double>(), N, Npad, d_center, r * r, opB, nrm_half);
+    MPB_LAUNCHED();
+    plan->opB = opB;
+    plan->nrm_half = nrm_half;
+    plan->Npad = Npad;
+    plan->delta = tc_delta(r, D, Rmax2);
+    return 0;
+}
+
+template <int D>
+int tc_sweep(mpb200_samples *s, const TcPlan &P, double r, int64_t nq_run, int *counts, int cap, int *slab_j,
+             double *slab_s) {
+    cudaStream_t st = ctx().stream;
+    const unsigned nb = (unsigned)ceil_div(nq_run > 0 ? nq_run : 1, kTcM);
+    if (cap > 0)
+        tc_rball_kernel<D, 2><<<nb, kTcM, 0, st>>>(s->V.as<double>(), P.opB, P.nrm_half, s->N, P.Npad, s->q0, nq_run, r * r,
+                                                   P.delta, counts, cap, slab_j, slab_s);
+    else
+        tc_rball_kernel<D, 0><<<nb, kTcM, 0, st>>>(s->V.as<double>(), P.opB, P.nrm_half, s->N, P.Npad, s->q0, nq_run, r * r,
+                                                   P.delta, counts, 0, nullptr, nullptr);
+    MPB_LAUNCHED();
+    return 0;
+}
+
+#define MPB_TC_INSTANTIATE(D_)                                                                                 \
+    template int tc_prepare_operands<D_>(mpb200_samples *, double, TcPlan *);                                   \
+    template int tc_sweep<D_>(mpb200_samples *, const TcPlan &, double, int64_t, int *, int, int *, double *);
+MPB_TC_INSTANTIATE(4) MPB_TC_INSTANTIATE(5) MPB_TC_INSTANTIATE(6) MPB_TC_INSTANTIATE(7) MPB_TC_INSTANTIATE(8)
+MPB_TC_INSTANTIATE(9) MPB_TC_INSTANTIATE(10) MPB_TC_INSTANTIATE(11) MPB_TC_INSTANTIATE(12) MPB_TC_INSTANTIATE(13)
+MPB_TC_INSTANTIATE(14)
+
+}  // namespace mpb

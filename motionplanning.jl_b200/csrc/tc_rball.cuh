@@ -1,0 +1,18 @@
+// tc_rball.cuh -- interface of the tcgen05 prefilter (tc_rball.cu) used by brute_rball.cu
+#pragma once
+#include "common.cuh"
+
+namespace mpb {
+
+struct TcPlan {
+    float *opB;        // TF32 operands in the canonical UMMA layout, [tile of 128][chunk 4][row 128][4]
+    float *nrm_half;   // |x~|^2 / 2 per (padded) sample
+    int64_t Npad;
+    float delta;       // error allowance of the tensor-core test quantity
+};
+template <int D> int tc_prepare_operands(mpb200_samples *s, double r, TcPlan *plan);
+// sweep the first nq_run query columns of the shard; cap > 0: also append hits to the slabs
+template <int D> int tc_sweep(mpb200_samples *s, const TcPlan &P, double r, int64_t nq_run, int *counts, int cap,
+                              int *slab_j, double *slab_s);
+
+}  // namespace mpb
