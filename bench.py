@@ -227,7 +227,12 @@ def main():
 
     n_total = SAMPLES_PER_GPU * world
     r = fmt_radius(n_total, 2)
-    V_host = torch.from_numpy(make_samples(n_total)).pin_memory()
+    samples = make_samples(n_total)
+    if world > 1:
+        # stripe order: each rank's query range is then a spatial stripe and its grid covers only the
+        # stripe + r (FMT* is invariant to the order of i.i.d. samples; N = 1 keeps the raw order)
+        samples = samples[np.argsort(samples[:, 0], kind="stable")]
+    V_host = torch.from_numpy(np.ascontiguousarray(samples)).pin_memory()
     V = V_host.numpy()
     q0, q1 = rank * SAMPLES_PER_GPU, (rank + 1) * SAMPLES_PER_GPU
     CC = mpb200.PointRobot2D(mpb200.obstaclesets.ISRR_2H())
@@ -337,7 +342,7 @@ def main():
             "config": {"workload": "C2: FMT* 2-D unit square, ISRR_2H, N=%d uniform samples (%d query columns per GPU), r=%.7f"
                                    % (n_total, SAMPLES_PER_GPU, r),
                        "l2": "512 MiB flush between timed iterations", "index_type": "int64 (reference ABI)",
-                       "parallelism": "query-range shards x%d, samples+obstacles replicated%s"
+                       "parallelism": "query-range shards x%d (samples in stripe order when x > 1), samples+obstacles replicated%s"
                                       % (world, ", NCCL all-gather of colptr + validity words per step" if world > 1 else "")},
             "nn_queries_per_sec": queries_all / (ms_per_step / 1e3),
             "edges_per_step": edges_all, "mean_degree": deg,

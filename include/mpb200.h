@@ -126,8 +126,9 @@ typedef struct {
 } mpb200_space_desc;
 
 /* ---- batched validity ---------------------------------------------------------- */
-/* F[i] = is_free_state(V[i], CC, SS) for all N samples (fmt.jl:31-36, sampling.jl:25;
- * statespaces.jl:151-152; robots2D.jl:12; boxesND.jl:42-43).  bits: ceil(N/64) words. */
+/* F[i] = is_free_state(V[i], CC, SS) for the samples of the query range [q0, q1) -- all N by
+ * default (fmt.jl:31-36, sampling.jl:25; statespaces.jl:151-152; robots2D.jl:12;
+ * boxesND.jl:42-43).  bits: ceil((q1-q0)/64) words, bit k = sample q0 + k. */
 int mpb200_points_free(const mpb200_samples *s, const mpb200_obstacles *o, const mpb200_space_desc *ss,
                        uint64_t *bitchunks);
 /* For every stored entry (row y, column x) of a table, in storage order:

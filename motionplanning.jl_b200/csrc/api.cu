@@ -75,7 +75,7 @@ int phases_collect(int n) {
 }
 
 // implemented in the kernel translation units
-int compute_bbox(mpb200_samples *s);
+int compute_bbox(mpb200_samples *s, int64_t j0, int64_t j1);
 int grid_inball_build(mpb200_samples *s, double r, mpb200_table *t);
 int brute_inball_build(mpb200_samples *s, double r, mpb200_table *t);
 
@@ -200,11 +200,12 @@ int mpb200_samples_create(const double *V_aos, int64_t N, int d, mpb200_samples 
     if (N > 0) {
         cudaError_t e = cudaMemcpyAsync(s->V.p, V_aos, sizeof(double) * (size_t)(N * d), cudaMemcpyHostToDevice, st);
         if (e != cudaSuccess) { s->V.release(); delete s; return fail(MPB200_ECUDA, "H2D copy failed: %s", cudaGetErrorString(e)); }
-        rc = compute_bbox(s);
+        rc = compute_bbox(s, 0, N);
         if (rc) { mpb200_samples_destroy(s); return rc; }
         MPB_CUDA(cudaMemcpyAsync(s->h_bbox, s->minmax.p, sizeof(double) * 2 * d, cudaMemcpyDeviceToHost, st));
     }
     MPB_CUDA(cudaStreamSynchronize(st));
+    memcpy(s->h_qbbox, s->h_bbox, sizeof(s->h_bbox));
     *out = s;
     return MPB200_OK;
 }
@@ -222,6 +223,14 @@ int mpb200_samples_set_query_range(mpb200_samples *s, int64_t q0, int64_t q1) {
     MPB_CHECK_ARG(0 <= q0 && q0 <= q1 && q1 <= s->N, "query range must satisfy 0 <= q0 <= q1 <= N");
     s->q0 = q0;
     s->q1 = q1;
+    // bounding box of the shard's own samples: the grid only has to cover it (+ r)
+    memcpy(s->h_qbbox, s->h_bbox, sizeof(s->h_bbox));
+    if (ctx().ready && q1 > q0 && (q0 != 0 || q1 != s->N)) {
+        cudaStream_t st = ctx().stream;
+        if (int rc = compute_bbox(s, q0, q1)) return rc;
+        MPB_CUDA(cudaMemcpyAsync(s->h_qbbox, s->minmax.p, sizeof(double) * 2 * s->d, cudaMemcpyDeviceToHost, st));
+        MPB_CUDA(cudaStreamSynchronize(st));
+    }
     return MPB200_OK;
 }
 
@@ -419,11 +428,13 @@ int mpb200_points_free(const mpb200_samples *s_, const mpb200_obstacles *o, cons
     MPB_CHECK_ARG(s_ != nullptr, "samples handle is NULL");
     mpb200_samples *s = const_cast<mpb200_samples *>(s_);
     cudaStream_t st = ctx().stream;
-    const size_t words = (size_t)ceil_div(s->N, 64);
+    const int64_t n = s->q1 - s->q0;  // this process's shard of the samples (all of them by default)
+    const size_t words = (size_t)ceil_div(n, 64);
     if (int rc = s->point_bits.reserve(sizeof(uint64_t) * (words + 1))) return rc;
     phase_mark(0);
     MPB_CUDA(cudaMemsetAsync(s->point_bits.p, 0, sizeof(uint64_t) * (words + 1), st));
-    if (int rc = points_free_device(s->V.as<double>(), s->N, s->d, o, ss, s->point_bits.as<uint32_t>(), nullptr)) return rc;
+    if (int rc = points_free_device(s->V.as<double>() + s->q0 * s->d, n, s->d, o, ss, s->point_bits.as<uint32_t>(), nullptr))
+        return rc;
     phase_mark(1);
     if (bitchunks && words)
         MPB_CUDA(cudaMemcpyAsync(bitchunks, s->point_bits.p, sizeof(uint64_t) * words, cudaMemcpyDeviceToHost, st));

@@ -106,6 +106,7 @@ struct mpb200_samples {
     mpb::DevBuf sorted_pos;  // f64 d x N positions in cell order (AoS)
     mpb::DevBuf minmax;      // f64 2*d bounding box
     double h_bbox[32] = {};  // host copy of the bounding box (mins then maxs), read once at create
+    double h_qbbox[32] = {}; // bounding box of the query range's samples (== h_bbox for the full range)
     mpb::DevBuf scan_tmp;    // scan block sums
     mpb::DevBuf q_order;     // int32: cell-order positions owned by this shard (+ scratch)
     mpb::DevBuf point_bits;  // uint64 ceil(N/64): last mpb200_points_free result
@@ -113,7 +114,7 @@ struct mpb200_samples {
     // CUDA graph of the launch-bound front half of a grid build (K1 + count + scans), replayed
     // while the launch parameters (sizes, radius, buffer addresses) stay the same
     cudaGraphExec_t graph_exec = nullptr;
-    uint64_t graph_key[24] = {};
+    uint64_t graph_key[32] = {};
     int graph_launches = 0;  // kernels inside the graph (launch accounting)
 };
 

@@ -25,6 +25,10 @@ struct GridDev {
     double lo[3];
     double inv_h;
     int n[3];
+    // only samples inside [in_lo, in_hi] are inserted: the query shard's bounding box grown by r.  With a
+    // spatially coherent query range (samples stored in stripe / Morton order) each GPU then grids
+    // only its stripe + halo instead of the whole replicated sample set.
+    double in_lo[3], in_hi[3];
 };
 
 template <int D>
@@ -90,8 +94,13 @@ __global__ void __launch_bounds__(256) cell_histogram(const double *__restrict__
     int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= N) return;
     double p[D];
+    bool inside = true;
 #pragma unroll
-    for (int i = 0; i < D; ++i) p[i] = V[j * D + i];
+    for (int i = 0; i < D; ++i) {
+        p[i] = V[j * D + i];
+        inside = inside && (p[i] >= g.in_lo[i] && p[i] <= g.in_hi[i]);
+    }
+    if (!inside) { cell_id[j] = -1; return; }  // cannot be within r of any query of this shard
     int c[D];
     cell_of<D>(g, p, c);
     int l = cell_linear<D>(g, c);
@@ -106,6 +115,7 @@ __global__ void __launch_bounds__(256) cell_scatter(const double *__restrict__ V
     int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= N) return;
     int l = cell_id[j];
+    if (l < 0) return;
     int pos = cell_start[l] + atomicAdd(&cursor[l], 1);
     sorted_idx[pos] = (int)j;
 #pragma unroll
@@ -465,10 +475,11 @@ rball_fill_big(const double *__restrict__ V, const int *__restrict__ big_list, i
 }
 
 // shard support: cell-order positions whose sample index lies in [q0, q1)
-__global__ void __launch_bounds__(256) range_flags(const int *__restrict__ sorted_idx, int64_t N, int64_t q0, int64_t q1,
+__global__ void __launch_bounds__(256) range_flags(const int *__restrict__ sorted_idx, int64_t N,
+                                                   const int *__restrict__ n_valid, int64_t q0, int64_t q1,
                                                    int *__restrict__ flags) {
     int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < N) flags[k] = (sorted_idx[k] >= q0 && sorted_idx[k] < q1) ? 1 : 0;
+    if (k < N) flags[k] = (k < *n_valid && sorted_idx[k] >= q0 && sorted_idx[k] < q1) ? 1 : 0;  // n_valid = gridded samples
 }
 __global__ void __launch_bounds__(256) range_scatter(const int *__restrict__ flags, const int *__restrict__ offs,
                                                      int64_t N, int *__restrict__ q_order) {
@@ -513,7 +524,15 @@ static int build_table(mpb200_samples *s, double r, mpb200_table *t) {
     const double *V = s->V.as<double>();
 
     // bounding box (host copy made at samples_create) -> grid geometry
-    const double *bb = s->h_bbox;
+    // grid over the query shard's bounding box grown by r (clipped to the samples' box)
+    double bb[6];
+    const double grow = r * (1.0 + 1e-6);
+    for (int i = 0; i < D; ++i) {
+        const double pad = grow + 4.5e-16 * fmax(fabs(s->h_qbbox[i]), fabs(s->h_qbbox[D + i]));
+        bb[i] = fmax(s->h_bbox[i], s->h_qbbox[i] - pad);
+        bb[D + i] = fmin(s->h_bbox[D + i], s->h_qbbox[D + i] + pad);
+        if (!(bb[i] <= bb[D + i])) { bb[i] = s->h_bbox[i]; bb[D + i] = s->h_bbox[i]; }
+    }
     GridDev g;
     const int max_per_dim = (D == 2) ? 4096 : 256;
     double ext_max = 0;
@@ -532,6 +551,7 @@ static int build_table(mpb200_samples *s, double r, mpb200_table *t) {
     }
     for (int i = D; i < 3; ++i) { g.lo[i] = 0; g.n[i] = 1; }
     g.inv_h = 1.0 / h;
+    for (int i = 0; i < 3; ++i) { g.in_lo[i] = i < D ? bb[i] : 0; g.in_hi[i] = i < D ? bb[D + i] : 0; }
 
     // ---- reserve every buffer of the front half up front (nothing may allocate during graph capture)
     if (int rc = s->cell_start.reserve(sizeof(int) * (size_t)(ncells + 1))) return rc;
@@ -572,7 +592,7 @@ static int build_table(mpb200_samples *s, double r, mpb200_table *t) {
         if (nq != N) {  // shard: compact the cell-order positions this process owns
             int *qo = s->q_order.as<int>();
             int *flags = qo + N + 1, *offs = flags + N + 1;
-            range_flags<<<nbN, 256, 0, st>>>(sorted_idx, N, s->q0, s->q1, flags);
+            range_flags<<<nbN, 256, 0, st>>>(sorted_idx, N, cell_start + ncells, s->q0, s->q1, flags);
             MPB_LAUNCHED();
             if (int rc = exclusive_scan<int, int>(flags, N, offs, 0, s->scan_tmp, nullptr)) return rc;
             range_scatter<<<nbN, 256, 0, st>>>(flags, offs, N, qo);
@@ -590,7 +610,7 @@ static int build_table(mpb200_samples *s, double r, mpb200_table *t) {
     static const bool use_graph = getenv("MPB200_NO_GRAPH") == nullptr;
     phase_mark(0);
     if (use_graph && nq > 0 && ncells > 0) {
-        uint64_t key[24] = {};
+        uint64_t key[32] = {};
         int kk = 0;
         auto put = [&](const void *p, size_t n) { uint64_t v = 0; memcpy(&v, p, n); key[kk++] = v; };
         const void *ptrs[] = {V, hist, cell_start, sorted_idx, sorted_pos, hit_lists, counts, t->colptr.p, s->scan_tmp.p,
@@ -598,6 +618,7 @@ static int build_table(mpb200_samples *s, double r, mpb200_table *t) {
         for (const void *p : ptrs) put(&p, sizeof(p));
         put(&N, 8); put(&nq, 8); put(&s->q0, 8); put(&r, 8); put(&g.inv_h, 8); put(&g.lo[0], 8); put(&g.lo[1], 8);
         put(&g.lo[2], 8); put(&g.n[0], 4); put(&g.n[1], 4); put(&g.n[2], 4);
+        put(&g.in_hi[0], 8); put(&g.in_hi[1], 8); put(&g.in_hi[2], 8);
         key[kk++] = (uint64_t)D;
         if (!(s->graph_exec && memcmp(key, s->graph_key, sizeof(key)) == 0)) {
             if (s->graph_exec) { cudaGraphExecDestroy(s->graph_exec); s->graph_exec = nullptr; }
@@ -673,13 +694,14 @@ static int build_table(mpb200_samples *s, double r, mpb200_table *t) {
     return 0;
 }
 
-int compute_bbox(mpb200_samples *s) {
+// bounding box of samples [j0, j1) into s->minmax (device); the caller copies it to the host
+int compute_bbox(mpb200_samples *s, int64_t j0, int64_t j1) {
     Context &c = ctx();
     const int nb = 2 * c.sm_count;
     if (int rc = s->minmax.reserve(sizeof(double) * (size_t)(2 * s->d) * (size_t)(nb + 1))) return rc;
     double *out = s->minmax.as<double>();
     double *part = out + 2 * s->d;
-    bbox_partial<<<nb, 256, 0, c.stream>>>(s->V.as<double>(), s->N, s->d, part);
+    bbox_partial<<<nb, 256, 0, c.stream>>>(s->V.as<double>() + j0 * s->d, j1 - j0, s->d, part);
     MPB_LAUNCHED();
     bbox_final<<<1, 32, 0, c.stream>>>(part, nb, s->d, out);
     MPB_LAUNCHED();

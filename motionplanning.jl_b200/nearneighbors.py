@@ -144,8 +144,9 @@ class SampleSet:
 
     # ---- batched validity over this sample set --------------------------------------------
     def points_free(self, CC, SS, fetch=True):
-        """F[i] = is_free_state(V[i], CC, SS) for all i (fmt.jl:31-36) as BitVector chunks."""
-        n = len(self)
+        """F[i] = is_free_state(V[i], CC, SS) for the owned samples [q0, q1) -- all of them unless a
+        query range is set -- (fmt.jl:31-36) as BitVector chunks."""
+        n = self.q1 - self.q0
         d = SS.desc()
         bits = self.pool.array("point_bits", (n + 63) // 64, np.uint64) if fetch else None
         _lib.check(_lib.lib().mpb200_points_free(self.handle(), CC.handle(), ctypes.byref(d), _lib.ptr(bits)))

@@ -326,3 +326,33 @@ def test_k3_single_sweep_slab_overflow_falls_back(gpu, orc):
     deg = np.diff(D.colptr)
     assert deg[:2048].max() * 1.5 + 64 < deg.max()        # the probe really underestimates
     NN.close()
+
+
+@pytest.mark.parametrize("d", [2, 3])
+def test_k2_stripe_sorted_shards_use_restricted_grid(gpu, orc, d):
+    """samples stored in stripe order: every shard's query range is a spatial stripe, its grid only
+    covers the stripe + r, and out-of-stripe samples are never inserted -- results unchanged"""
+    mp = gpu
+    N = 40_000
+    V = fx.uniform_samples(N, d, 31 + d)
+    V = V[np.argsort(V[:, 0], kind="stable")]
+    r = fx.fmt_radius(N, d) * 1.3
+    full = orc.KDTree(V).rball(r)
+    got_rows, got_vals = [], []
+    CC = mp.PointRobotNDBoxes([mp.BoxBounds(b) for b in (fx.BOXES2D if d == 2 else fx.BOXES3D)])
+    SSp, SSo = _space_pair(mp, orc, np.zeros(d), np.ones(d))
+    B = orc.Boxes(fx.BOXES2D if d == 2 else fx.BOXES3D)
+    for q0, q1 in ((0, 9_000), (9_000, 9_001), (9_001, 31_000), (31_000, N)):
+        NN = mp.MetricNN(V)
+        NN.set_query_range(q0, q1)
+        cache, bits, checks = NN.precompute_checked(r, CC, SSp)
+        ref = orc.KDTree(V).rball(r, q0, q1)
+        assert np.array_equal(cache.D.colptr, ref[0]) and np.array_equal(cache.D.rowval, ref[1])
+        assert cache.D.nzval.tobytes() == ref[2].tobytes()
+        exp, cnt = orc.edges_free_csc(B, SSo, V, ref[0], ref[1], q0)
+        assert np.array_equal(unpack_bits(bits, cache.D.nnz), exp.astype(bool)) and checks == cnt
+        F = unpack_bits(NN.points_free(CC, SSp), q1 - q0)
+        assert np.array_equal(F, orc.states_free(B, SSo, V[q0:q1]))
+        got_rows.append(cache.D.rowval.copy())
+        NN.close()
+    assert np.array_equal(np.concatenate(got_rows), full[1])
