@@ -213,15 +213,22 @@ rball_count(const double *__restrict__ sorted_pos, const int *__restrict__ sorte
 #pragma unroll
         for (int run = 0; run < kRuns; ++run) {
             const int beg = begs[run], end = begs[run] + lens[run];
-            for (int k = beg; k < end; ++k, ++j) {
+            // branch-free body (predicated store), unrolled: the loads of several candidates are in flight
+#pragma unroll 4
+            for (int k = beg; k < end; ++k) {
                 double b[D];
+                if (D == 2) {
+                    const double2 v = reinterpret_cast<const double2 *>(sorted_pos)[k];  // one 16-byte load
+                    b[0] = v.x; b[D - 1] = v.y;
+                } else {
 #pragma unroll
-                for (int i = 0; i < D; ++i) b[i] = sorted_pos[(size_t)k * D + i];
-                if ((k != pos) && (sqdist<D>(p, b) <= r2)) {
-                    if (cnt < kListCap) s_hits[cnt][threadIdx.x] = (unsigned char)j;
-                    ++cnt;
+                    for (int i = 0; i < D; ++i) b[i] = sorted_pos[(size_t)k * D + i];
                 }
+                const bool hit = (k != pos) & (sqdist<D>(p, b) <= r2);
+                if (hit & (cnt < kListCap)) s_hits[cnt][threadIdx.x] = (unsigned char)(j + (k - beg));
+                cnt += hit ? 1 : 0;
             }
+            j += end - beg;
         }
         const int w = (int)(sorted_idx[pos] - q0);
         counts[w] = cnt;
@@ -395,8 +402,13 @@ rball_fill(const double *__restrict__ sorted_pos, const int *__restrict__ sorted
                 const int kp = (src >> 5) ? kp_b : kp_a;
                 if (e < kc[u]) {
                     double b[D];
+                    if (D == 2) {
+                        const double2 v = reinterpret_cast<const double2 *>(sorted_pos)[kp];  // one 16-byte load
+                        b[0] = v.x; b[D - 1] = v.y;
+                    } else {
 #pragma unroll
-                    for (int i = 0; i < D; ++i) b[i] = sorted_pos[(size_t)kp * D + i];
+                        for (int i = 0; i < D; ++i) b[i] = sorted_pos[(size_t)kp * D + i];
+                    }
                     emit_entry<D>(b, ky >> 6, pc[u], basec[u] + e, rowval, nzval);
                 }
             }
