@@ -252,7 +252,7 @@ int mpb200_inball_build(mpb200_samples *s, double r, mpb200_table **table, int64
         if (!rc) {
             int64_t one = 1;
             cudaMemcpy(t->colptr.p, &one, sizeof(one), cudaMemcpyHostToDevice);
-            t->ncols = 0; t->col0 = 0; t->nnz = 0; t->r = r; t->euclid = true;
+            t->ncols = 0; t->col0 = 0; t->nnz = 0; t->r = r; t->euclid = true; t->has_order = false;
         }
     } else if (s->d <= 3 && s->d >= 2) {
         rc = grid_inball_build(s, r, t);
@@ -316,7 +316,7 @@ int mpb200_table_destroy(mpb200_table *t) {
     if (!t) return MPB200_OK;
     if (ctx().ready) cudaStreamSynchronize(ctx().stream);
     t->colptr.release(); t->rowval.release(); t->nzval.release(); t->counts.release(); t->masks.release();
-    t->edge_bits.release(); t->scratch.release(); t->col_list.release();
+    t->edge_bits.release(); t->scratch.release(); t->col_list.release(); t->col_order.release();
     delete t;
     return MPB200_OK;
 }

@@ -263,6 +263,7 @@ static int brute_build(mpb200_samples *s, double r, mpb200_table *t) {
     t->nnz = nnz;
     t->r = r;
     t->euclid = true;
+    t->has_order = false;
     return 0;
 }
 

@@ -165,15 +165,19 @@ __global__ void __launch_bounds__(kThreads)
 classify_columns(const double *__restrict__ V, const int64_t *__restrict__ colptr, int64_t ncols, int64_t col0,
                  double r, SpaceDev S, const double *__restrict__ g_table, int table_words, int M, bool use_smem,
                  unsigned long long *__restrict__ bits64, unsigned long long *__restrict__ checks,
-                 int *__restrict__ list, unsigned long long *__restrict__ n_list) {
+                 int *__restrict__ list, unsigned long long *__restrict__ n_list, const int *__restrict__ order) {
     extern __shared__ double s_table[];
     const double *T = stage_table(g_table, table_words, use_smem, s_table);
     const int lane = threadIdx.x & 31;
     unsigned long long my_checks = 0;
     const int64_t n_pad = (ncols + 31) & ~int64_t(31);
-    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_pad; c += (int64_t)gridDim.x * blockDim.x) {
+    // `order` (optional) lists the columns in grid-cell order: the lanes of a warp then look at neighbouring
+    // points, take the same branches below, and the flagged list comes out spatially coherent too
+    for (int64_t ti = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; ti < n_pad; ti += (int64_t)gridDim.x * blockDim.x) {
         bool flagged = false;
-        if (c < ncols) {
+        int64_t c = ti;
+        if (ti < ncols) {
+            if (order) c = order[ti];
             const int64_t beg = colptr[c] - 1, end = colptr[c + 1] - 1;
             if (beg < end) {
                 double lo[DW], hi[DW];
@@ -414,7 +418,8 @@ int edges_free_device(const double *dV, int d, const mpb200_table *t, const mpb2
         if (int rc = prep_kernel(classify_columns<DW_, K_>, L.smem)) return rc;                                \
         classify_columns<DW_, K_><<<L.grid, kThreads, L.smem, st>>>(dV, t->colptr.as<int64_t>(), t->ncols, t->col0, \
                                                                     t->r, S, L.table, L.words, L.M, L.use_smem, \
-                                                                    bits64, d_checks, list, n_list);           \
+                                                                    bits64, d_checks, list, n_list,            \
+                                                                    t->has_order ? t->col_order.as<int>() : nullptr); \
     } while (0)
     if (o->kind == 0) {
         if (dw != 2) return fail(MPB200_EARG, "2-D obstacles need a 2-D workspace");

@@ -92,6 +92,8 @@ struct mpb200_table {
     mpb::DevBuf edge_bits; // uint64 ceil(nnz/64): last mpb200_edges_free result
     mpb::DevBuf scratch;   // big-column spill etc.
     mpb::DevBuf col_list;  // int32 ncols + counter: columns that need per-edge checks
+    mpb::DevBuf col_order; // int32 ncols: the shard's columns in grid-cell order (spatially coherent warps)
+    bool has_order = false;
 };
 
 struct mpb200_samples {

@@ -195,7 +195,7 @@ template <int D>
 __global__ void __launch_bounds__(kQThreads)
 rball_count(const double *__restrict__ sorted_pos, const int *__restrict__ sorted_idx,
             const int *__restrict__ q_order, int64_t nq, int64_t q0, GridDev g, double r2,
-            const int *__restrict__ cell_start, int list_cap, int *__restrict__ counts,
+            const int *__restrict__ cell_start, int list_cap, int *__restrict__ counts, int *__restrict__ col_order,
             uint32_t *__restrict__ hit_lists, int *__restrict__ big_list, unsigned long long *__restrict__ n_big) {
     constexpr int kRuns = (D == 2) ? 3 : 9;
     __shared__ __align__(16) unsigned char s_hits[kListCap][kQThreads];
@@ -232,6 +232,7 @@ rball_count(const double *__restrict__ sorted_pos, const int *__restrict__ sorte
         }
         const int w = (int)(sorted_idx[pos] - q0);
         counts[w] = cnt;
+        col_order[t] = w;  // columns in cell order, for the collision passes (classify_columns)
         if (cnt > 0 && (cnt > list_cap || total > kMaxCand)) {
             unsigned long long slot = atomicAdd(n_big, 1ULL);
             big_list[slot] = w;
@@ -281,22 +282,23 @@ __device__ __forceinline__ void bitonic64(unsigned &k0, unsigned &k1, int lane) 
     }
 }
 
-// Fill.  Thread t owns query t of the cell order and keeps that query's point, column base, count
-// and candidate spans in registers; the warp then walks over its 32 columns, U at a time.  For a
-// column, lane e reads the e-th byte of the column's hit list (written by rball_count), maps the
-// candidate number to a cell-order position, loads the sample index, and the column is sorted by
-// index with a register bitonic network over the lanes (key = index << 6 | source slot).  The neighbour position comes
-// from the cell-ordered copy (cache-friendly), the exact distance is recomputed, and the column
-// is written as one contiguous Int64/Float64 burst.  No shared memory, no re-evaluation of
-// distances.  Columns with more than kListCap entries or more than kMaxCand candidates are left
-// to rball_fill_big.  Requires N < 2^26 (key packing).
-template <int D>
-__device__ __forceinline__ void emit_entry(const double *b, unsigned idx, const double *pc, long long at,
-                                           int64_t *__restrict__ rowval, double *__restrict__ nzval) {
-    rowval[at] = (int64_t)idx + 1;
-    nzval[at] = sqrt(sqdist<D>(pc, b));
-}
-
+// Fill.  Thread t owns query t of the cell order and parks that query's record (point, column
+// base, candidate spans) in shared memory; the warp then walks over its 32 columns, U at a time,
+// reading the record of the current column with a few broadcast 16-byte loads (no shuffles, and
+// the record does not occupy registers).  For a column, lane e reads the e-th byte of the
+// column's hit list (written by rball_count), maps the candidate number to a cell-order
+// position, and loads the sample index AND the neighbour position together (independent loads
+// from the cache-friendly cell-ordered copy); the exact distance is recomputed there and parked
+// in shared memory by source slot.  The column is then sorted by index with a register bitonic
+// network over the lanes (key = index << 6 | source slot), each lane picks up the distance of
+// its sorted entry from the slot named in the key, and the column is written as one contiguous
+// Int64/Float64 burst.  Columns with more than kListCap entries or more than kMaxCand
+// candidates are left to rball_fill_big.  Requires N < 2^26 (key packing).
+//
+// Measured alternative (r1m): ranking each index against the column's indices read back from
+// shared memory four at a time (no shuffles, rows stored at base + rank) halves the LSU
+// wavefronts of the sort but costs ~2.3 ALU instructions per comparison: 269M warp
+// instructions instead of 195M, issue-bound at 79%, 321 us against 295 us for this form.
 // U = columns sorted concurrently by one warp (independent dependency chains vs register budget)
 template <int D, int U>
 __global__ void __launch_bounds__(kQThreads)
@@ -305,32 +307,41 @@ rball_fill(const double *__restrict__ sorted_pos, const int *__restrict__ sorted
            GridDev g, const int *__restrict__ cell_start, const int64_t *__restrict__ colptr,
            int64_t *__restrict__ rowval, double *__restrict__ nzval) {
     constexpr int kRuns = (D == 2) ? 3 : 9;
-    const int lane = threadIdx.x & 31;
+    constexpr int kWBase = 2 * D, kWBeg = 2 * D + 2, kWLen = kWBeg + kRuns;  // word offsets in a record
+    constexpr int NV = (kWLen + kRuns + 3) / 4;                                // 16-byte vectors per record
+    __shared__ int4 s_rec[NV][kQThreads];
+    __shared__ double s_dist[kQThreads / 32][U][kListCap];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned char *tile_list = hit_lists + (t >> 5) * (int64_t)(kListCap * 32);  // same tiling as rball_count
     int k_mine = 0;
-    long long base = 0;
-    int begs[kRuns], lens[kRuns];
-    double p[D];
+    {
+        int rec[NV * 4];
 #pragma unroll
-    for (int i = 0; i < D; ++i) p[i] = 0.0;
+        for (int i = 0; i < NV * 4; ++i) rec[i] = 0;
+        if (t < nq) {
+            const int pos = q_order ? q_order[t] : (int)t;
+            double p[D];
 #pragma unroll
-    for (int r = 0; r < kRuns; ++r) { begs[r] = 0; lens[r] = 0; }
-    if (t < nq) {
-        const int pos = q_order ? q_order[t] : (int)t;
+            for (int i = 0; i < D; ++i) {
+                p[i] = sorted_pos[(size_t)pos * D + i];
+                rec[2 * i] = __double2loint(p[i]);
+                rec[2 * i + 1] = __double2hiint(p[i]);
+            }
+            const int64_t w = sorted_idx[pos] - q0;
+            const long long base = colptr[w] - 1;
+            rec[kWBase] = (int)(unsigned)(base & 0xffffffffLL);
+            rec[kWBase + 1] = (int)(base >> 32);
+            k_mine = (int)(colptr[w + 1] - colptr[w]);
+            const int total = query_spans<D>(g, p, cell_start, rec + kWBeg, rec + kWLen);
+            if (k_mine > kListCap || total > kMaxCand) k_mine = 0;  // handled by rball_fill_big
+        }
 #pragma unroll
-        for (int i = 0; i < D; ++i) p[i] = sorted_pos[(size_t)pos * D + i];
-        const int64_t w = sorted_idx[pos] - q0;
-        base = colptr[w] - 1;
-        k_mine = (int)(colptr[w + 1] - colptr[w]);
-        const int total = query_spans<D>(g, p, cell_start, begs, lens);
-        if (k_mine > kListCap || total > kMaxCand) k_mine = 0;  // handled by rball_fill_big
+        for (int v = 0; v < NV; ++v) s_rec[v][threadIdx.x] = make_int4(rec[4 * v], rec[4 * v + 1], rec[4 * v + 2], rec[4 * v + 3]);
     }
+    __syncwarp();
     for (int cl0 = 0; cl0 < 32; cl0 += U) {
         int kc[U];
-        long long basec[U];
-        double pc[U][D];
-        int kpos[U][2];
         unsigned key[U][2];
         int kmax = 0;
 #pragma unroll
@@ -342,35 +353,44 @@ rball_fill(const double *__restrict__ sorted_pos, const int *__restrict__ sorted
         const int rounds = (kmax > 32) ? 2 : 1;  // warp-uniform
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            basec[u] = __shfl_sync(0xffffffffu, base, cl0 + u);
+            int rec[NV * 4];
 #pragma unroll
-            for (int i = 0; i < D; ++i) pc[u][i] = __shfl_sync(0xffffffffu, p[i], cl0 + u);
-            int cb_[kRuns], cn_[kRuns];
-#pragma unroll
-            for (int r = 0; r < kRuns; ++r) {
-                cb_[r] = __shfl_sync(0xffffffffu, begs[r], cl0 + u);
-                cn_[r] = __shfl_sync(0xffffffffu, lens[r], cl0 + u);
+            for (int v = 0; v < NV; ++v) {   // broadcast reads of column (cl0 + u)'s record
+                const int4 q = s_rec[v][wid * 32 + cl0 + u];
+                rec[4 * v] = q.x; rec[4 * v + 1] = q.y; rec[4 * v + 2] = q.z; rec[4 * v + 3] = q.w;
             }
-            // element e = lane + 32 h: candidate number -> cell-order position -> sort key
+            double pc[D];
+#pragma unroll
+            for (int i = 0; i < D; ++i) pc[i] = __hiloint2double(rec[2 * i + 1], rec[2 * i]);
+            // element e = lane + 32 h: candidate number -> cell-order position -> sort key, distance
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 key[u][h] = 0xffffffffu;
-                kpos[u][h] = 0;
                 const int e = lane + 32 * h;
                 if (h < rounds && e < kc[u]) {
                     int j = tile_list[e * 32 + cl0 + u];  // candidate number of the e-th hit of this column
                     int kp = 0;
 #pragma unroll
                     for (int r = 0; r < kRuns; ++r) {  // run containing candidate j
-                        const bool here = (j >= 0) && (j < cn_[r]);
-                        kp = here ? cb_[r] + j : kp;
-                        j = here ? -1 : j - cn_[r];
+                        const bool here = (j >= 0) && (j < rec[kWLen + r]);
+                        kp = here ? rec[kWBeg + r] + j : kp;
+                        j = here ? -1 : j - rec[kWLen + r];
                     }
-                    kpos[u][h] = kp;
-                    key[u][h] = ((unsigned)sorted_idx[kp] << 6) | (unsigned)e;
+                    const unsigned idx = (unsigned)sorted_idx[kp];
+                    double b[D];
+                    if (D == 2) {
+                        const double2 v = reinterpret_cast<const double2 *>(sorted_pos)[kp];  // one 16-byte load
+                        b[0] = v.x; b[D - 1] = v.y;
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < D; ++i) b[i] = sorted_pos[(size_t)kp * D + i];
+                    }
+                    key[u][h] = (idx << 6) | (unsigned)e;
+                    s_dist[wid][u][e] = sqrt(sqdist<D>(pc, b));
                 }
             }
         }
+        __syncwarp();
         if (rounds == 1) {
 #pragma unroll
             for (int size = 2; size <= 32; size <<= 1) {
@@ -391,28 +411,19 @@ rball_fill(const double *__restrict__ sorted_pos, const int *__restrict__ sorted
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
+            const int2 bw = reinterpret_cast<const int2 *>(&s_rec[kWBase / 4][wid * 32 + cl0 + u])[(kWBase % 4) / 2];
+            const long long basec = ((long long)bw.y << 32) | (unsigned)bw.x;
             const int ru = (kc[u] > 32) ? 2 : (kc[u] > 0 ? 1 : 0);  // warp-uniform
             for (int h = 0; h < ru; ++h) {
                 const int e = lane + 32 * h;
                 const unsigned ky = h ? key[u][1] : key[u][0];
-                const int src = (int)(ky & 63u);
-                // cell-order position of the source slot: held by lane (src & 31), register (src >> 5)
-                const int kp_a = __shfl_sync(0xffffffffu, kpos[u][0], src & 31);
-                const int kp_b = (ru > 1) ? __shfl_sync(0xffffffffu, kpos[u][1], src & 31) : 0;
-                const int kp = (src >> 5) ? kp_b : kp_a;
                 if (e < kc[u]) {
-                    double b[D];
-                    if (D == 2) {
-                        const double2 v = reinterpret_cast<const double2 *>(sorted_pos)[kp];  // one 16-byte load
-                        b[0] = v.x; b[D - 1] = v.y;
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < D; ++i) b[i] = sorted_pos[(size_t)kp * D + i];
-                    }
-                    emit_entry<D>(b, ky >> 6, pc[u], basec[u] + e, rowval, nzval);
+                    rowval[basec + e] = (int64_t)(ky >> 6) + 1;
+                    nzval[basec + e] = s_dist[wid][u][ky & 63u];  // distance parked by the entry's source slot
                 }
             }
         }
+        __syncwarp();  // s_dist is reused by the next group of columns
     }
 }
 
@@ -576,6 +587,8 @@ static int build_table(mpb200_samples *s, double r, mpb200_table *t) {
     if (int rc = t->counts.reserve(sizeof(int) * (size_t)(2 * nq + 2))) return rc;
     if (int rc = t->colptr.reserve(sizeof(int64_t) * (size_t)(nq + 1))) return rc;
     if (int rc = t->masks.reserve((size_t)kListCap * 32 * (size_t)(ceil_div(nq, 32) + 1))) return rc;
+    if (int rc = t->col_order.reserve(sizeof(int) * (size_t)(nq + 1))) return rc;
+    t->has_order = false;
     int *hist = s->cell_fill.as<int>();
     int *cell_start = s->cell_start.as<int>();
     int *sorted_idx = s->sorted_idx.as<int>();
@@ -613,7 +626,7 @@ static int build_table(mpb200_samples *s, double r, mpb200_table *t) {
         MPB_CUDA(cudaMemsetAsync(c.d_scalar, 0, sizeof(int64_t) * 2, st));
         if (nq > 0) {
             rball_count<D><<<nbQ, kQThreads, 0, st>>>(sorted_pos, sorted_idx, q_order, nq, s->q0, g, r2, cell_start,
-                                                     list_cap, counts, hit_lists, big_list, d_nbig);
+                                                     list_cap, counts, t->col_order.as<int>(), hit_lists, big_list, d_nbig);
             MPB_LAUNCHED();
         }
         return exclusive_scan<int, int64_t>(counts, nq, t->colptr.as<int64_t>(), (int64_t)1, s->scan_tmp, c.d_scalar);
@@ -626,7 +639,7 @@ static int build_table(mpb200_samples *s, double r, mpb200_table *t) {
         int kk = 0;
         auto put = [&](const void *p, size_t n) { uint64_t v = 0; memcpy(&v, p, n); key[kk++] = v; };
         const void *ptrs[] = {V, hist, cell_start, sorted_idx, sorted_pos, hit_lists, counts, t->colptr.p, s->scan_tmp.p,
-                              s->q_order.p, c.d_scalar, (const void *)st};
+                              s->q_order.p, c.d_scalar, (const void *)st, t->col_order.p};
         for (const void *p : ptrs) put(&p, sizeof(p));
         put(&N, 8); put(&nq, 8); put(&s->q0, 8); put(&r, 8); put(&g.inv_h, 8); put(&g.lo[0], 8); put(&g.lo[1], 8);
         put(&g.lo[2], 8); put(&g.n[0], 4); put(&g.n[1], 4); put(&g.n[2], 4);
@@ -703,6 +716,7 @@ static int build_table(mpb200_samples *s, double r, mpb200_table *t) {
     t->nnz = nnz;
     t->r = r;
     t->euclid = true;
+    t->has_order = nq > 0;
     return 0;
 }
 

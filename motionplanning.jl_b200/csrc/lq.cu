@@ -446,6 +446,7 @@ static int lq_build(mpb200_samples *s, const mpb200_lq *lq, double r, mpb200_tab
     tB->nnz = nnzB;
     tF->r = tB->r = r;
     tF->euclid = tB->euclid = false;
+    tF->has_order = tB->has_order = false;
     return 0;
 }
 
