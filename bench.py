@@ -222,7 +222,11 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = mpb200.init(local)
-    stream = torch.cuda.current_stream()
+    # ONE explicit stream for everything in the timed region: the L2 flush, the timing events, the library's
+    # kernels and (N > 1) the NCCL exchange.  (torch's default stream has handle 0, which mpb200_set_stream
+    # reads as "use the library's own non-blocking stream": the flush would then overlap the step.)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     _lib.check(lib.mpb200_set_stream(_lib.c_vp(stream.cuda_stream)))
 
     n_total = SAMPLES_PER_GPU * world
@@ -269,19 +273,19 @@ def main():
         flush.zero_()  # L2 flush between iterations (outside the event pair)
         if it >= args.warmup:
             ev[it - args.warmup][0].record(stream)
-        nnz = NN.build_table(r)                       # K1 + K2
-        if it >= args.warmup:
-            phases[:5] += [lib.mpb200_last_ms(k) for k in range(5)]
+        # the three calls of a planning step, issued back to back: only build_table waits (for nnz, once,
+        # between count and fill); the validity calls enqueue their kernels and return
         NN.points_free(CC, SS, fetch=False)           # K6
-        if it >= args.warmup:
-            point_ms.append(lib.mpb200_last_ms(1))
-        NN.edges_free(NN.table, CC, SS, fetch=False)  # K7
-        if it >= args.warmup:
-            edge_ms.append(lib.mpb200_last_ms(1))
+        nnz = NN.build_table(r)                       # K1 + K2
+        NN.edges_free(NN.table, CC, SS, fetch=False, count=False)  # K7
         if exchange is not None:
             exchange.run(NN.table)          # NCCL all-gather of shard colptrs + validity words
         if it >= args.warmup:
             ev[it - args.warmup][1].record(stream)
+            # per-kernel times of THIS step (events recorded inside the calls, read after the step's end event)
+            phases[:5] += [lib.mpb200_last_ms_of(_lib.OP_TABLE, k) for k in range(5)]
+            point_ms.append(lib.mpb200_last_ms_of(_lib.OP_POINTS, 1))
+            edge_ms.append(lib.mpb200_last_ms_of(_lib.OP_EDGES, 1))
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()

@@ -59,8 +59,18 @@ int mpb200_host_free(void *p);
 /* Number of kernels this library has launched since mpb200_init (bench "gpu_launches"). */
 int64_t mpb200_launch_count(void);
 /* Device time of the last entry point, milliseconds, measured with CUDA events on the
- * launching stream; phase 0 = whole call, 1.. = entry-point specific. */
+ * launching stream; phase 0 = whole call, 1.. = entry-point specific.
+ * The events are recorded inside the call and read back lazily here (this waits for the
+ * recorded work), so entry points that return nothing from the device never block.
+ * mpb200_last_ms_of keeps one record per kind of operation, so the three calls of a
+ * planning step (table build, point validity, edge validity) can be issued back to back
+ * and timed afterwards. */
+#define MPB200_OP_TABLE 0  /* mpb200_inball_build / mpb200_lq_inball_build */
+#define MPB200_OP_POINTS 1 /* mpb200_points_free */
+#define MPB200_OP_EDGES 2  /* mpb200_edges_free / mpb200_lq_edges_free */
+#define MPB200_OP_OTHER 3  /* mpb200_mc_collision_probability */
 double mpb200_last_ms(int phase);
+double mpb200_last_ms_of(int op, int phase);
 
 /* ---- sample sets: replaces MetricNN/QuasiMetricNN.V (nearneighbors.jl:62-92) ---- */
 int mpb200_samples_create(const double *V_aos, int64_t N, int d, mpb200_samples **out);
@@ -128,14 +138,17 @@ typedef struct {
 /* ---- batched validity ---------------------------------------------------------- */
 /* F[i] = is_free_state(V[i], CC, SS) for the samples of the query range [q0, q1) -- all N by
  * default (fmt.jl:31-36, sampling.jl:25; statespaces.jl:151-152; robots2D.jl:12;
- * boxesND.jl:42-43).  bits: ceil((q1-q0)/64) words, bit k = sample q0 + k. */
+ * boxesND.jl:42-43).  bits: ceil((q1-q0)/64) words, bit k = sample q0 + k.
+ * bitchunks may be NULL: the call then only enqueues the work (no wait); the bits stay on the
+ * device, ordered on the launching stream before every later call. */
 int mpb200_points_free(const mpb200_samples *s, const mpb200_obstacles *o, const mpb200_space_desc *ss,
                        uint64_t *bitchunks);
 /* For every stored entry (row y, column x) of a table, in storage order:
  * is_free_motion(V[y], V[x], CC, SS) with straight-line waypoints (fmt.jl:75;
  * statespaces.jl:153-158; geometric.jl:20; robots2D.jl:13-14; boxesND.jl:52-56).
  * bits: ceil(nnz/64) words.  *checks receives the number of segment checks that
- * CC.count would have been incremented by. */
+ * CC.count would have been incremented by.  With bitchunks == NULL and checks == NULL the call
+ * only enqueues the work (no wait); read the bits later with mpb200_table_fetch_edge_bits. */
 int mpb200_edges_free(const mpb200_samples *s, const mpb200_table *t, const mpb200_obstacles *o,
                       const mpb200_space_desc *ss, uint64_t *bitchunks, int64_t *checks);
 /* Convenience for config "batched r-ball neighbours + edge validity precompute": build the

@@ -48,6 +48,8 @@ class McResult(ctypes.Structure):
 
 
 # every symbol include/mpb200.h declares: name -> (restype, argtypes)
+OP_TABLE, OP_POINTS, OP_EDGES, OP_OTHER = 0, 1, 2, 3  # mpb200_last_ms_of operation kinds
+
 SIGNATURES = {
     "mpb200_init": (ctypes.c_int, [ctypes.c_int]),
     "mpb200_shutdown": (None, []),
@@ -59,6 +61,7 @@ SIGNATURES = {
     "mpb200_host_free": (ctypes.c_int, [c_vp]),
     "mpb200_launch_count": (c_i64, []),
     "mpb200_last_ms": (c_dbl, [ctypes.c_int]),
+    "mpb200_last_ms_of": (c_dbl, [ctypes.c_int, ctypes.c_int]),
     "mpb200_samples_create": (ctypes.c_int, [c_vp, c_i64, ctypes.c_int, P(c_vp)]),
     "mpb200_samples_destroy": (ctypes.c_int, [c_vp]),
     "mpb200_samples_set_query_range": (ctypes.c_int, [c_vp, c_i64, c_i64]),

@@ -3,6 +3,8 @@
 #include "common.cuh"
 #include "predicates.cuh"
 #include <climits>
+#include <cstdio>
+#include <cstring>
 #include <limits>
 #include <new>
 #include <vector>
@@ -57,21 +59,63 @@ void DevBuf::release() {
     cap = 0;
 }
 
+namespace {
+struct TraceRec { cudaEvent_t ev; const char *file; int line; };
+std::vector<TraceRec> g_trace;
+size_t g_trace_n = 0;
+const bool g_trace_on = getenv("MPB200_TRACE") != nullptr;
+}  // namespace
+void trace_mark(const char *file, int line) {
+    if (!g_trace_on) return;
+    if (g_trace_n == g_trace.size()) {
+        TraceRec r{nullptr, file, line};
+        cudaEventCreate(&r.ev);
+        g_trace.push_back(r);
+    }
+    g_trace[g_trace_n].file = file;
+    g_trace[g_trace_n].line = line;
+    cudaEventRecord(g_trace[g_trace_n].ev, ctx().stream);
+    ++g_trace_n;
+}
+void trace_dump() {
+    if (!g_trace_on || g_trace_n == 0) return;
+    cudaStreamSynchronize(ctx().stream);
+    for (size_t i = 0; i < g_trace_n; ++i) {
+        float ms = 0;
+        if (i) cudaEventElapsedTime(&ms, g_trace[i - 1].ev, g_trace[i].ev);
+        const char *f = strrchr(g_trace[i].file, '/');
+        fprintf(stderr, "[trace] %-18s:%-4d +%8.1f us\n", f ? f + 1 : g_trace[i].file, g_trace[i].line, ms * 1e3);
+    }
+    g_trace_n = 0;
+}
+
 int phase_mark(int i) {
     Context &c = ctx();
     if (i < 0 || i > kMaxPhases) return 0;
-    cudaEventRecord(c.ev[i], c.stream);
+    trace_mark("phase", i);
+    cudaEventRecord(c.ev[c.bank][i], c.stream);
     return 0;
+}
+void phase_bank(int op) {
+    if (op >= 0 && op < kBanks) ctx().bank = op;
 }
 int phases_collect(int n) {
     Context &c = ctx();
-    for (int k = 0; k < kMaxPhases; ++k) c.last_ms[k] = 0;
-    float ms = 0;
-    if (cudaEventElapsedTime(&ms, c.ev[0], c.ev[n]) == cudaSuccess) c.last_ms[0] = ms;
-    for (int k = 0; k < n && k + 1 < kMaxPhases; ++k)
-        if (cudaEventElapsedTime(&ms, c.ev[k], c.ev[k + 1]) == cudaSuccess) c.last_ms[k + 1] = ms;
-    cudaGetLastError();
+    c.pending_marks[c.bank] = n;  // resolved lazily by phases_resolve(): the API call itself does not wait for the GPU
     return 0;
+}
+static void phases_resolve(int b) {
+    Context &c = ctx();
+    const int n = c.pending_marks[b];
+    if (n <= 0) return;
+    c.pending_marks[b] = 0;
+    cudaEventSynchronize(c.ev[b][n]);
+    for (int k = 0; k < kMaxPhases; ++k) c.last_ms[b][k] = 0;
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, c.ev[b][0], c.ev[b][n]) == cudaSuccess) c.last_ms[b][0] = ms;
+    for (int k = 0; k < n && k + 1 < kMaxPhases; ++k)
+        if (cudaEventElapsedTime(&ms, c.ev[b][k], c.ev[b][k + 1]) == cudaSuccess) c.last_ms[b][k + 1] = ms;
+    cudaGetLastError();
 }
 
 // implemented in the kernel translation units
@@ -131,7 +175,9 @@ int mpb200_init(int device) {
     c.sm_count = prop.multiProcessorCount;
     MPB_CUDA(cudaStreamCreateWithFlags(&c.own_stream, cudaStreamNonBlocking));
     c.stream = c.own_stream;
-    for (int i = 0; i <= kMaxPhases; ++i) MPB_CUDA(cudaEventCreate(&c.ev[i]));
+    for (int b = 0; b < kBanks; ++b)
+        for (int i = 0; i <= kMaxPhases; ++i) MPB_CUDA(cudaEventCreate(&c.ev[b][i]));
+    MPB_CUDA(cudaEventCreateWithFlags(&c.ev_scalar, cudaEventDisableTiming));
     MPB_CUDA(cudaMalloc(&c.d_scalar, sizeof(int64_t) * 16));
     MPB_CUDA(cudaMallocHost(&c.h_scalar, sizeof(int64_t) * 16));
     c.launches = 0;
@@ -143,8 +189,10 @@ void mpb200_shutdown(void) {
     Context &c = ctx();
     if (!c.ready) return;
     cudaDeviceSynchronize();
-    for (int i = 0; i <= kMaxPhases; ++i)
-        if (c.ev[i]) cudaEventDestroy(c.ev[i]), c.ev[i] = nullptr;
+    for (int b = 0; b < kBanks; ++b)
+        for (int i = 0; i <= kMaxPhases; ++i)
+            if (c.ev[b][i]) cudaEventDestroy(c.ev[b][i]), c.ev[b][i] = nullptr;
+    if (c.ev_scalar) cudaEventDestroy(c.ev_scalar), c.ev_scalar = nullptr;
     if (c.d_scalar) cudaFree(c.d_scalar), c.d_scalar = nullptr;
     if (c.h_scalar) cudaFreeHost(c.h_scalar), c.h_scalar = nullptr;
     if (c.own_stream) cudaStreamDestroy(c.own_stream), c.own_stream = nullptr;
@@ -162,6 +210,7 @@ int mpb200_set_stream(void *cuda_stream) {
 int mpb200_synchronize(void) {
     MPB_REQUIRE_INIT();
     MPB_CUDA(cudaStreamSynchronize(ctx().stream));
+    trace_dump();
     return MPB200_OK;
 }
 int mpb200_host_alloc(uint64_t bytes, void **out) {
@@ -176,10 +225,12 @@ int mpb200_host_free(void *p) {
     return MPB200_OK;
 }
 int64_t mpb200_launch_count(void) { return ctx().launches; }
-double mpb200_last_ms(int phase) {
-    if (phase < 0 || phase >= kMaxPhases) return 0;
-    return ctx().last_ms[phase];
+double mpb200_last_ms_of(int op, int phase) {
+    if (op < 0 || op >= kBanks || phase < 0 || phase >= kMaxPhases) return 0;
+    if (ctx().ready) phases_resolve(op);
+    return ctx().last_ms[op][phase];
 }
+double mpb200_last_ms(int phase) { return mpb200_last_ms_of(ctx().bank, phase); }
 
 // ---- samples -----------------------------------------------------------------------
 int mpb200_samples_create(const double *V_aos, int64_t N, int d, mpb200_samples **out) {
@@ -431,15 +482,17 @@ int mpb200_points_free(const mpb200_samples *s_, const mpb200_obstacles *o, cons
     const int64_t n = s->q1 - s->q0;  // this process's shard of the samples (all of them by default)
     const size_t words = (size_t)ceil_div(n, 64);
     if (int rc = s->point_bits.reserve(sizeof(uint64_t) * (words + 1))) return rc;
+    phase_bank(MPB200_OP_POINTS);
     phase_mark(0);
     MPB_CUDA(cudaMemsetAsync(s->point_bits.p, 0, sizeof(uint64_t) * (words + 1), st));
     if (int rc = points_free_device(s->V.as<double>() + s->q0 * s->d, n, s->d, o, ss, s->point_bits.as<uint32_t>(), nullptr))
         return rc;
     phase_mark(1);
-    if (bitchunks && words)
-        MPB_CUDA(cudaMemcpyAsync(bitchunks, s->point_bits.p, sizeof(uint64_t) * words, cudaMemcpyDeviceToHost, st));
-    MPB_CUDA(cudaStreamSynchronize(st));
     phases_collect(1);
+    if (bitchunks) {  // NULL: asynchronous, the bits stay on the device (stream-ordered with later calls)
+        if (words) MPB_CUDA(cudaMemcpyAsync(bitchunks, s->point_bits.p, sizeof(uint64_t) * words, cudaMemcpyDeviceToHost, st));
+        MPB_CUDA(cudaStreamSynchronize(st));
+    }
     return MPB200_OK;
 }
 
@@ -452,6 +505,7 @@ int mpb200_edges_free(const mpb200_samples *s, const mpb200_table *t_, const mpb
     cudaStream_t st = c.stream;
     const size_t words = (size_t)ceil_div(t->nnz, 64);
     if (int rc = t->edge_bits.reserve(sizeof(uint64_t) * (words + 1))) return rc;
+    phase_bank(MPB200_OP_EDGES);
     phase_mark(0);
     MPB_CUDA(cudaMemsetAsync(t->edge_bits.p, 0, sizeof(uint64_t) * (words + 1), st));
     MPB_CUDA(cudaMemsetAsync(c.d_scalar + 4, 0, sizeof(int64_t), st));
@@ -459,12 +513,14 @@ int mpb200_edges_free(const mpb200_samples *s, const mpb200_table *t_, const mpb
                                    reinterpret_cast<unsigned long long *>(c.d_scalar + 4)))
         return rc;
     phase_mark(1);
-    if (bitchunks && words)
-        MPB_CUDA(cudaMemcpyAsync(bitchunks, t->edge_bits.p, sizeof(uint64_t) * words, cudaMemcpyDeviceToHost, st));
-    MPB_CUDA(cudaMemcpyAsync(c.h_scalar + 4, c.d_scalar + 4, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-    MPB_CUDA(cudaStreamSynchronize(st));
     phases_collect(1);
-    if (checks) *checks = c.h_scalar[4];
+    if (bitchunks || checks) {  // both NULL: asynchronous, the bits stay on the device
+        if (bitchunks && words)
+            MPB_CUDA(cudaMemcpyAsync(bitchunks, t->edge_bits.p, sizeof(uint64_t) * words, cudaMemcpyDeviceToHost, st));
+        MPB_CUDA(cudaMemcpyAsync(c.h_scalar + 4, c.d_scalar + 4, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        MPB_CUDA(cudaStreamSynchronize(st));
+        if (checks) *checks = c.h_scalar[4];
+    }
     return MPB200_OK;
 }
 
@@ -591,6 +647,7 @@ int mpb200_lq_edges_free(const mpb200_samples *s, const mpb200_table *t_, const 
     cudaStream_t st = c.stream;
     const size_t words = (size_t)ceil_div(t->nnz, 64);
     if (int rc = t->edge_bits.reserve(sizeof(uint64_t) * (words + 1))) return rc;
+    phase_bank(MPB200_OP_EDGES);
     phase_mark(0);
     MPB_CUDA(cudaMemsetAsync(t->edge_bits.p, 0, sizeof(uint64_t) * (words + 1), st));
     MPB_CUDA(cudaMemsetAsync(c.d_scalar + 4, 0, sizeof(int64_t), st));
@@ -598,12 +655,14 @@ int mpb200_lq_edges_free(const mpb200_samples *s, const mpb200_table *t_, const 
                                       reinterpret_cast<unsigned long long *>(c.d_scalar + 4)))
         return rc;
     phase_mark(1);
-    if (bitchunks && words)
-        MPB_CUDA(cudaMemcpyAsync(bitchunks, t->edge_bits.p, sizeof(uint64_t) * words, cudaMemcpyDeviceToHost, st));
-    MPB_CUDA(cudaMemcpyAsync(c.h_scalar + 4, c.d_scalar + 4, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-    MPB_CUDA(cudaStreamSynchronize(st));
     phases_collect(1);
-    if (checks) *checks = c.h_scalar[4];
+    if (bitchunks || checks) {  // both NULL: asynchronous, the bits stay on the device
+        if (bitchunks && words)
+            MPB_CUDA(cudaMemcpyAsync(bitchunks, t->edge_bits.p, sizeof(uint64_t) * words, cudaMemcpyDeviceToHost, st));
+        MPB_CUDA(cudaMemcpyAsync(c.h_scalar + 4, c.d_scalar + 4, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        MPB_CUDA(cudaStreamSynchronize(st));
+        if (checks) *checks = c.h_scalar[4];
+    }
     return MPB200_OK;
 }
 

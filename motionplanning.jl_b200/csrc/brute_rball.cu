@@ -152,6 +152,7 @@ static int brute_build(mpb200_samples *s, double r, mpb200_table *t) {
     constexpr bool kTcDim = (D >= 4 && D <= 14);
     const bool use_tc = kTcDim && !no_tc;
     TcPlan plan = {nullptr, nullptr, 0, 0.0f};
+    phase_bank(MPB200_OP_TABLE);
     phase_mark(0);
     float *Vf = nullptr;
     if (use_tc) {

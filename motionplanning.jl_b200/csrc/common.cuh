@@ -13,6 +13,7 @@ namespace mpb {
 
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 constexpr int kMaxPhases = 8;
+constexpr int kBanks = 4;  // separate phase-event banks: MPB200_OP_TABLE / _POINTS / _EDGES / _OTHER
 
 struct Context {
     bool ready = false;
@@ -20,11 +21,14 @@ struct Context {
     int sm_count = kNumSMs;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;  // the launching stream (own or caller's)
-    cudaEvent_t ev[kMaxPhases + 1] = {};
-    double last_ms[kMaxPhases] = {};
+    cudaEvent_t ev[kBanks][kMaxPhases + 1] = {};
+    double last_ms[kBanks][kMaxPhases] = {};
+    int pending_marks[kBanks] = {};  // phase events recorded but not yet turned into last_ms (done lazily: no sync in the call)
+    int bank = 0;                    // bank of the operation in progress / most recent
     int64_t launches = 0;
     int64_t *d_scalar = nullptr;  // small device scratch for scalars read back to the host
     int64_t *h_scalar = nullptr;  // pinned mirror
+    cudaEvent_t ev_scalar = nullptr;  // marks the end of a scalar read-back (waited on instead of the whole stream)
 };
 Context &ctx();
 
@@ -54,6 +58,7 @@ int fail(int code, const char *fmt, ...);
 #define MPB_LAUNCHED()                                                                            \
     do {                                                                                          \
         mpb::ctx().launches++;                                                                    \
+        mpb::trace_mark(__FILE__, __LINE__);                                                      \
         cudaError_t e__ = cudaGetLastError();                                                     \
         if (e__ != cudaSuccess)                                                                   \
             return mpb::fail(MPB200_ECUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), \
@@ -70,8 +75,12 @@ struct DevBuf {
 };
 
 // timing phases: phase_begin(0) ... phase_end(0) record events on the launching stream
+void phase_bank(int op);               // select the event bank of the operation that starts now
 int phase_mark(int i);                 // record event i
-int phases_collect(int n_marks);       // after a sync: last_ms[k] = elapsed(ev[k], ev[k+1]), last_ms[0] = total
+// MPB200_TRACE=1: an event after every kernel launch (no graph), per-launch gaps printed by trace_dump()
+void trace_mark(const char *file, int line);
+void trace_dump();
+int phases_collect(int n_marks);       // note n_marks events; mpb200_last_ms() waits for them and computes last_ms
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include "predicates.cuh"
 #include "scan.cuh"
+#include <algorithm>
 #include <cstdlib>
 
 namespace mpb {
@@ -305,7 +306,11 @@ __global__ void __launch_bounds__(kQThreads)
 rball_fill(const double *__restrict__ sorted_pos, const int *__restrict__ sorted_idx,
            const int *__restrict__ q_order, const unsigned char *__restrict__ hit_lists, int64_t nq, int64_t q0,
            GridDev g, const int *__restrict__ cell_start, const int64_t *__restrict__ colptr,
-           int64_t *__restrict__ rowval, double *__restrict__ nzval) {
+           int64_t *__restrict__ rowval, double *__restrict__ nzval, const int64_t *__restrict__ nnz_dev,
+           int64_t capacity) {
+    // speculative launch (before the host has read nnz back): do nothing if the table would not fit
+    // the buffers kept from the previous build; the host then grows them and launches again
+    if (nnz_dev && *nnz_dev > capacity) return;
     constexpr int kRuns = (D == 2) ? 3 : 9;
     constexpr int kWBase = 2 * D, kWBeg = 2 * D + 2, kWLen = kWBeg + kRuns;  // word offsets in a record
     constexpr int NV = (kWLen + kRuns + 3) / 4;                                // 16-byte vectors per record
@@ -633,6 +638,7 @@ static int build_table(mpb200_samples *s, double r, mpb200_table *t) {
     };
 
     static const bool use_graph = getenv("MPB200_NO_GRAPH") == nullptr;
+    phase_bank(MPB200_OP_TABLE);
     phase_mark(0);
     if (use_graph && nq > 0 && ncells > 0) {
         uint64_t key[32] = {};
@@ -668,11 +674,43 @@ static int build_table(mpb200_samples *s, double r, mpb200_table *t) {
     }
     phase_mark(1);
     phase_mark(2);
+    static const int fill_u = [] { const char *e = getenv("MPB200_FILL_U"); return e ? atoi(e) : 2; }();
+    auto launch_fill = [&](const int64_t *guard, int64_t capacity) -> int {
+        const int64_t *cp = t->colptr.as<int64_t>();
+        int64_t *rv = t->rowval.as<int64_t>();
+        double *nz = t->nzval.as<double>();
+        const unsigned char *hl = t->masks.as<unsigned char>();
+        if (fill_u == 4)
+            rball_fill<D, 4><<<nbQ, kQThreads, 0, st>>>(sorted_pos, sorted_idx, q_order, hl, nq, s->q0, g, cell_start, cp, rv, nz, guard, capacity);
+        else if (fill_u == 1)
+            rball_fill<D, 1><<<nbQ, kQThreads, 0, st>>>(sorted_pos, sorted_idx, q_order, hl, nq, s->q0, g, cell_start, cp, rv, nz, guard, capacity);
+        else
+            rball_fill<D, 2><<<nbQ, kQThreads, 0, st>>>(sorted_pos, sorted_idx, q_order, hl, nq, s->q0, g, cell_start, cp, rv, nz, guard, capacity);
+        MPB_LAUNCHED();
+        return 0;
+    };
+    // Speculative fill: when the table still owns row/value buffers from an earlier build (a planner
+    // rebuilding with a new radius, or repeated planning steps), the fill is enqueued BEFORE nnz is read
+    // back, guarded on the device by nnz <= capacity, so the GPU does not idle during the read-back.
+    static const bool no_spec = getenv("MPB200_NO_SPEC_FILL") != nullptr;
+    const bool small_keys = N < (int64_t(1) << 26);
+    const int64_t capacity = (int64_t)(std::min(t->rowval.cap / sizeof(int64_t), t->nzval.cap / sizeof(double))) - 1;
+    const bool speculate = !no_spec && small_keys && nq > 0 && capacity > 0;
+    // nnz and n_big come back right after the count scan; the host waits for THAT copy only (an event), so
+    // with a speculative fill it learns nnz -- and returns to the caller, who can enqueue the validity passes --
+    // while the fill is still running
     MPB_CUDA(cudaMemcpyAsync(c.h_scalar, c.d_scalar, sizeof(int64_t) * 2, cudaMemcpyDeviceToHost, st));
-    MPB_CUDA(cudaStreamSynchronize(st));
+    MPB_CUDA(cudaEventRecord(c.ev_scalar, st));
+    phase_mark(3);
+    if (speculate) {
+        if (int rc = launch_fill(c.d_scalar, capacity)) return rc;
+        phase_mark(4);
+    }
+    MPB_CUDA(cudaEventSynchronize(c.ev_scalar));
     const int64_t nnz = c.h_scalar[0];
     const int64_t n_big = c.h_scalar[1];
 
+    const bool filled = speculate && nnz <= capacity;
     if (int rc = t->rowval.reserve(sizeof(int64_t) * (size_t)(nnz + 1))) return rc;
     if (int rc = t->nzval.reserve(sizeof(double) * (size_t)(nnz + 1))) return rc;
     int64_t *spill_row = nullptr;
@@ -682,22 +720,10 @@ static int build_table(mpb200_samples *s, double r, mpb200_table *t) {
         spill_row = t->scratch.as<int64_t>();
         spill_val = reinterpret_cast<double *>(spill_row + nnz);
     }
-    phase_mark(3);
+    if (!filled) phase_mark(3);
     if (nq > 0 && nnz > 0) {
-        if (N < (int64_t(1) << 26)) {
-            static const int fill_u = [] { const char *e = getenv("MPB200_FILL_U"); return e ? atoi(e) : 2; }();
-            const int64_t *cp = t->colptr.as<int64_t>();
-            int64_t *rv = t->rowval.as<int64_t>();
-            double *nz = t->nzval.as<double>();
-            const unsigned char *hl = t->masks.as<unsigned char>();
-            if (fill_u == 4)
-                rball_fill<D, 4><<<nbQ, kQThreads, 0, st>>>(sorted_pos, sorted_idx, q_order, hl, nq, s->q0, g, cell_start, cp, rv, nz);
-            else if (fill_u == 1)
-                rball_fill<D, 1><<<nbQ, kQThreads, 0, st>>>(sorted_pos, sorted_idx, q_order, hl, nq, s->q0, g, cell_start, cp, rv, nz);
-            else
-                rball_fill<D, 2><<<nbQ, kQThreads, 0, st>>>(sorted_pos, sorted_idx, q_order, hl, nq, s->q0, g, cell_start, cp, rv, nz);
-            MPB_LAUNCHED();
-        }
+        if (small_keys && !filled)
+            if (int rc = launch_fill(nullptr, 0)) return rc;
         if (n_big > 0) {
             rball_fill_big<D><<<(unsigned)ceil_div(n_big, kWarpsPerBlock), kWarpsPerBlock * 32, 0, st>>>(
                 V, big_list, n_big, s->q0, g, r2, cell_start, sorted_idx, sorted_pos, t->colptr.as<int64_t>(),
@@ -708,9 +734,8 @@ static int build_table(mpb200_samples *s, double r, mpb200_table *t) {
             MPB_LAUNCHED();
         }
     }
-    phase_mark(4);
-    MPB_CUDA(cudaStreamSynchronize(st));
-    phases_collect(4);
+    if (!filled || n_big > 0) phase_mark(4);
+    phases_collect(4);  // no trailing sync: the fill is stream-ordered before anything that reads the table
     t->ncols = nq;
     t->col0 = s->q0;
     t->nnz = nnz;

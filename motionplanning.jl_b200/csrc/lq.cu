@@ -357,6 +357,7 @@ static int lq_build(mpb200_samples *s, const mpb200_lq *lq, double r, mpb200_tab
     }
     const unsigned nb = (unsigned)ceil_div(nq > 0 ? nq : 1, kLqThreads);
     int *d_max = reinterpret_cast<int *>(c.d_scalar + 2);
+    phase_bank(MPB200_OP_TABLE);
     phase_mark(0);
     // slab capacity from a probe of up to 1024 query columns (exact counts for those columns)
     int cap = 0;

@@ -316,6 +316,7 @@ int mc_run_device(const mpb200_mc_problem *p, const mpb200_obstacles *o, unsigne
     double *d_w = nullptr;
     if (h_hit) { if (int rc = hitb.reserve((size_t)n + 8)) return rc; d_hit = hitb.as<uint8_t>(); }
     if (h_w) { if (int rc = wb.reserve(sizeof(double) * (size_t)(n + 1))) return rc; d_w = wb.as<double>(); }
+    phase_bank(MPB200_OP_OTHER);
     phase_mark(0);
 #define CALL(NZ_, Q_, DW_, K_)                                                                                     \
     do {                                                                                                           \

@@ -152,10 +152,14 @@ class SampleSet:
         _lib.check(_lib.lib().mpb200_points_free(self.handle(), CC.handle(), ctypes.byref(d), _lib.ptr(bits)))
         return bits
 
-    def edges_free(self, table, CC, SS, fetch=True):
-        """Validity bit per stored entry (row y -> column x) of `table`; returns (chunks, checks)."""
+    def edges_free(self, table, CC, SS, fetch=True, count=True):
+        """Validity bit per stored entry (row y -> column x) of `table`; returns (chunks, checks).
+        fetch=False, count=False only enqueues the work (bits stay on the device, no wait)."""
         d = SS.desc()
         bits = self.pool.array(("edge_bits", id(table)), (table.nnz + 63) // 64, np.uint64) if fetch else None
+        if not fetch and not count:
+            _lib.check(_lib.lib().mpb200_edges_free(self.handle(), table.h, CC.handle(), ctypes.byref(d), None, None))
+            return None, None
         checks = _lib.c_i64(0)
         _lib.check(_lib.lib().mpb200_edges_free(self.handle(), table.h, CC.handle(), ctypes.byref(d), _lib.ptr(bits),
                                                 ctypes.byref(checks)))

@@ -150,6 +150,8 @@ class ValidityExchange:
         self.bits_all = torch.empty(self.world * self.cap, dtype=torch.int64, device=dev)
 
     def run(self, table):
+        """Stream-ordered on torch's current stream: either make that the library's launching stream
+        (mpb200_set_stream) or use the waiting forms of the validity calls before calling this."""
         colptr, _, _, words = table_device_tensors(table)
         if words is not None:
             if words.numel() > self.cap:
