@@ -54,6 +54,10 @@ int mpb200_version(void);
 int mpb200_set_stream(void *cuda_stream);
 int mpb200_synchronize(void);
 /* Pinned host memory for result buffers (fast D2H); plain malloc'ed buffers work too. */
+/* Device arrays released by the library (destroyed tables / sample sets, outgrown buffers) are parked
+ * in a free list and reused by later calls instead of going through cudaFree / cudaMalloc (milliseconds
+ * each, device-synchronising).  This returns every parked block to the driver. */
+int mpb200_release_cached(void);
 int mpb200_host_alloc(uint64_t bytes, void **out);
 int mpb200_host_free(void *p);
 /* Number of kernels this library has launched since mpb200_init (bench "gpu_launches"). */

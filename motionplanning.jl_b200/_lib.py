@@ -60,6 +60,7 @@ SIGNATURES = {
     "mpb200_host_alloc": (ctypes.c_int, [ctypes.c_uint64, P(c_vp)]),
     "mpb200_host_free": (ctypes.c_int, [c_vp]),
     "mpb200_launch_count": (c_i64, []),
+    "mpb200_release_cached": (ctypes.c_int, []),
     "mpb200_last_ms": (c_dbl, [ctypes.c_int]),
     "mpb200_last_ms_of": (c_dbl, [ctypes.c_int, ctypes.c_int]),
     "mpb200_samples_create": (ctypes.c_int, [c_vp, c_i64, ctypes.c_int, P(c_vp)]),

@@ -31,30 +31,73 @@ int fail(int code, const char *fmt, ...) {
     return code;
 }
 
+// ---- device memory: DevBuf over a block cache ------------------------------------------------
+// cudaMalloc / cudaFree of the few-hundred-MB arrays of a table cost milliseconds each (and cudaFree
+// synchronises the device), which dwarfs the sub-millisecond kernels when a caller creates and drops
+// sample sets and tables per planning step.  Released blocks are therefore parked in a free list and
+// handed back by best fit.  Everything the library enqueues goes to ONE stream at a time
+// (mpb200_set_stream synchronises the old one), so a parked block can be reused without waiting: its
+// next user is ordered after its last one.
+namespace {
+struct Block { void *p; size_t cap; };
+std::vector<Block> g_blocks;
+size_t g_cached_bytes = 0;
+constexpr size_t kCacheLimit = size_t(64) << 30;  // beyond this, released blocks go back to the driver
+
+void *cache_take(size_t bytes, size_t *cap) {
+    int best = -1;
+    for (int i = 0; i < (int)g_blocks.size(); ++i) {
+        const size_t c = g_blocks[i].cap;
+        if (c >= bytes && c <= 2 * bytes + (size_t(1) << 20) && (best < 0 || c < g_blocks[best].cap)) best = i;
+    }
+    if (best < 0) return nullptr;
+    void *p = g_blocks[best].p;
+    *cap = g_blocks[best].cap;
+    g_cached_bytes -= *cap;
+    g_blocks[best] = g_blocks.back();
+    g_blocks.pop_back();
+    return p;
+}
+}  // namespace
+
+void cache_release_all() {
+    for (const Block &b : g_blocks) cudaFree(b.p);
+    g_blocks.clear();
+    g_cached_bytes = 0;
+}
+
 int DevBuf::reserve(size_t bytes) {
     if (bytes <= cap) return 0;
+    release();
     // grow geometrically so repeated builds with slightly different sizes settle quickly
     size_t want = bytes + bytes / 8 + 256;
-    cudaStream_t st = ctx().stream;
-    cudaStreamSynchronize(st);
-    if (p) cudaFree(p);
-    p = nullptr;
-    cap = 0;
+    if ((p = cache_take(bytes, &cap))) return 0;
     cudaError_t e = cudaMalloc(&p, want);
-    if (e != cudaSuccess) {
+    if (e != cudaSuccess) {  // give the parked blocks back to the driver and ask for the exact size
+        cudaGetLastError();
+        cudaStreamSynchronize(ctx().stream);
+        cache_release_all();
         e = cudaMalloc(&p, bytes);
         want = bytes;
     }
     if (e != cudaSuccess) {
         cudaGetLastError();
         p = nullptr;
+        cap = 0;
         return fail(MPB200_ENOMEM, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
     }
     cap = want;
     return 0;
 }
 void DevBuf::release() {
-    if (p) cudaFree(p);
+    if (p) {
+        if (ctx().ready && g_cached_bytes + cap <= kCacheLimit) {
+            g_blocks.push_back({p, cap});
+            g_cached_bytes += cap;
+        } else {
+            cudaFree(p);
+        }
+    }
     p = nullptr;
     cap = 0;
 }
@@ -192,6 +235,7 @@ void mpb200_shutdown(void) {
     for (int b = 0; b < kBanks; ++b)
         for (int i = 0; i <= kMaxPhases; ++i)
             if (c.ev[b][i]) cudaEventDestroy(c.ev[b][i]), c.ev[b][i] = nullptr;
+    cache_release_all();
     if (c.ev_scalar) cudaEventDestroy(c.ev_scalar), c.ev_scalar = nullptr;
     if (c.d_scalar) cudaFree(c.d_scalar), c.d_scalar = nullptr;
     if (c.h_scalar) cudaFreeHost(c.h_scalar), c.h_scalar = nullptr;
@@ -211,6 +255,12 @@ int mpb200_synchronize(void) {
     MPB_REQUIRE_INIT();
     MPB_CUDA(cudaStreamSynchronize(ctx().stream));
     trace_dump();
+    return MPB200_OK;
+}
+int mpb200_release_cached(void) {
+    MPB_REQUIRE_INIT();
+    MPB_CUDA(cudaStreamSynchronize(ctx().stream));
+    cache_release_all();
     return MPB200_OK;
 }
 int mpb200_host_alloc(uint64_t bytes, void **out) {

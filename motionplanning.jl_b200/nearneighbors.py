@@ -76,10 +76,11 @@ class ImmutableNNC:
 class DeviceTable:
     """Owner of a device-resident CSC table handle (mpb200_table)."""
 
-    def __init__(self):
+    def __init__(self, name="nn"):
         self.h = _lib.c_vp()
         self.nnz = 0
         self.ncols = 0
+        self.name = name  # role of the table ("nn", "F", "B"): keys the reusable pinned result buffers
 
     def close(self):
         if self.h:
@@ -156,7 +157,7 @@ class SampleSet:
         """Validity bit per stored entry (row y -> column x) of `table`; returns (chunks, checks).
         fetch=False, count=False only enqueues the work (bits stay on the device, no wait)."""
         d = SS.desc()
-        bits = self.pool.array(("edge_bits", id(table)), (table.nnz + 63) // 64, np.uint64) if fetch else None
+        bits = self.pool.array(("edge_bits", table.name), (table.nnz + 63) // 64, np.uint64) if fetch else None
         if not fetch and not count:
             _lib.check(_lib.lib().mpb200_edges_free(self.handle(), table.h, CC.handle(), ctypes.byref(d), None, None))
             return None, None
@@ -213,7 +214,7 @@ class MetricNN(SampleSet):
 
     def fetch_edge_bits(self, table=None):
         table = table or self.table
-        bits = self.pool.array(("edge_bits", id(table)), (table.nnz + 63) // 64, np.uint64)
+        bits = self.pool.array(("edge_bits", table.name), (table.nnz + 63) // 64, np.uint64)
         _lib.check(_lib.lib().mpb200_table_fetch_edge_bits(table.h, _lib.ptr(bits)))
         return bits
 
@@ -244,7 +245,7 @@ class QuasiMetricNN(SampleSet):
         V = np.ascontiguousarray(V, dtype=np.float64)
         super().__init__(V, dist, init if init is not None else V[0])
         self.cacheF = self.cacheB = None
-        self.tableF, self.tableB = DeviceTable(), DeviceTable()
+        self.tableF, self.tableB = DeviceTable("F"), DeviceTable("B")
 
     def build_tables(self, r):
         nF, nB = _lib.c_i64(0), _lib.c_i64(0)
