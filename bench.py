@@ -32,6 +32,24 @@ METRIC = "collision_checked_edges_per_sec"
 UNIT = "edges/s"
 
 
+def fill_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of rball_fill<2, U> on this workload, from the
+    committed `ncu --set full` capture of the newest round (profiles/rN/traffic.json, scripts/ncu_traffic.py);
+    None when no capture is committed.  Measured under the profiler, so it is traffic only, never a time."""
+    import glob
+    for path in sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r*", "traffic.json")),
+                       reverse=True):
+        try:
+            with open(path) as f:
+                t = json.load(f)
+        except (OSError, ValueError):
+            continue
+        for k, v in t.items():
+            if k.startswith("rball_fill<2"):
+                return v["dram_bytes_per_launch"]
+    return None
+
+
 def fmt_radius(N, d, rm=1.0, vol=1.0):
     import math
     return rm * 2 * (1 / d * vol / (math.pi ** (d / 2) / math.gamma(d / 2 + 1)) * math.log(N) / N) ** (1 / d)
@@ -360,7 +378,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": 1e3 * float(e2e_t[0]), "steps": args.e2e_steps},
             "roofline": {"kernel": "rball_fill<2>", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind,
+                         "frac": achieved / peak, "traffic": fill_traffic(), "peak_kind": peak_kind,
                          "algorithmic_bytes_per_launch": alg_bytes},
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -296,7 +296,10 @@ __device__ __forceinline__ void bitonic64(unsigned &k0, unsigned &k1, int lane) 
 // Int64/Float64 burst.  Columns with more than kListCap entries or more than kMaxCand
 // candidates are left to rball_fill_big.  Requires N < 2^26 (key packing).
 //
-// Measured alternative (r1m): ranking each index against the column's indices read back from
+// Measured alternatives: (r1o) prefetching the next column group's hit byte -> position -> index/point chain
+// one group ahead (software pipeline) changed nothing (297 us for U = 1, 2, 4): the kernel is bound by LSU
+// wavefronts + issue slots, not by the latency of that chain, although half the stall samples sit on it.
+// (r1m) ranking each index against the column's indices read back from
 // shared memory four at a time (no shuffles, rows stored at base + rank) halves the LSU
 // wavefronts of the sort but costs ~2.3 ALU instructions per comparison: 269M warp
 // instructions instead of 195M, issue-bound at 79%, 321 us against 295 us for this form.
