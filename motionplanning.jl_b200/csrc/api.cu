@@ -167,7 +167,7 @@ int grid_inball_build(mpb200_samples *s, double r, mpb200_table *t);
 int brute_inball_build(mpb200_samples *s, double r, mpb200_table *t);
 
 int points_free_device(const double *dV, int64_t n, int d, const mpb200_obstacles *o, const mpb200_space_desc *ss,
-                       uint32_t *d_bits32, uint8_t *d_bytes);
+                       uint32_t *d_bits32, uint8_t *d_bytes, const int *order = nullptr);
 int edges_free_device(const double *dV, int d, const mpb200_table *t, const mpb200_obstacles *o,
                       const mpb200_space_desc *ss, uint32_t *d_bits32, unsigned long long *d_checks);
 int segments_free_device(const double *dA, const double *dB, int64_t n, int d, const mpb200_obstacles *o,
@@ -315,7 +315,7 @@ int mpb200_samples_destroy(mpb200_samples *s) {
     if (ctx().ready) cudaStreamSynchronize(ctx().stream);
     if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
     s->V.release(); s->cell_start.release(); s->cell_fill.release(); s->sorted_idx.release();
-    s->sorted_pos.release(); s->minmax.release(); s->scan_tmp.release(); s->point_bits.release(); s->q_order.release(); s->aux.release();
+    s->sorted_pos.release(); s->pt_order.release(); s->minmax.release(); s->scan_tmp.release(); s->point_bits.release(); s->q_order.release(); s->aux.release();
     delete s;
     return MPB200_OK;
 }
@@ -324,6 +324,7 @@ int mpb200_samples_set_query_range(mpb200_samples *s, int64_t q0, int64_t q1) {
     MPB_CHECK_ARG(0 <= q0 && q0 <= q1 && q1 <= s->N, "query range must satisfy 0 <= q0 <= q1 <= N");
     s->q0 = q0;
     s->q1 = q1;
+    s->pt_order_valid = false;
     // bounding box of the shard's own samples: the grid only has to cover it (+ r)
     memcpy(s->h_qbbox, s->h_bbox, sizeof(s->h_bbox));
     if (ctx().ready && q1 > q0 && (q0 != 0 || q1 != s->N)) {
@@ -535,7 +536,9 @@ int mpb200_points_free(const mpb200_samples *s_, const mpb200_obstacles *o, cons
     phase_bank(MPB200_OP_POINTS);
     phase_mark(0);
     MPB_CUDA(cudaMemsetAsync(s->point_bits.p, 0, sizeof(uint64_t) * (words + 1), st));
-    if (int rc = points_free_device(s->V.as<double>() + s->q0 * s->d, n, s->d, o, ss, s->point_bits.as<uint32_t>(), nullptr))
+    // after a grid build the samples are visited in cell order: neighbouring lanes test neighbouring points
+    if (int rc = points_free_device(s->V.as<double>() + s->q0 * s->d, n, s->d, o, ss, s->point_bits.as<uint32_t>(), nullptr,
+                                    s->pt_order_valid ? s->pt_order.as<int>() : nullptr))
         return rc;
     phase_mark(1);
     phases_collect(1);

@@ -51,10 +51,24 @@ template <int N, int DW, int KIND>
 __global__ void __launch_bounds__(kThreads)
 points_free_kernel(const double *__restrict__ V, int64_t n, SpaceDev S, const double *__restrict__ g_table,
                    int table_words, int M, bool use_smem, uint32_t *__restrict__ bits32,
-                   uint8_t *__restrict__ bytes) {
+                   uint8_t *__restrict__ bytes, const int *__restrict__ order) {
     extern __shared__ double s_table[];
     const double *T = stage_table(g_table, table_words, use_smem, s_table);
     const int64_t n_pad = (n + 31) & ~int64_t(31);
+    if (order) {
+        // points visited in grid-cell order (a permutation of 0 .. n-1): a warp's points are neighbours, so its
+        // lanes agree on which obstacles they are near; bits land in the pre-zeroed words with atomicOr
+        for (int64_t ti = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; ti < n; ti += (int64_t)gridDim.x * blockDim.x) {
+            const int64_t i = order[ti];
+            double v[N];
+#pragma unroll
+            for (int k = 0; k < N; ++k) v[k] = V[i * N + k];
+            const bool ok = state_free<N, DW, KIND>(S, T, M, v);
+            if (bits32 && ok) atomicOr(&bits32[i >> 5], 1u << (i & 31));
+            if (bytes) bytes[i] = ok ? 1 : 0;
+        }
+        return;
+    }
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += (int64_t)gridDim.x * blockDim.x) {
         bool ok = false;
         if (i < n) {
@@ -372,7 +386,7 @@ static int check_obstacles(const mpb200_obstacles *o, int dw) {
 }
 
 int points_free_device(const double *dV, int64_t n, int d, const mpb200_obstacles *o, const mpb200_space_desc *ss,
-                       uint32_t *d_bits32, uint8_t *d_bytes) {
+                       uint32_t *d_bits32, uint8_t *d_bytes, const int *order) {
     SpaceDev S;
     int dw;
     if (int rc = make_space(ss, d, &S, &dw)) return rc;
@@ -383,7 +397,7 @@ int points_free_device(const double *dV, int64_t n, int d, const mpb200_obstacle
     do {                                                                                               \
         if (int rc = prep_kernel(points_free_kernel<N_, DW_, K_>, L.smem)) return rc;                  \
         points_free_kernel<N_, DW_, K_><<<L.grid, kThreads, L.smem, st>>>(dV, n, S, L.table, L.words, L.M, \
-                                                                          L.use_smem, d_bits32, d_bytes); \
+                                                                          L.use_smem, d_bits32, d_bytes, order); \
     } while (0)
     MPB_DISPATCH_DIMS(S.n, dw, o->kind, CALL);
 #undef CALL

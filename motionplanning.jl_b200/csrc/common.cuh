@@ -115,6 +115,8 @@ struct mpb200_samples {
     mpb::DevBuf cell_fill;   // int32 ncells (scatter cursors)
     mpb::DevBuf sorted_idx;  // int32 N   original index of the k-th point in cell order
     mpb::DevBuf sorted_pos;  // f64 d x N positions in cell order (AoS)
+    mpb::DevBuf pt_order;    // int32 (q1-q0): the shard's samples (relative to q0) in grid-cell order, from the last grid build
+    bool pt_order_valid = false;
     mpb::DevBuf minmax;      // f64 2*d bounding box
     double h_bbox[32] = {};  // host copy of the bounding box (mins then maxs), read once at create
     double h_qbbox[32] = {}; // bounding box of the query range's samples (== h_bbox for the full range)

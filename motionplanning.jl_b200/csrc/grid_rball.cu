@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(kQThreads)
 rball_count(const double *__restrict__ sorted_pos, const int *__restrict__ sorted_idx,
             const int *__restrict__ q_order, int64_t nq, int64_t q0, GridDev g, double r2,
             const int *__restrict__ cell_start, int list_cap, int *__restrict__ counts, int *__restrict__ col_order,
-            uint32_t *__restrict__ hit_lists, int *__restrict__ big_list, unsigned long long *__restrict__ n_big) {
+            int *__restrict__ pt_order, uint32_t *__restrict__ hit_lists, int *__restrict__ big_list, unsigned long long *__restrict__ n_big) {
     constexpr int kRuns = (D == 2) ? 3 : 9;
     __shared__ __align__(16) unsigned char s_hits[kListCap][kQThreads];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -234,6 +234,7 @@ rball_count(const double *__restrict__ sorted_pos, const int *__restrict__ sorte
         const int w = (int)(sorted_idx[pos] - q0);
         counts[w] = cnt;
         col_order[t] = w;  // columns in cell order, for the collision passes (classify_columns)
+        pt_order[t] = w;   // the same permutation kept with the sample set (points_free_kernel)
         if (cnt > 0 && (cnt > list_cap || total > kMaxCand)) {
             unsigned long long slot = atomicAdd(n_big, 1ULL);
             big_list[slot] = w;
@@ -596,6 +597,8 @@ static int build_table(mpb200_samples *s, double r, mpb200_table *t) {
     if (int rc = t->colptr.reserve(sizeof(int64_t) * (size_t)(nq + 1))) return rc;
     if (int rc = t->masks.reserve((size_t)kListCap * 32 * (size_t)(ceil_div(nq, 32) + 1))) return rc;
     if (int rc = t->col_order.reserve(sizeof(int) * (size_t)(nq + 1))) return rc;
+    if (int rc = s->pt_order.reserve(sizeof(int) * (size_t)(nq + 1))) return rc;
+    s->pt_order_valid = false;
     t->has_order = false;
     int *hist = s->cell_fill.as<int>();
     int *cell_start = s->cell_start.as<int>();
@@ -634,7 +637,7 @@ static int build_table(mpb200_samples *s, double r, mpb200_table *t) {
         MPB_CUDA(cudaMemsetAsync(c.d_scalar, 0, sizeof(int64_t) * 2, st));
         if (nq > 0) {
             rball_count<D><<<nbQ, kQThreads, 0, st>>>(sorted_pos, sorted_idx, q_order, nq, s->q0, g, r2, cell_start,
-                                                     list_cap, counts, t->col_order.as<int>(), hit_lists, big_list, d_nbig);
+                                                     list_cap, counts, t->col_order.as<int>(), s->pt_order.as<int>(), hit_lists, big_list, d_nbig);
             MPB_LAUNCHED();
         }
         return exclusive_scan<int, int64_t>(counts, nq, t->colptr.as<int64_t>(), (int64_t)1, s->scan_tmp, c.d_scalar);
@@ -648,7 +651,7 @@ static int build_table(mpb200_samples *s, double r, mpb200_table *t) {
         int kk = 0;
         auto put = [&](const void *p, size_t n) { uint64_t v = 0; memcpy(&v, p, n); key[kk++] = v; };
         const void *ptrs[] = {V, hist, cell_start, sorted_idx, sorted_pos, hit_lists, counts, t->colptr.p, s->scan_tmp.p,
-                              s->q_order.p, c.d_scalar, (const void *)st, t->col_order.p};
+                              s->q_order.p, c.d_scalar, (const void *)st, t->col_order.p, s->pt_order.p};
         for (const void *p : ptrs) put(&p, sizeof(p));
         put(&N, 8); put(&nq, 8); put(&s->q0, 8); put(&r, 8); put(&g.inv_h, 8); put(&g.lo[0], 8); put(&g.lo[1], 8);
         put(&g.lo[2], 8); put(&g.n[0], 4); put(&g.n[1], 4); put(&g.n[2], 4);
@@ -745,6 +748,7 @@ static int build_table(mpb200_samples *s, double r, mpb200_table *t) {
     t->r = r;
     t->euclid = true;
     t->has_order = nq > 0;
+    s->pt_order_valid = nq > 0;
     return 0;
 }
 

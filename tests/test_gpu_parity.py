@@ -356,3 +356,30 @@ def test_k2_stripe_sorted_shards_use_restricted_grid(gpu, orc, d):
         got_rows.append(cache.D.rowval.copy())
         NN.close()
     assert np.array_equal(np.concatenate(got_rows), full[1])
+
+
+@pytest.mark.parametrize("d", [2, 3])
+def test_k6_cell_ordered_points_equal_index_ordered(gpu, orc, d):
+    """points_free walks the samples in grid-cell order once a grid exists (and over a shard's own range):
+    same bits as the index-ordered pass before any build, and as the oracle."""
+    mp = gpu
+    N = 30_011   # not a multiple of 32 or 64
+    V = fx.uniform_samples(N, d, 77) * 1.06 - 0.03   # some points out of bounds
+    SSp, SSo = _space_pair(mp, orc, [0] * d, [1] * d)
+    if d == 2:
+        CC, R = mp.PointRobot2D(mp.obstaclesets.ISRR_2H()), orc.Obstacles2D(fx.ISRR_2H)
+    else:
+        CC, R = mp.PointRobotNDBoxes([mp.BoxBounds(b) for b in fx.BOXES3D]), orc.Boxes(fx.BOXES3D)
+    exp = orc.states_free(R, SSo, V)
+    NN = mp.MetricNN(V)
+    before = unpack_bits(NN.points_free(CC, SSp), N).copy()
+    NN.build_table(0.02 if d == 2 else 0.05)
+    after = unpack_bits(NN.points_free(CC, SSp), N).copy()
+    assert np.array_equal(before, exp) and np.array_equal(after, exp)
+    q0, q1 = 10_007, 20_033
+    NN.set_query_range(q0, q1)
+    shard_before = unpack_bits(NN.points_free(CC, SSp), q1 - q0).copy()
+    NN.build_table(0.02 if d == 2 else 0.05)
+    shard_after = unpack_bits(NN.points_free(CC, SSp), q1 - q0).copy()
+    assert np.array_equal(shard_before, exp[q0:q1]) and np.array_equal(shard_after, exp[q0:q1])
+    NN.close()
