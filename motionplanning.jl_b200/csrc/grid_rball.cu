@@ -192,6 +192,12 @@ __device__ __forceinline__ int query_spans(const GridDev &g, const double *p, co
 // (the candidate's number in run order), staged per thread in shared memory and written out by
 // the warp as a [tile = 32 queries][slot][lane] byte array (one 32-byte sector per slot), so the
 // fill pass never re-evaluates a distance and reads its column's list with coalesced byte loads.
+//
+// The kernel is bound by the L1 data pipe (ncu r1k: l1tex__data_pipe_lsu_wavefronts 86% of peak): the
+// lanes of a warp sit in 3-4 different cells, so every candidate load touches 3-4 lines.  Measured
+// alternatives that did NOT help: an FP32 grid-relative prefilter with exact FP64 recheck in a rounding
+// band (8-byte loads; count 96 -> 102 us, scatter +22 us for the extra array), staging the warp's union
+// spans in shared memory (60 registers, 100 us), unroll 1/2/8 (+-2 us).
 template <int D>
 __global__ void __launch_bounds__(kQThreads)
 rball_count(const double *__restrict__ sorted_pos, const int *__restrict__ sorted_idx,
