@@ -123,6 +123,87 @@ __global__ void __launch_bounds__(256) cell_scatter(const double *__restrict__ V
     for (int i = 0; i < D; ++i) sorted_pos[(size_t)pos * D + i] = V[j * D + i];
 }
 
+// Shard form of the grid build (query range != all samples).  The samples are replicated, but only those
+// inside the shard's box (own bounding box grown by r) can matter: the histogram pass is the ONLY pass
+// over all N samples; it appends the in-range ones to a compact list (warp-aggregated atomics), and the
+// scatter runs over that list.  q_order -- the cell-order positions of the shard's own query samples -- is
+// then collected by a pass over the gridded positions that appends 256 consecutive positions at a time
+// (one atomic per block): the list is not globally sorted, but every run of it is cell-coherent, which is
+// all the thread-per-query kernels need, and no N-sized flag / scan / compaction pass is left.
+// Append slots for the threads of a 256-thread block whose `flag` is set: ONE atomicAdd on the list counter per block
+// (same-address atomics serialise in L2; per-warp aggregation was measured at ~30 us per million items).  Returns
+// the thread's slot (valid when flag).  All threads of the block must call it.
+__device__ __forceinline__ int block_append_slot(bool flag, int *__restrict__ counter) {
+    __shared__ int s_warp[8];
+    __shared__ int s_base;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned m = __ballot_sync(0xffffffffu, flag);
+    if (lane == 0) s_warp[wid] = __popc(m);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { const int c = s_warp[w]; s_warp[w] = tot; tot += c; }
+        s_base = tot ? atomicAdd(counter, tot) : 0;
+    }
+    __syncthreads();
+    return s_base + s_warp[wid] + __popc(m & ((1u << lane) - 1u));
+}
+
+template <int D>
+__global__ void __launch_bounds__(256) cell_histogram_shard(const double *__restrict__ V, int64_t N, GridDev g,
+                                                            int *__restrict__ hist, int *__restrict__ in_j,
+                                                            int *__restrict__ in_l, int *__restrict__ n_in) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool inside = j < N;
+    double p[D];
+    if (inside) {
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            p[i] = V[j * D + i];
+            inside = inside && (p[i] >= g.in_lo[i] && p[i] <= g.in_hi[i]);
+        }
+    }
+    int l = -1;
+    if (inside) {
+        int c[D];
+        cell_of<D>(g, p, c);
+        l = cell_linear<D>(g, c);
+        atomicAdd(&hist[l], 1);
+    }
+    const int slot = block_append_slot(inside, n_in);
+    if (inside) {
+        in_j[slot] = (int)j;
+        in_l[slot] = l;
+    }
+}
+template <int D>
+__global__ void __launch_bounds__(256) cell_scatter_shard(const double *__restrict__ V, const int *__restrict__ n_in,
+                                                          const int *__restrict__ in_j, const int *__restrict__ in_l,
+                                                          const int *__restrict__ cell_start, int *__restrict__ cursor,
+                                                          int *__restrict__ sorted_idx, double *__restrict__ sorted_pos) {
+    const int n = *n_in;  // grid-stride: the grid is sized for the SMs, not for the (device-side) list length
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int j = in_j[i], l = in_l[i];
+        const int pos = cell_start[l] + atomicAdd(&cursor[l], 1);
+        sorted_idx[pos] = j;
+#pragma unroll
+        for (int k = 0; k < D; ++k) sorted_pos[(size_t)pos * D + k] = V[(size_t)j * D + k];
+    }
+}
+__global__ void __launch_bounds__(256) collect_queries(const int *__restrict__ sorted_idx, const int *__restrict__ n_in,
+                                                       int64_t q0, int64_t q1, int *__restrict__ q_order,
+                                                       int *__restrict__ n_q) {
+    const int n = *n_in;
+    for (int64_t b0 = (int64_t)blockIdx.x * blockDim.x; b0 < n; b0 += (int64_t)gridDim.x * blockDim.x) {  // block-uniform
+        const int64_t k = b0 + threadIdx.x;
+        const bool mine = k < n && sorted_idx[k] >= q0 && sorted_idx[k] < q1;
+        const int slot = block_append_slot(mine, n_q);
+        if (mine) q_order[slot] = (int)k;
+        __syncthreads();  // block_append_slot's shared scratch is reused by the next chunk
+    }
+}
+
 // ---- K2: r-ball ------------------------------------------------------------------------
 // squared distance in the reference's order: s = (a1-b1)^2; s = s + (a_i-b_i)^2 ...
 template <int D>
@@ -512,19 +593,6 @@ rball_fill_big(const double *__restrict__ V, const int *__restrict__ big_list, i
     }
 }
 
-// shard support: cell-order positions whose sample index lies in [q0, q1)
-__global__ void __launch_bounds__(256) range_flags(const int *__restrict__ sorted_idx, int64_t N,
-                                                   const int *__restrict__ n_valid, int64_t q0, int64_t q1,
-                                                   int *__restrict__ flags) {
-    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < N) flags[k] = (k < *n_valid && sorted_idx[k] >= q0 && sorted_idx[k] < q1) ? 1 : 0;  // n_valid = gridded samples
-}
-__global__ void __launch_bounds__(256) range_scatter(const int *__restrict__ flags, const int *__restrict__ offs,
-                                                     int64_t N, int *__restrict__ q_order) {
-    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < N && flags[k]) q_order[offs[k]] = (int)k;
-}
-
 // spill path: one block per over-sized column; rank sort from the unsorted spill copy
 __global__ void __launch_bounds__(256)
 sort_big_columns(const int *__restrict__ big_list, const int64_t *__restrict__ colptr,
@@ -597,7 +665,7 @@ static int build_table(mpb200_samples *s, double r, mpb200_table *t) {
     if (int rc = s->sorted_idx.reserve(sizeof(int) * (size_t)(2 * N + 2))) return rc;  // + cell_id scratch
     if (int rc = s->sorted_pos.reserve(sizeof(double) * (size_t)(D * N + 1))) return rc;
     if (int rc = s->scan_tmp.reserve(sizeof(int64_t) * (size_t)(ceil_div(ncells > N ? ncells : N, kScanTile) + 2))) return rc;
-    if (nq != N)
+    if (nq != N)  // shard: q_order | compact in-range list (sample, cell)
         if (int rc = s->q_order.reserve(sizeof(int) * (size_t)(3 * N + 4))) return rc;
     if (int rc = t->counts.reserve(sizeof(int) * (size_t)(2 * nq + 2))) return rc;
     if (int rc = t->colptr.reserve(sizeof(int64_t) * (size_t)(nq + 1))) return rc;
@@ -624,20 +692,29 @@ static int build_table(mpb200_samples *s, double r, mpb200_table *t) {
 
     // the front half: K1 (histogram, scan, scatter) [+ shard compaction] + count pass + colptr scan
     auto front = [&]() -> int {
-        MPB_CUDA(cudaMemsetAsync(hist, 0, sizeof(int) * (size_t)(ncells + 1), st));
-        cell_histogram<D><<<nbN, 256, 0, st>>>(V, N, g, hist, cell_id);
-        MPB_LAUNCHED();
-        if (int rc = exclusive_scan<int, int>(hist, ncells, cell_start, 0, s->scan_tmp, nullptr)) return rc;
-        MPB_CUDA(cudaMemsetAsync(hist, 0, sizeof(int) * (size_t)(ncells + 1), st));
-        cell_scatter<D><<<nbN, 256, 0, st>>>(V, N, cell_id, cell_start, hist, sorted_idx, sorted_pos);
-        MPB_LAUNCHED();
-        if (nq != N) {  // shard: compact the cell-order positions this process owns
+        if (nq != N) {  // shard: one pass over all N samples, everything else over the in-range ones
             int *qo = s->q_order.as<int>();
-            int *flags = qo + N + 1, *offs = flags + N + 1;
-            range_flags<<<nbN, 256, 0, st>>>(sorted_idx, N, cell_start + ncells, s->q0, s->q1, flags);
+            int *in_j = qo + N + 1, *in_l = in_j + N + 1;
+            int *n_in = reinterpret_cast<int *>(c.d_scalar + 6);  // length of the compact list
+            int *n_q = reinterpret_cast<int *>(c.d_scalar + 7);   // queries collected (== nq)
+            const unsigned nbS = (unsigned)std::min<int64_t>(nbN, (int64_t)c.sm_count * 8);
+            MPB_CUDA(cudaMemsetAsync(hist, 0, sizeof(int) * (size_t)(ncells + 1), st));
+            MPB_CUDA(cudaMemsetAsync(n_in, 0, sizeof(int64_t) * 2, st));
+            cell_histogram_shard<D><<<nbN, 256, 0, st>>>(V, N, g, hist, in_j, in_l, n_in);
             MPB_LAUNCHED();
-            if (int rc = exclusive_scan<int, int>(flags, N, offs, 0, s->scan_tmp, nullptr)) return rc;
-            range_scatter<<<nbN, 256, 0, st>>>(flags, offs, N, qo);
+            if (int rc = exclusive_scan<int, int>(hist, ncells, cell_start, 0, s->scan_tmp, nullptr)) return rc;
+            MPB_CUDA(cudaMemsetAsync(hist, 0, sizeof(int) * (size_t)(ncells + 1), st));
+            cell_scatter_shard<D><<<nbS, 256, 0, st>>>(V, n_in, in_j, in_l, cell_start, hist, sorted_idx, sorted_pos);
+            MPB_LAUNCHED();
+            collect_queries<<<nbS, 256, 0, st>>>(sorted_idx, n_in, s->q0, s->q1, qo, n_q);
+            MPB_LAUNCHED();
+        } else {
+            MPB_CUDA(cudaMemsetAsync(hist, 0, sizeof(int) * (size_t)(ncells + 1), st));
+            cell_histogram<D><<<nbN, 256, 0, st>>>(V, N, g, hist, cell_id);
+            MPB_LAUNCHED();
+            if (int rc = exclusive_scan<int, int>(hist, ncells, cell_start, 0, s->scan_tmp, nullptr)) return rc;
+            MPB_CUDA(cudaMemsetAsync(hist, 0, sizeof(int) * (size_t)(ncells + 1), st));
+            cell_scatter<D><<<nbN, 256, 0, st>>>(V, N, cell_id, cell_start, hist, sorted_idx, sorted_pos);
             MPB_LAUNCHED();
         }
         MPB_CUDA(cudaMemsetAsync(c.d_scalar, 0, sizeof(int64_t) * 2, st));

@@ -8,11 +8,17 @@ import mpb200
 from mpb200 import _lib
 from bench import fmt_radius, make_samples
 lib = _lib.load()
-N = 1_000_000
+G = int(os.environ.get("SHARDS", "1"))   # emulate rank 0 of a G-GPU weak-scaling run on one GPU
+N = 1_000_000 * G
 r = fmt_radius(N, 2)
 V = make_samples(N)
+if G > 1:
+    V = V[np.argsort(V[:, 0], kind="stable")]
 CC = mpb200.PointRobot2D(mpb200.obstaclesets.ISRR_2H()); SS = mpb200.UnitHypercube(2); CC.handle()
-NN = mpb200.MetricNN(V); NN.handle()
+NN = mpb200.MetricNN(V)
+if G > 1:
+    NN.set_query_range(0, 1_000_000)
+NN.handle()
 flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
 stream = torch.cuda.Stream()
 torch.cuda.set_stream(stream)
