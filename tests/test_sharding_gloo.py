@@ -83,3 +83,34 @@ def test_world2_gloo_allgathers(tmp_path):
     mp_.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
     for r in range(world):
         assert open(tmp_path / ("ok%d" % r)).read() == "1"
+
+
+def test_validity_exchange_wire_format_roundtrip():
+    """ValidityExchange packs [int32 column lengths | uint64 validity words] per rank; assemble() must rebuild
+    the global colptr and the concatenated BitVector from the gathered buffer (host logic, no GPU/NCCL)."""
+    import torch
+    from mpb200 import sharding
+    rng = np.random.Generator(np.random.PCG64(5))
+    world, ncols = 3, 7                                  # odd column count: the int32 block is padded to 8 bytes
+    counts = rng.integers(0, 40, size=(world, ncols)).astype(np.int64)
+    nnz = counts.sum(axis=1)
+    cap = int((nnz.max() + 63) // 64) + 2
+    ex = sharding.ValidityExchange.__new__(sharding.ValidityExchange)
+    ex.world, ex.ncols, ex.cap = world, ncols, cap
+    ex.cnt_words = (ncols + 1) // 2
+    ex.stride = ex.cnt_words + cap
+    buf = np.zeros((world, ex.stride), dtype=np.int64)
+    bits = []
+    for g in range(world):
+        buf[g, :ex.cnt_words].view(np.int32)[:ncols] = counts[g]
+        b = rng.integers(0, 2, size=int(nnz[g])).astype(np.uint8)
+        bits.append(b)
+        words = np.packbits(np.concatenate([b, np.zeros((-len(b)) % 64, np.uint8)]), bitorder="little").view(np.uint64)
+        buf[g, ex.cnt_words:ex.cnt_words + len(words)] = words.view(np.int64)
+    ex.recv = torch.from_numpy(buf.reshape(-1).copy())
+    colptr, chunks = ex.assemble()
+    exp_colptr = np.concatenate([[1], 1 + np.cumsum(counts.reshape(-1))])
+    assert np.array_equal(colptr, exp_colptr)
+    allbits = np.concatenate(bits)
+    got = np.unpackbits(chunks.view(np.uint8), bitorder="little")[:len(allbits)]
+    assert np.array_equal(got, allbits)
