@@ -69,7 +69,7 @@ def peaks():
 
 # ---------------------------------------------------------------------------------------------
 class ClockSampler:
-    """SM clock + throttle reasons sampled DURING the timed region (pynvml, 20 ms period)."""
+    """SM clock + throttle reasons sampled DURING the timed region (pynvml, 2 ms period: the region is tens of ms)."""
 
     def __init__(self, index):
         self.samples, self.reasons, self.max_mhz = [], set(), None
@@ -101,7 +101,7 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(0.002)
 
     def start(self):
         if self.nv:
