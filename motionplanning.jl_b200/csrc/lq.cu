@@ -140,6 +140,18 @@ constexpr int kLqTile = 128;
 // K5.  MODE 0: per-column counts for both directions; MODE 1: rows + costs into the CSC arrays;
 // MODE 2: ONE sweep that counts and appends every neighbour (index, cost) to the column's slab
 // (capacity `cap` per direction), finished by lq_slab_to_csc -- the all-pairs work runs once.
+//
+// Two stages per warp.  Stage 1 is uniform: every lane evaluates alpha/beta/gamma and the reference's
+// candidate test dcost(r) > 0 (linearquadratic.jl:213) for its own query against the staged sample, both
+// directions; a fraction of a percent of the pairs survive.  Running the safeguarded Newton right there
+// left 7 of 32 lanes busy (ncu, profiles/r1/lq_inball_ncu_summary.txt: 61% of stall samples on fixed-latency
+// dependencies of the few active lanes).  Survivors are therefore pushed, in lane order, into a per-warp ring
+// (owner lane | direction | sample index), and stage 2 runs whenever 32 are waiting: lane e takes item e,
+// reads the owner's state from shared memory and the sample from global memory, redoes alpha/beta/gamma in the
+// same operation order (bit-identical), runs topt_newton + cost, and the accepted ones are emitted to their
+// owner's column.  Items of one (owner, direction) enter the ring in ascending sample order and leave it in
+// FIFO order; inside a batch the slot is the owner's running count plus the number of accepted earlier
+// peers (match.any + ballot), so rows still come out ascending without a sort.
 template <int D, int MODE>
 __global__ void __launch_bounds__(kLqThreads)
 lq_inball_kernel(const double *__restrict__ V, int64_t N, int64_t q0, int64_t nq, LqDev L, double r,
@@ -149,42 +161,100 @@ lq_inball_kernel(const double *__restrict__ V, int64_t N, int64_t q0, int64_t nq
                  double *__restrict__ slabF_c, int *__restrict__ slabB_j, double *__restrict__ slabB_c) {
     constexpr int NS = 2 * D;
     constexpr bool FILL = (MODE == 1);
+    constexpr int kRing = 128;  // >= 31 waiting + 64 pushed per step
     __shared__ double tile[kLqTile * NS];
+    __shared__ double s_x[kLqThreads * NS];
+    __shared__ unsigned s_ring[kLqThreads / 32][kRing];
+    __shared__ int s_cnt[2][kLqThreads];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = w < nq;
     const int64_t q = q0 + w;
     double x[NS];
 #pragma unroll
-    for (int i = 0; i < NS; ++i) x[i] = active ? V[q * NS + i] : 0.0;
-    int nF = 0, nB = 0;
-    int64_t posF = 0, posB = 0;
-    if (FILL && active) { posF = colptrF[w] - 1; posB = colptrB[w] - 1; }
+    for (int i = 0; i < NS; ++i) {
+        x[i] = active ? V[q * NS + i] : 0.0;
+        s_x[threadIdx.x * NS + i] = x[i];
+    }
+    s_cnt[0][threadIdx.x] = 0;
+    s_cnt[1][threadIdx.x] = 0;
+    unsigned head = 0, tail = 0;  // warp-uniform ring positions (monotone; slot = pos % kRing)
+
+    // stage 2 over the first n ring items (n <= 32); every lane of the warp calls it
+    auto process = [&](int n) {
+        const bool have = lane < n;
+        const unsigned item = have ? s_ring[wid][(head + lane) % kRing] : 0u;
+        const int owner = (int)(item >> 27), dir = (int)((item >> 26) & 1u);
+        const int64_t j = (int64_t)(item & 0x3ffffffu);
+        double c = 0.0;
+        bool acc = false;
+        if (have) {
+            double from[NS], to[NS];  // forwards: owner -> sample; backwards: sample -> owner
+#pragma unroll
+            for (int i = 0; i < NS; ++i) {
+                const double xo = s_x[(wid * 32 + owner) * NS + i], y = V[j * NS + i];
+                from[i] = dir ? y : xo;
+                to[i] = dir ? xo : y;
+            }
+            if (same_state<D>(from, to)) {
+                c = 0.0;                                            // linearquadratic.jl:192 (duplicate states)
+            } else {
+                const Abg k = lq_abg<D>(L, from, to);
+                c = lq_cost(k, lq_topt_newton(k, r));
+            }
+            acc = c <= r;                                           // :221
+        }
+        const unsigned peers = __match_any_sync(0xffffffffu, have ? (item >> 26) : (0x80000000u | (unsigned)lane));
+        const unsigned accm = __ballot_sync(0xffffffffu, acc);
+        const unsigned mine = peers & accm;
+        if (acc) {
+            const int col = wid * 32 + owner;
+            const int slot = s_cnt[dir][col] + __popc(mine & ((1u << lane) - 1u));
+            const int64_t wo = (int64_t)blockIdx.x * blockDim.x + col;
+            if (FILL) {
+                const int64_t pos = (dir ? colptrB[wo] : colptrF[wo]) - 1 + slot;
+                if (dir) { rowvalB[pos] = j + 1; nzvalB[pos] = c; } else { rowvalF[pos] = j + 1; nzvalF[pos] = c; }
+            }
+            if (MODE == 2 && slot < cap) {
+                if (dir) { slabB_j[wo * cap + slot] = (int)j; slabB_c[wo * cap + slot] = c; }
+                else { slabF_j[wo * cap + slot] = (int)j; slabF_c[wo * cap + slot] = c; }
+            }
+        }
+        __syncwarp();
+        if (acc && (mine >> lane) == 1u)  // the last accepted item of this (owner, direction) in the batch
+            s_cnt[dir][wid * 32 + owner] += __popc(mine);
+        __syncwarp();
+        head += (unsigned)n;
+    };
+
     for (int64_t t0 = 0; t0 < N; t0 += kLqTile) {
         const int cnt = (int)((N - t0 < kLqTile) ? (N - t0) : kLqTile);
         __syncthreads();
         for (int i = threadIdx.x; i < cnt * NS; i += blockDim.x) tile[i] = V[t0 * NS + i];
         __syncthreads();
-        if (!active) continue;
         for (int jj = 0; jj < cnt; ++jj) {
             const int64_t j = t0 + jj;
-            if (j == q) continue;  // nearneighbors.jl:171: allinds[i] != v
             double y[NS];
 #pragma unroll
             for (int i = 0; i < NS; ++i) y[i] = tile[jj * NS + i];
-            double c;
-            if (lq_pair<D>(L, x, y, r, &c)) {  // forwards: cost(V[q] -> V[j])
-                if (FILL) { rowvalF[posF] = j + 1; nzvalF[posF] = c; ++posF; }
-                if (MODE == 2 && nF < cap) { slabF_j[w * cap + nF] = (int)j; slabF_c[w * cap + nF] = c; }
-                ++nF;
-            }
-            if (lq_pair<D>(L, y, x, r, &c)) {  // backwards: cost(V[j] -> V[q])
-                if (FILL) { rowvalB[posB] = j + 1; nzvalB[posB] = c; ++posB; }
-                if (MODE == 2 && nB < cap) { slabB_j[w * cap + nB] = (int)j; slabB_c[w * cap + nB] = c; }
-                ++nB;
+            // stage 1: cands = cd .> 0 (linearquadratic.jl:213), both directions; j == q is dropped (nearneighbors.jl:171)
+            const bool live = active && j != q;
+            const bool pf = live && (lq_dcost(lq_abg<D>(L, x, y), r) > 0);
+            const bool pb = live && (lq_dcost(lq_abg<D>(L, y, x), r) > 0);
+            const unsigned mf = __ballot_sync(0xffffffffu, pf), mb = __ballot_sync(0xffffffffu, pb);
+            if (mf | mb) {
+                const unsigned lt = (1u << lane) - 1u;
+                if (pf) s_ring[wid][(tail + __popc(mf & lt)) % kRing] = ((unsigned)lane << 27) | (unsigned)j;
+                tail += __popc(mf);
+                if (pb) s_ring[wid][(tail + __popc(mb & lt)) % kRing] = ((unsigned)lane << 27) | (1u << 26) | (unsigned)j;
+                tail += __popc(mb);
+                __syncwarp();
+                while (tail - head >= 32u) process(32);
             }
         }
     }
-    if (!FILL && active) { countsF[w] = nF; countsB[w] = nB; }
+    if (tail != head) process((int)(tail - head));  // < 32 left
+    if (!FILL && active) { countsF[w] = s_cnt[0][threadIdx.x]; countsB[w] = s_cnt[1][threadIdx.x]; }
 }
 
 __global__ void __launch_bounds__(256)
@@ -452,6 +522,7 @@ static int lq_build(mpb200_samples *s, const mpb200_lq *lq, double r, mpb200_tab
 }
 
 int lq_inball_build(mpb200_samples *s, const mpb200_lq *lq, double r, mpb200_table *tF, mpb200_table *tB) {
+    if (s->N >= (int64_t(1) << 26)) return fail(MPB200_EARG, "all-pairs LQ tables support N < 2^26 samples");
     if (s->d != 2 * lq->d) return fail(MPB200_EARG, "sample dimension %d != 2 x %d", s->d, lq->d);
     if (lq->d == 1) return lq_build<1>(s, lq, r, tF, tB);
     if (lq->d == 2) return lq_build<2>(s, lq, r, tF, tB);
