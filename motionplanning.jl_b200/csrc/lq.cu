@@ -57,6 +57,40 @@ __device__ __forceinline__ Abg lq_abg(const LqDev &L, const double *x0, const do
     Abg k = {dmul(12.0, a), dmul(12.0, b), dmul(4.0, g)};
     return k;
 }
+// Both directions of one pair at once for the stage-1 prefilter: kF = lq_abg(x, y), kB = lq_abg(y, x), bit for
+// bit.  Swapping the roles negates dp = x1 - x0 exactly, so every product with it is negated exactly as well:
+// alpha (quadratic in dp) is unchanged and beta changes sign; sv = v0 + v1 is commutative.  Only gamma has a
+// different operation order in the two directions and is evaluated twice.
+template <int D>
+__device__ __forceinline__ void lq_abg_both(const LqDev &L, const double *x, const double *y, Abg *kF, Abg *kB) {
+    double dp[D], sv[D];
+    const double *vx = x + D, *vy = y + D;
+#pragma unroll
+    for (int i = 0; i < D; ++i) { dp[i] = dsub(y[i], x[i]); sv[i] = dadd(vx[i], vy[i]); }
+    double a = 0.0, b = 0.0, gF = 0.0, gB = 0.0;
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+        double Rdp, Rvx, Rvy;
+        if (L.scalar_R) {
+            Rdp = dmul(L.R[0], dp[i]); Rvx = dmul(L.R[0], vx[i]); Rvy = dmul(L.R[0], vy[i]);
+        } else {
+            Rdp = 0.0; Rvx = 0.0; Rvy = 0.0;
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                Rdp = dadd(Rdp, dmul(L.R[i * D + j], dp[j]));
+                Rvx = dadd(Rvx, dmul(L.R[i * D + j], vx[j]));
+                Rvy = dadd(Rvy, dmul(L.R[i * D + j], vy[j]));
+            }
+        }
+        a = dadd(a, dmul(dp[i], Rdp));
+        b = dadd(b, dmul(sv[i], Rdp));
+        gF = dadd(gF, dadd(dadd(dmul(vx[i], Rvx), dmul(vx[i], Rvy)), dmul(vy[i], Rvy)));  // v0 = vx, v1 = vy
+        gB = dadd(gB, dadd(dadd(dmul(vy[i], Rvy), dmul(vy[i], Rvx)), dmul(vx[i], Rvx)));  // v0 = vy, v1 = vx
+    }
+    const double alpha = dmul(12.0, a), beta = dmul(12.0, b);
+    kF->alpha = alpha; kF->beta = beta;  kF->gamma = dmul(4.0, gF);
+    kB->alpha = alpha; kB->beta = -beta; kB->gamma = dmul(4.0, gB);
+}
 __device__ __forceinline__ double lq_cost(const Abg &k, double t) {
     const double it = ddiv(1.0, t), it2 = dmul(it, it), it3 = dmul(it2, it);
     return dadd(t, dadd(dsub(dmul(k.alpha, it3), dmul(k.beta, it2)), dmul(k.gamma, it)));
@@ -239,8 +273,10 @@ lq_inball_kernel(const double *__restrict__ V, int64_t N, int64_t q0, int64_t nq
             for (int i = 0; i < NS; ++i) y[i] = tile[jj * NS + i];
             // stage 1: cands = cd .> 0 (linearquadratic.jl:213), both directions; j == q is dropped (nearneighbors.jl:171)
             const bool live = active && j != q;
-            const bool pf = live && (lq_dcost(lq_abg<D>(L, x, y), r) > 0);
-            const bool pb = live && (lq_dcost(lq_abg<D>(L, y, x), r) > 0);
+            Abg kF, kB;
+            lq_abg_both<D>(L, x, y, &kF, &kB);
+            const bool pf = live && (lq_dcost(kF, r) > 0);
+            const bool pb = live && (lq_dcost(kB, r) > 0);
             const unsigned mf = __ballot_sync(0xffffffffu, pf), mb = __ballot_sync(0xffffffffu, pb);
             if (mf | mb) {
                 const unsigned lt = (1u << lane) - 1u;
