@@ -88,3 +88,55 @@ def test_everything_colliding(gpu, orc):
         assert np.array_equal(unpack_bits(bits, D.nnz), exp.astype(bool)) and checks == cnt
         assert not exp.any()
         NN.close()
+
+
+def test_lq_degenerate_sample_sets(gpu, orc):
+    """ControlNN tables on 1 and 2 samples, duplicates included, and with a radius nothing reaches"""
+    mp = gpu
+    SS = mp.DoubleIntegrator(2)
+    L = orc.DoubleIntegratorLQ(2)
+    one = np.array([[0.2, 0.3, 0.1, -0.4]])
+    cases = [(one, 0.7), (np.vstack([one, one]), 0.7), (np.vstack([one, one + [0.05, 0.0, 0.0, 0.1]]), 0.7),
+             (np.vstack([one, one + [0.6, 0.6, 1.0, 1.0]]), 0.05)]
+    for V, r in cases:
+        NN = mp.QuasiMetricNN(V, SS.dist)
+        cF, cB = NN.precompute(r)
+        for cache, fwd in ((cF, True), (cB, False)):
+            ref = L.inball(V, r, fwd)
+            assert np.array_equal(cache.D.colptr, ref[0]) and np.array_equal(cache.D.rowval, ref[1])
+            assert cache.D.nzval.tobytes() == ref[2].tobytes()
+        NN.close()
+
+
+def test_lq_many_survivors_per_column_keep_row_order(gpu, orc):
+    """a tight cluster: almost every pair passes the candidate test, so the per-warp survivor ring is saturated
+    and batches mix many owners -- rows must still come out ascending and bit-identical to the oracle"""
+    mp = gpu
+    rng = np.random.Generator(np.random.PCG64(31))
+    V = np.hstack([0.5 + 0.02 * rng.random((600, 2)), 0.05 * (rng.random((600, 2)) - 0.5)])
+    V[5] = V[4]
+    SS = mp.DoubleIntegrator(2)
+    L = orc.DoubleIntegratorLQ(2)
+    NN = mp.QuasiMetricNN(V, SS.dist)
+    cF, cB = NN.precompute(0.6)
+    for cache, fwd in ((cF, True), (cB, False)):
+        ref = L.inball(V, 0.6, fwd)
+        assert np.array_equal(cache.D.colptr, ref[0]) and np.array_equal(cache.D.rowval, ref[1])
+        assert cache.D.nzval.tobytes() == ref[2].tobytes()
+        assert all(np.all(np.diff(cache.D.rowval[cache.D.colptr[c] - 1:cache.D.colptr[c + 1] - 1]) > 0) for c in range(600))
+    assert cF.D.nnz > 600 * 300
+    NN.close()
+
+
+def test_mc_zero_and_one_rollout(gpu, orc):
+    mp = gpu
+    Bx = mp.PointRobotNDBoxes([mp.BoxBounds(np.array([0.5, -10.0]), np.array([10.0, 10.0]))])
+    P = mp.MCProblem(np.eye(2)[None], (np.eye(2) * 0.1)[None], np.eye(2), np.array([[0.2, 0.0]] * 2), [0.3, 0.7],
+                     [[3.0, 0.0]])
+    r0 = mp.collision_probability(P, Bx, 0, seed=3)
+    assert r0["n"] == 0 and r0["hits"] == 0 and r0["S1"] == 0.0
+    r1 = mp.collision_probability(P, Bx, 1, seed=3, first=41)
+    whole = mp.collision_probability(P, Bx, 64, seed=3, per_rollout=True)
+    assert r1["n"] == 1
+    one = mp.collision_probability(P, Bx, 1, seed=3, first=41, per_rollout=True)
+    assert one["hit"][0] == whole["hit"][41] and one["w"][0] == whole["w"][41]
