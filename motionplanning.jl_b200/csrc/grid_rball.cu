@@ -278,7 +278,12 @@ __device__ __forceinline__ int query_spans(const GridDev &g, const double *p, co
 // lanes of a warp sit in 3-4 different cells, so every candidate load touches 3-4 lines.  Measured
 // alternatives that did NOT help: an FP32 grid-relative prefilter with exact FP64 recheck in a rounding
 // band (8-byte loads; count 96 -> 102 us, scatter +22 us for the extra array), staging the warp's union
-// spans in shared memory (60 registers, 100 us), unroll 1/2/8 (+-2 us).
+// spans in shared memory (60 registers, 100 us), unroll 1/2/8 (+-2 us), and a cell-centric form (r1q: the warp takes
+// one grid cell of its tile at a time, lanes hold the cell's candidates in registers, the cell's queries are
+// broadcast one after the other, hits compacted by ballot + popc into 64-byte rows per query): no per-test loads
+// and 32/32 lanes active, but the per-round bookkeeping (ballot, two popc, slot, byte store) doubles the warp
+// instructions (122M against 60M) and the kernel becomes issue-bound at 83% -- 142 us; the per-query row layout
+// also cost the fill 7% (its list reads were L1 hits shared by the 32 columns of a tile, now one cold line each).
 template <int D>
 __global__ void __launch_bounds__(kQThreads)
 rball_count(const double *__restrict__ sorted_pos, const int *__restrict__ sorted_idx,
