@@ -80,18 +80,27 @@ __global__ void __launch_bounds__(256) bbox_partial(const double *__restrict__ V
     }
 }
 __global__ void bbox_final(const double *__restrict__ part, int nb, int d, double *__restrict__ out) {
-    int i = threadIdx.x;
+    const int i = threadIdx.x >> 5, lane = threadIdx.x & 31;  // one warp per dimension
     if (i >= d) return;
     const double inf = __longlong_as_double(0x7ff0000000000000LL);
     double mn = inf, mx = -inf;
-    for (int b = 0; b < nb; ++b) { mn = fmin(mn, part[(size_t)b * 2 * d + i]); mx = fmax(mx, part[(size_t)b * 2 * d + d + i]); }
-    out[i] = mn; out[d + i] = mx;
+    for (int b = lane; b < nb; b += 32) { mn = fmin(mn, part[(size_t)b * 2 * d + i]); mx = fmax(mx, part[(size_t)b * 2 * d + d + i]); }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if (lane == 0) { out[i] = mn; out[d + i] = mx; }
 }
 
 // ---- K1: grid build ------------------------------------------------------------------
+// The histogram's atomicAdd already hands every sample its rank inside its cell: it is kept (packed with the
+// cell id would not fit 32 bits, so a second int array), and the scatter needs neither atomics nor a zeroed
+// cursor array.
 template <int D>
 __global__ void __launch_bounds__(256) cell_histogram(const double *__restrict__ V, int64_t N, GridDev g,
-                                                      int *__restrict__ hist, int *__restrict__ cell_id) {
+                                                      int *__restrict__ hist, int *__restrict__ cell_id,
+                                                      int *__restrict__ cell_rank) {
     int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= N) return;
     double p[D];
@@ -106,30 +115,23 @@ __global__ void __launch_bounds__(256) cell_histogram(const double *__restrict__
     cell_of<D>(g, p, c);
     int l = cell_linear<D>(g, c);
     cell_id[j] = l;
-    atomicAdd(&hist[l], 1);
+    cell_rank[j] = atomicAdd(&hist[l], 1);
 }
 template <int D>
 __global__ void __launch_bounds__(256) cell_scatter(const double *__restrict__ V, int64_t N,
-                                                    const int *__restrict__ cell_id,
-                                                    const int *__restrict__ cell_start, int *__restrict__ cursor,
+                                                    const int *__restrict__ cell_id, const int *__restrict__ cell_rank,
+                                                    const int *__restrict__ cell_start,
                                                     int *__restrict__ sorted_idx, double *__restrict__ sorted_pos) {
     int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= N) return;
     int l = cell_id[j];
     if (l < 0) return;
-    int pos = cell_start[l] + atomicAdd(&cursor[l], 1);
+    int pos = cell_start[l] + cell_rank[j];
     sorted_idx[pos] = (int)j;
 #pragma unroll
     for (int i = 0; i < D; ++i) sorted_pos[(size_t)pos * D + i] = V[j * D + i];
 }
 
-// Shard form of the grid build (query range != all samples).  The samples are replicated, but only those
-// inside the shard's box (own bounding box grown by r) can matter: the histogram pass is the ONLY pass
-// over all N samples; it appends the in-range ones to a compact list (warp-aggregated atomics), and the
-// scatter runs over that list.  q_order -- the cell-order positions of the shard's own query samples -- is
-// then collected by a pass over the gridded positions that appends 256 consecutive positions at a time
-// (one atomic per block): the list is not globally sorted, but every run of it is cell-coherent, which is
-// all the thread-per-query kernels need, and no N-sized flag / scan / compaction pass is left.
 // Append slots for the threads of a 256-thread block whose `flag` is set: ONE atomicAdd on the list counter per block
 // (same-address atomics serialise in L2; per-warp aggregation was measured at ~30 us per million items).  Returns
 // the thread's slot (valid when flag).  All threads of the block must call it.
@@ -153,7 +155,8 @@ __device__ __forceinline__ int block_append_slot(bool flag, int *__restrict__ co
 template <int D>
 __global__ void __launch_bounds__(256) cell_histogram_shard(const double *__restrict__ V, int64_t N, GridDev g,
                                                             int *__restrict__ hist, int *__restrict__ in_j,
-                                                            int *__restrict__ in_l, int *__restrict__ n_in) {
+                                                            int *__restrict__ in_l, int *__restrict__ in_r,
+                                                            int *__restrict__ n_in) {
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool inside = j < N;
     double p[D];
@@ -164,28 +167,29 @@ __global__ void __launch_bounds__(256) cell_histogram_shard(const double *__rest
             inside = inside && (p[i] >= g.in_lo[i] && p[i] <= g.in_hi[i]);
         }
     }
-    int l = -1;
+    int l = -1, rank = 0;
     if (inside) {
         int c[D];
         cell_of<D>(g, p, c);
         l = cell_linear<D>(g, c);
-        atomicAdd(&hist[l], 1);
+        rank = atomicAdd(&hist[l], 1);  // the sample's rank inside its cell: the scatter needs no atomics
     }
     const int slot = block_append_slot(inside, n_in);
     if (inside) {
         in_j[slot] = (int)j;
         in_l[slot] = l;
+        in_r[slot] = rank;
     }
 }
 template <int D>
 __global__ void __launch_bounds__(256) cell_scatter_shard(const double *__restrict__ V, const int *__restrict__ n_in,
                                                           const int *__restrict__ in_j, const int *__restrict__ in_l,
-                                                          const int *__restrict__ cell_start, int *__restrict__ cursor,
+                                                          const int *__restrict__ in_r, const int *__restrict__ cell_start,
                                                           int *__restrict__ sorted_idx, double *__restrict__ sorted_pos) {
     const int n = *n_in;  // grid-stride: the grid is sized for the SMs, not for the (device-side) list length
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const int j = in_j[i], l = in_l[i];
-        const int pos = cell_start[l] + atomicAdd(&cursor[l], 1);
+        const int j = in_j[i];
+        const int pos = cell_start[in_l[i]] + in_r[i];
         sorted_idx[pos] = j;
 #pragma unroll
         for (int k = 0; k < D; ++k) sorted_pos[(size_t)pos * D + k] = V[(size_t)j * D + k];
@@ -667,11 +671,11 @@ static int build_table(mpb200_samples *s, double r, mpb200_table *t) {
     // ---- reserve every buffer of the front half up front (nothing may allocate during graph capture)
     if (int rc = s->cell_start.reserve(sizeof(int) * (size_t)(ncells + 1))) return rc;
     if (int rc = s->cell_fill.reserve(sizeof(int) * (size_t)(ncells + 1))) return rc;
-    if (int rc = s->sorted_idx.reserve(sizeof(int) * (size_t)(2 * N + 2))) return rc;  // + cell_id scratch
+    if (int rc = s->sorted_idx.reserve(sizeof(int) * (size_t)(3 * N + 3))) return rc;  // + cell_id, cell_rank scratch
     if (int rc = s->sorted_pos.reserve(sizeof(double) * (size_t)(D * N + 1))) return rc;
     if (int rc = s->scan_tmp.reserve(sizeof(int64_t) * (size_t)(ceil_div(ncells > N ? ncells : N, kScanTile) + 2))) return rc;
-    if (nq != N)  // shard: q_order | compact in-range list (sample, cell)
-        if (int rc = s->q_order.reserve(sizeof(int) * (size_t)(3 * N + 4))) return rc;
+    if (nq != N)  // shard: q_order | compact in-range list (sample, cell, rank in cell)
+        if (int rc = s->q_order.reserve(sizeof(int) * (size_t)(4 * N + 5))) return rc;
     if (int rc = t->counts.reserve(sizeof(int) * (size_t)(2 * nq + 2))) return rc;
     if (int rc = t->colptr.reserve(sizeof(int64_t) * (size_t)(nq + 1))) return rc;
     if (int rc = t->masks.reserve((size_t)kListCap * 32 * (size_t)(ceil_div(nq, 32) + 1))) return rc;
@@ -682,7 +686,7 @@ static int build_table(mpb200_samples *s, double r, mpb200_table *t) {
     int *hist = s->cell_fill.as<int>();
     int *cell_start = s->cell_start.as<int>();
     int *sorted_idx = s->sorted_idx.as<int>();
-    int *cell_id = sorted_idx + N;
+    int *cell_id = sorted_idx + N, *cell_rank = cell_id + N;
     double *sorted_pos = s->sorted_pos.as<double>();
     uint32_t *hit_lists = t->masks.as<uint32_t>();
     int *counts = t->counts.as<int>();
@@ -699,27 +703,25 @@ static int build_table(mpb200_samples *s, double r, mpb200_table *t) {
     auto front = [&]() -> int {
         if (nq != N) {  // shard: one pass over all N samples, everything else over the in-range ones
             int *qo = s->q_order.as<int>();
-            int *in_j = qo + N + 1, *in_l = in_j + N + 1;
+            int *in_j = qo + N + 1, *in_l = in_j + N + 1, *in_r = in_l + N + 1;
             int *n_in = reinterpret_cast<int *>(c.d_scalar + 6);  // length of the compact list
             int *n_q = reinterpret_cast<int *>(c.d_scalar + 7);   // queries collected (== nq)
             const unsigned nbS = (unsigned)std::min<int64_t>(nbN, (int64_t)c.sm_count * 8);
             MPB_CUDA(cudaMemsetAsync(hist, 0, sizeof(int) * (size_t)(ncells + 1), st));
             MPB_CUDA(cudaMemsetAsync(n_in, 0, sizeof(int64_t) * 2, st));
-            cell_histogram_shard<D><<<nbN, 256, 0, st>>>(V, N, g, hist, in_j, in_l, n_in);
+            cell_histogram_shard<D><<<nbN, 256, 0, st>>>(V, N, g, hist, in_j, in_l, in_r, n_in);
             MPB_LAUNCHED();
             if (int rc = exclusive_scan<int, int>(hist, ncells, cell_start, 0, s->scan_tmp, nullptr)) return rc;
-            MPB_CUDA(cudaMemsetAsync(hist, 0, sizeof(int) * (size_t)(ncells + 1), st));
-            cell_scatter_shard<D><<<nbS, 256, 0, st>>>(V, n_in, in_j, in_l, cell_start, hist, sorted_idx, sorted_pos);
+            cell_scatter_shard<D><<<nbS, 256, 0, st>>>(V, n_in, in_j, in_l, in_r, cell_start, sorted_idx, sorted_pos);
             MPB_LAUNCHED();
             collect_queries<<<nbS, 256, 0, st>>>(sorted_idx, n_in, s->q0, s->q1, qo, n_q);
             MPB_LAUNCHED();
         } else {
             MPB_CUDA(cudaMemsetAsync(hist, 0, sizeof(int) * (size_t)(ncells + 1), st));
-            cell_histogram<D><<<nbN, 256, 0, st>>>(V, N, g, hist, cell_id);
+            cell_histogram<D><<<nbN, 256, 0, st>>>(V, N, g, hist, cell_id, cell_rank);
             MPB_LAUNCHED();
             if (int rc = exclusive_scan<int, int>(hist, ncells, cell_start, 0, s->scan_tmp, nullptr)) return rc;
-            MPB_CUDA(cudaMemsetAsync(hist, 0, sizeof(int) * (size_t)(ncells + 1), st));
-            cell_scatter<D><<<nbN, 256, 0, st>>>(V, N, cell_id, cell_start, hist, sorted_idx, sorted_pos);
+            cell_scatter<D><<<nbN, 256, 0, st>>>(V, N, cell_id, cell_rank, cell_start, sorted_idx, sorted_pos);
             MPB_LAUNCHED();
         }
         MPB_CUDA(cudaMemsetAsync(c.d_scalar, 0, sizeof(int64_t) * 2, st));
@@ -849,7 +851,7 @@ int compute_bbox(mpb200_samples *s, int64_t j0, int64_t j1) {
     double *part = out + 2 * s->d;
     bbox_partial<<<nb, 256, 0, c.stream>>>(s->V.as<double>() + j0 * s->d, j1 - j0, s->d, part);
     MPB_LAUNCHED();
-    bbox_final<<<1, 32, 0, c.stream>>>(part, nb, s->d, out);
+    bbox_final<<<1, 32 * s->d, 0, c.stream>>>(part, nb, s->d, out);
     MPB_LAUNCHED();
     return 0;
 }
