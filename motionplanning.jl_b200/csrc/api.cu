@@ -163,6 +163,7 @@ static void phases_resolve(int b) {
 
 // implemented in the kernel translation units
 int compute_bbox(mpb200_samples *s, int64_t j0, int64_t j1);
+int check_sorted_x(mpb200_samples *s, int *d_flag);
 int grid_inball_build(mpb200_samples *s, double r, mpb200_table *t);
 int brute_inball_build(mpb200_samples *s, double r, mpb200_table *t);
 
@@ -304,8 +305,15 @@ int mpb200_samples_create(const double *V_aos, int64_t N, int d, mpb200_samples 
         rc = compute_bbox(s, 0, N);
         if (rc) { mpb200_samples_destroy(s); return rc; }
         MPB_CUDA(cudaMemcpyAsync(s->h_bbox, s->minmax.p, sizeof(double) * 2 * d, cudaMemcpyDeviceToHost, st));
+        // samples ordered along x (e.g. stored in stripe order for sharding)?  Then a shard's grid build only
+        // has to look at its own stripe of the array.
+        Context &c = ctx();
+        rc = check_sorted_x(s, reinterpret_cast<int *>(c.d_scalar + 8));
+        if (rc) { mpb200_samples_destroy(s); return rc; }
+        MPB_CUDA(cudaMemcpyAsync(c.h_scalar + 8, c.d_scalar + 8, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     }
     MPB_CUDA(cudaStreamSynchronize(st));
+    if (N > 0) s->sorted_x = *reinterpret_cast<int *>(ctx().h_scalar + 8) == 0;
     memcpy(s->h_qbbox, s->h_bbox, sizeof(s->h_bbox));
     *out = s;
     return MPB200_OK;

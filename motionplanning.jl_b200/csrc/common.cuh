@@ -117,6 +117,7 @@ struct mpb200_samples {
     mpb::DevBuf sorted_pos;  // f64 d x N positions in cell order (AoS)
     mpb::DevBuf pt_order;    // int32 (q1-q0): the shard's samples (relative to q0) in grid-cell order, from the last grid build
     bool pt_order_valid = false;
+    bool sorted_x = false;   // samples are non-decreasing along the first coordinate (checked once at create)
     mpb::DevBuf minmax;      // f64 2*d bounding box
     double h_bbox[32] = {};  // host copy of the bounding box (mins then maxs), read once at create
     double h_qbbox[32] = {}; // bounding box of the query range's samples (== h_bbox for the full range)
