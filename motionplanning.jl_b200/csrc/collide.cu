@@ -4,8 +4,11 @@
 // Replaces the per-call loops of the reference: F[i] = is_free_state(V[i], CC, SS)
 // (fmt.jl:31-36, sampling.jl:25) and the lazy is_free_motion(V[y], V[x], CC, SS) of fmt.jl:75,
 // batched over every stored entry of a neighbour table.  One lane per point / edge, the
-// obstacle table staged once per CTA into shared memory, results packed by warp ballot into
-// Julia BitVector words (bit k&63 of word k>>6 == bit k&31 of 32-bit word k>>5, little endian).
+// obstacle table staged once per CTA into shared memory, results packed into Julia BitVector words
+// (bit k&63 of word k>>6 == bit k&31 of 32-bit word k>>5, little endian).  After a grid build the
+// points and the columns are visited in grid-cell order (the lanes of a warp then agree on which
+// obstacles they are near); classify_columns settles whole columns whose r-box is clear of every
+// obstacle (or inside one convex polygon) and only the rest reach the per-edge kernel.
 #include "common.cuh"
 #include "predicates.cuh"
 #include <climits>

@@ -7,10 +7,14 @@
 //
 // Data layout in HBM: samples stay AoS (d x N column-major, exactly the reference's
 // Vector{SVector{d,Float64}}); the grid adds a cell-ordered AoS copy + the permutation, so a
-// 3-cell x-run of candidates is one contiguous, coalesced span.  One warp per query; three
-// (d=2) or nine (d=3) x-runs per query; hits are compacted with warp ballots into a
-// per-warp shared-memory stage, rank-sorted by sample index there, and written as one
-// contiguous Int64/Float64 burst per column.
+// 3-cell x-run of candidates is one contiguous span; three (d=2) or nine (d=3) x-runs per query.
+// Pipeline of one build (the first five steps are one CUDA graph):
+//   cell_histogram (each sample's cell + its rank in the cell) -> scan -> cell_scatter (no atomics)
+//   [shard form: one pass over the samples that can be in range, compact list, query collection]
+//   -> rball_count (thread per query in cell order; FP64 test; one byte per hit) -> colptr scan
+//   -> nnz read-back (event) overlapped with rball_fill (per column: hit bytes -> index + point ->
+//      distance -> register bitonic sort by index -> contiguous Int64/Float64 burst)
+//   -> rball_fill_big / sort_big_columns for the rare columns beyond 64 entries or 255 candidates.
 #include "common.cuh"
 #include "predicates.cuh"
 #include "scan.cuh"
