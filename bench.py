@@ -84,7 +84,7 @@ class ClockSampler:
         except Exception:
             self.nv = None
 
-    def _loop(self):
+    def _sample(self):
         nv = self.nv
         names = {
             "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
@@ -92,15 +92,18 @@ class ClockSampler:
             "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
             "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
         }
+        try:
+            self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+            mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            for k, bit in names.items():
+                if mask & bit:
+                    self.reasons.add(k)
+        except Exception:
+            pass
+
+    def _loop(self):
         while not self._stop.is_set():
-            try:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for k, bit in names.items():
-                    if mask & bit:
-                        self.reasons.add(k)
-            except Exception:
-                pass
+            self._sample()
             time.sleep(0.002)
 
     def start(self):
@@ -304,6 +307,8 @@ def main():
             phases[:5] += [lib.mpb200_last_ms_of(_lib.OP_TABLE, k) for k in range(5)]
             point_ms.append(lib.mpb200_last_ms_of(_lib.OP_POINTS, 1))
             edge_ms.append(lib.mpb200_last_ms_of(_lib.OP_EDGES, 1))
+            if sampler.nv and (it - args.warmup) % 8 == 0:
+                sampler._sample()   # also from this thread, between steps (outside the event pairs): the region is short
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
