@@ -56,6 +56,27 @@ __device__ __forceinline__ int cell_linear(const GridDev &g, const int *c) {
     return l;
 }
 
+// one sample of an AoS array: a single 16-byte access for d = 2 (the arrays are 16-byte aligned)
+template <int D>
+__device__ __forceinline__ void load_point(const double *__restrict__ A, int64_t j, double *p) {
+    if (D == 2) {
+        const double2 v = reinterpret_cast<const double2 *>(A)[j];
+        p[0] = v.x; p[D - 1] = v.y;
+    } else {
+#pragma unroll
+        for (int i = 0; i < D; ++i) p[i] = A[j * D + i];
+    }
+}
+template <int D>
+__device__ __forceinline__ void store_point(double *__restrict__ A, int64_t j, const double *p) {
+    if (D == 2) {
+        reinterpret_cast<double2 *>(A)[j] = make_double2(p[0], p[D - 1]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < D; ++i) A[j * D + i] = p[i];
+    }
+}
+
 // ---- bounding box ------------------------------------------------------------------
 __global__ void __launch_bounds__(256) bbox_partial(const double *__restrict__ V, int64_t N, int d,
                                                     double *__restrict__ part /*grid x 2d*/) {
@@ -109,11 +130,9 @@ __global__ void __launch_bounds__(256) cell_histogram(const double *__restrict__
     if (j >= N) return;
     double p[D];
     bool inside = true;
+    load_point<D>(V, j, p);
 #pragma unroll
-    for (int i = 0; i < D; ++i) {
-        p[i] = V[j * D + i];
-        inside = inside && (p[i] >= g.in_lo[i] && p[i] <= g.in_hi[i]);
-    }
+    for (int i = 0; i < D; ++i) inside = inside && (p[i] >= g.in_lo[i] && p[i] <= g.in_hi[i]);
     if (!inside) { cell_id[j] = -1; return; }  // cannot be within r of any query of this shard
     int c[D];
     cell_of<D>(g, p, c);
@@ -132,8 +151,9 @@ __global__ void __launch_bounds__(256) cell_scatter(const double *__restrict__ V
     if (l < 0) return;
     int pos = cell_start[l] + cell_rank[j];
     sorted_idx[pos] = (int)j;
-#pragma unroll
-    for (int i = 0; i < D; ++i) sorted_pos[(size_t)pos * D + i] = V[j * D + i];
+    double p[D];
+    load_point<D>(V, j, p);
+    store_point<D>(sorted_pos, pos, p);
 }
 
 // number of adjacent pairs out of order along the first coordinate (0 <=> sorted)
@@ -234,8 +254,9 @@ __global__ void __launch_bounds__(256) cell_scatter_shard(const double *__restri
         const int j = in_j[i];
         const int pos = cell_start[in_l[i]] + in_r[i];
         sorted_idx[pos] = j;
-#pragma unroll
-        for (int k = 0; k < D; ++k) sorted_pos[(size_t)pos * D + k] = V[(size_t)j * D + k];
+        double p[D];
+        load_point<D>(V, j, p);
+        store_point<D>(sorted_pos, pos, p);
     }
 }
 __global__ void __launch_bounds__(256) collect_queries(const int *__restrict__ sorted_idx, const int *__restrict__ n_in,
