@@ -169,6 +169,16 @@ int mpb200_states_free(const double *v_aos, int64_t n, int d, const mpb200_obsta
 int mpb200_segments_free(const double *v_aos, const double *w_aos, int64_t n, int d, const mpb200_obstacles *o,
                          const mpb200_space_desc *ss, uint8_t *out);
 
+/* Batched sample_free!(P, N) (sampling.jl:23-37): draws states uniformly in the state bounds
+ * (sample_space, statespaces.jl) and keeps the first N for which is_free_state(v, CC, SS) holds -- generated,
+ * tested and compacted on the device, so the sample set never crosses PCIe on its way in.  The reference draws
+ * from Julia's global RNG, which cannot be reproduced; the candidate stream here is specified in
+ * oracle/sample.c (Philox4x32-10 keyed by seed, counter = candidate number) and is independent of launch
+ * geometry: the same (obstacles, space, N, seed) always yields the same samples, in candidate order.
+ * V_host (N x n, may be NULL) receives a host copy; *candidates the number of candidates consumed. */
+int mpb200_sample_free(const mpb200_obstacles *o, const mpb200_space_desc *ss, int64_t N, uint64_t seed,
+                       mpb200_samples **out, double *V_host, int64_t *candidates);
+
 /* ---- linear-quadratic steering cost ("ControlNN") --------------------------------
  * Replaces LinearQuadratic(A, B, c, R) / LinearQuadratic2BVP (linearquadratic.jl:6-39,126-157).
  * A (n x n), B (n x m), R (m x m) column-major, c (n).  The reference's expAt handles nilpotent

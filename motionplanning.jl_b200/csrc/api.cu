@@ -164,6 +164,8 @@ static void phases_resolve(int b) {
 // implemented in the kernel translation units
 int compute_bbox(mpb200_samples *s, int64_t j0, int64_t j1);
 int check_sorted_x(mpb200_samples *s, int *d_flag);
+int sample_free_device(const mpb200_obstacles *o, const mpb200_space_desc *ss, int64_t n_want, uint64_t seed,
+                       double *dV, DevBuf &scratch, DevBuf &tmp, int64_t *h_used);
 int grid_inball_build(mpb200_samples *s, double r, mpb200_table *t);
 int brute_inball_build(mpb200_samples *s, double r, mpb200_table *t);
 
@@ -284,6 +286,24 @@ double mpb200_last_ms_of(int op, int phase) {
 double mpb200_last_ms(int phase) { return mpb200_last_ms_of(ctx().bank, phase); }
 
 // ---- samples -----------------------------------------------------------------------
+// bounding box + x-sortedness of a sample set whose V is already on the device; leaves the stream idle
+static int finish_samples(mpb200_samples *s) {
+    Context &c = ctx();
+    cudaStream_t st = c.stream;
+    const int d = s->d;
+    if (s->N > 0) {
+        if (int rc = compute_bbox(s, 0, s->N)) return rc;
+        MPB_CUDA(cudaMemcpyAsync(s->h_bbox, s->minmax.p, sizeof(double) * 2 * d, cudaMemcpyDeviceToHost, st));
+        // samples ordered along x (e.g. stored in stripe order for sharding)?  Then a shard's grid build only
+        // has to look at its own stripe of the array.
+        if (int rc = check_sorted_x(s, reinterpret_cast<int *>(c.d_scalar + 8))) return rc;
+        MPB_CUDA(cudaMemcpyAsync(c.h_scalar + 8, c.d_scalar + 8, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    }
+    MPB_CUDA(cudaStreamSynchronize(st));
+    if (s->N > 0) s->sorted_x = *reinterpret_cast<int *>(c.h_scalar + 8) == 0;
+    memcpy(s->h_qbbox, s->h_bbox, sizeof(s->h_bbox));
+    return MPB200_OK;
+}
 int mpb200_samples_create(const double *V_aos, int64_t N, int d, mpb200_samples **out) {
     MPB_REQUIRE_INIT();
     MPB_CHECK_ARG(out != nullptr, "out is NULL");
@@ -298,23 +318,39 @@ int mpb200_samples_create(const double *V_aos, int64_t N, int d, mpb200_samples 
     s->q1 = N;
     int rc = s->V.reserve(sizeof(double) * (size_t)(N * d + 1));
     if (rc) { delete s; return rc; }
-    cudaStream_t st = ctx().stream;
     if (N > 0) {
-        cudaError_t e = cudaMemcpyAsync(s->V.p, V_aos, sizeof(double) * (size_t)(N * d), cudaMemcpyHostToDevice, st);
+        cudaError_t e = cudaMemcpyAsync(s->V.p, V_aos, sizeof(double) * (size_t)(N * d), cudaMemcpyHostToDevice, ctx().stream);
         if (e != cudaSuccess) { s->V.release(); delete s; return fail(MPB200_ECUDA, "H2D copy failed: %s", cudaGetErrorString(e)); }
-        rc = compute_bbox(s, 0, N);
-        if (rc) { mpb200_samples_destroy(s); return rc; }
-        MPB_CUDA(cudaMemcpyAsync(s->h_bbox, s->minmax.p, sizeof(double) * 2 * d, cudaMemcpyDeviceToHost, st));
-        // samples ordered along x (e.g. stored in stripe order for sharding)?  Then a shard's grid build only
-        // has to look at its own stripe of the array.
-        Context &c = ctx();
-        rc = check_sorted_x(s, reinterpret_cast<int *>(c.d_scalar + 8));
-        if (rc) { mpb200_samples_destroy(s); return rc; }
-        MPB_CUDA(cudaMemcpyAsync(c.h_scalar + 8, c.d_scalar + 8, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     }
-    MPB_CUDA(cudaStreamSynchronize(st));
-    if (N > 0) s->sorted_x = *reinterpret_cast<int *>(ctx().h_scalar + 8) == 0;
-    memcpy(s->h_qbbox, s->h_bbox, sizeof(s->h_bbox));
+    rc = finish_samples(s);
+    if (rc) { mpb200_samples_destroy(s); return rc; }
+    *out = s;
+    return MPB200_OK;
+}
+int mpb200_sample_free(const mpb200_obstacles *o, const mpb200_space_desc *ss, int64_t N, uint64_t seed,
+                       mpb200_samples **out, double *V_host, int64_t *candidates) {
+    MPB_REQUIRE_INIT();
+    MPB_CHECK_ARG(o != nullptr && ss != nullptr && out != nullptr, "NULL argument");
+    MPB_CHECK_ARG(N >= 0 && N < INT_MAX, "N out of range");
+    MPB_CHECK_ARG(ss->n >= 1 && ss->n <= kMaxDim, "state dimension out of range (1..16)");
+    mpb200_samples *s = new (std::nothrow) mpb200_samples();
+    if (!s) return fail(MPB200_ENOMEM, "out of host memory");
+    s->N = N;
+    s->d = ss->n;
+    s->q0 = 0;
+    s->q1 = N;
+    int rc = s->V.reserve(sizeof(double) * (size_t)(N * s->d + 1));
+    int64_t used = 0;
+    if (!rc && N > 0) rc = sample_free_device(o, ss, N, seed, s->V.as<double>(), s->q_order, s->scan_tmp, &used);
+    if (!rc) rc = finish_samples(s);
+    if (!rc && V_host && N > 0) {
+        cudaStream_t st = ctx().stream;
+        cudaError_t e = cudaMemcpyAsync(V_host, s->V.p, sizeof(double) * (size_t)(N * s->d), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) rc = fail(MPB200_ECUDA, "D2H copy failed: %s", cudaGetErrorString(e));
+    }
+    if (rc) { mpb200_samples_destroy(s); return rc; }
+    if (candidates) *candidates = used;
     *out = s;
     return MPB200_OK;
 }

@@ -11,6 +11,8 @@
 // obstacle (or inside one convex polygon) and only the rest reach the per-edge kernel.
 #include "common.cuh"
 #include "predicates.cuh"
+#include "philox.cuh"
+#include "scan.cuh"
 #include <climits>
 #include <cstdlib>
 
@@ -297,6 +299,54 @@ segments_free_kernel(const double *__restrict__ A, const double *__restrict__ B,
 // ---- host dispatch --------------------------------------------------------------------
 constexpr size_t kSmemTableMax = 160 * 1024;
 
+// ---- batched free-state sampling (sample_free!, sampling.jl:23-37) ---------------------------
+// Candidate c of the stream (oracle/sample.c): coordinate i = lo_i + u (hi_i - lo_i) with u the 53-bit uniform
+// from Philox4x32-10(counter = (c lo, c hi, i / 2, 'SAMP'), key = seed); kept iff is_free_state.
+template <int N>
+__device__ __forceinline__ void sample_candidate(const SpaceDev &S, uint32_t k0, uint32_t k1, int64_t c, double *x) {
+    const Philox ph{k0, k1};
+#pragma unroll
+    for (int b = 0; 2 * b < N; ++b) {
+        uint32_t rnd[4];
+        ph((uint32_t)c, (uint32_t)((uint64_t)c >> 32), (uint32_t)b, 0x53414D50u, rnd);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int i = 2 * b + h;
+            if (i < N) x[i] = dadd(S.lo[i], dmul(u53(rnd[2 * h], rnd[2 * h + 1]), dsub(S.hi[i], S.lo[i])));
+        }
+    }
+}
+template <int N, int DW, int KIND>
+__global__ void __launch_bounds__(kThreads)
+sample_flags_kernel(SpaceDev S, const double *__restrict__ g_table, int table_words, int M, bool use_smem,
+                    uint32_t k0, uint32_t k1, int64_t c0, int64_t C, int *__restrict__ flags) {
+    extern __shared__ double s_table[];
+    const double *T = stage_table(g_table, table_words, use_smem, s_table);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < C; i += (int64_t)gridDim.x * blockDim.x) {
+        double x[N];
+        sample_candidate<N>(S, k0, k1, c0 + i, x);
+        flags[i] = state_free<N, DW, KIND>(S, T, M, x) ? 1 : 0;
+    }
+}
+// free candidate i of the chunk becomes sample base + offs[i] (candidate order is kept); the candidate is regenerated
+// instead of being stored; the thread that writes sample n_want - 1 reports how many candidates that took
+template <int N>
+__global__ void __launch_bounds__(kThreads)
+sample_scatter_kernel(SpaceDev S, uint32_t k0, uint32_t k1, int64_t c0, int64_t C, const int *__restrict__ flags,
+                      const int *__restrict__ offs, int64_t base, int64_t n_want, double *__restrict__ V,
+                      long long *__restrict__ used) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < C; i += (int64_t)gridDim.x * blockDim.x) {
+        if (!flags[i]) continue;
+        const int64_t pos = base + offs[i];
+        if (pos >= n_want) continue;
+        double x[N];
+        sample_candidate<N>(S, k0, k1, c0 + i, x);
+#pragma unroll
+        for (int k = 0; k < N; ++k) V[pos * N + k] = x[k];
+        if (pos == n_want - 1) *used = c0 + i + 1;
+    }
+}
+
 struct LaunchCfg {
     const double *table;
     int words, M;
@@ -495,6 +545,61 @@ int segments_free_device(const double *dA, const double *dB, int64_t n, int d, c
     MPB_DISPATCH_DIMS(S.n, dw, o->kind, CALL);
 #undef CALL
     MPB_LAUNCHED();
+    return 0;
+}
+
+// Fill dV (n_want x n states, AoS) with the first n_want free candidates of the stream; *h_used = candidates consumed.
+// `scratch` holds two int arrays of the chunk size, `tmp` the scan sums.
+int sample_free_device(const mpb200_obstacles *o, const mpb200_space_desc *ss, int64_t n_want, uint64_t seed,
+                       double *dV, DevBuf &scratch, DevBuf &tmp, int64_t *h_used) {
+    SpaceDev S;
+    int dw;
+    if (int rc = make_space(ss, ss ? ss->n : 0, &S, &dw)) return rc;
+    if (int rc = check_obstacles(o, dw)) return rc;
+    Context &c = ctx();
+    cudaStream_t st = c.stream;
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    int *d_total = reinterpret_cast<int *>(c.d_scalar + 12);  // free states in the chunk (upper half kept zero)
+    long long *d_used = reinterpret_cast<long long *>(c.d_scalar + 13);
+    MPB_CUDA(cudaMemsetAsync(d_used, 0, sizeof(long long), st));
+    int64_t got = 0, c0 = 0, cands = 0, frees = 0;
+    int empty_chunks = 0;
+    *h_used = 0;
+    while (got < n_want) {
+        // chunk sized from the acceptance rate seen so far (first chunk: assume everything is free)
+        const double p_hat = cands > 0 ? fmax((double)frees / (double)cands, 1e-3) : 1.0;
+        int64_t C = (int64_t)((double)(n_want - got) * 1.1 / p_hat) + 4096;
+        if (C > (int64_t(1) << 24)) C = int64_t(1) << 24;
+        if (int rc = scratch.reserve(sizeof(int) * (size_t)(2 * C + 2))) return rc;
+        if (int rc = tmp.reserve(sizeof(int64_t) * (size_t)(ceil_div(C, kScanTile) + 2))) return rc;
+        int *flags = scratch.as<int>(), *offs = flags + C + 1;
+        LaunchCfg L = make_cfg(o, C);
+        MPB_CUDA(cudaMemsetAsync(d_total, 0, sizeof(int64_t), st));
+#define CALLS(N_, DW_, K_)                                                                                     \
+        do {                                                                                                       \
+            if (int rc = prep_kernel(sample_flags_kernel<N_, DW_, K_>, L.smem)) return rc;                         \
+            sample_flags_kernel<N_, DW_, K_><<<L.grid, kThreads, L.smem, st>>>(S, L.table, L.words, L.M, L.use_smem, \
+                                                                               k0, k1, c0, C, flags);             \
+            MPB_LAUNCHED();                                                                                        \
+            if (int rc = exclusive_scan<int, int>(flags, C, offs, 0, tmp, d_total)) return rc;                     \
+            sample_scatter_kernel<N_><<<L.grid, kThreads, 0, st>>>(S, k0, k1, c0, C, flags, offs, got, n_want, dV, \
+                                                                   d_used);                                        \
+        } while (0)
+        MPB_DISPATCH_DIMS(S.n, dw, o->kind, CALLS);
+#undef CALLS
+        MPB_LAUNCHED();
+        MPB_CUDA(cudaMemcpyAsync(c.h_scalar + 12, c.d_scalar + 12, sizeof(int64_t) * 2, cudaMemcpyDeviceToHost, st));
+        MPB_CUDA(cudaStreamSynchronize(st));
+        const int64_t total = c.h_scalar[12];
+        got += total;
+        frees += total;
+        cands += C;
+        c0 += C;
+        empty_chunks = total ? 0 : empty_chunks + 1;
+        if (empty_chunks >= 8)
+            return fail(MPB200_EARG, "no free state among %lld candidates: the free space is empty", (long long)cands);
+    }
+    *h_used = c.h_scalar[13];
     return 0;
 }
 

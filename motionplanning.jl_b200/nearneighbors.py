@@ -125,6 +125,24 @@ class SampleSet:
                 _lib.check(lib.mpb200_samples_set_query_range(h, self.q0, self.q1))
         return self._handle
 
+    @classmethod
+    def sample_free(cls, CC, SS, N, seed=0, init=None, **kw):
+        """Sample set of N free states generated, tested and compacted on the device (mpb200_sample_free; the
+        bulk of sample_free!, sampling.jl:23-37): the samples never cross PCIe on their way in, the host copy
+        `V` is fetched once for the planner.  `candidates` = states drawn to find them.  Deterministic in
+        (CC, SS, N, seed); the candidate stream is specified in oracle/sample.c."""
+        N = int(N)
+        V = np.empty((N, SS.dim), dtype=np.float64)
+        d = SS.desc()
+        h = _lib.c_vp()
+        used = _lib.c_i64(0)
+        _lib.check(_lib.lib().mpb200_sample_free(CC.handle(), ctypes.byref(d), N, int(seed) & (2**64 - 1), ctypes.byref(h),
+                                                 _lib.ptr(V), ctypes.byref(used)))
+        obj = cls(V, init=(init if init is not None else (V[0] if N else np.zeros(SS.dim))), **kw)
+        obj._handle = h
+        obj.candidates = used.value
+        return obj
+
     def set_query_range(self, q0, q1):
         """Multi-GPU shard: this process owns query columns [q0, q1) (0-based)."""
         self.q0, self.q1 = int(q0), int(q1)

@@ -67,6 +67,9 @@ def lib():
         L.orc_kdtree_free.argtypes = [c_vp]
         L.orc_rball_kdtree.argtypes = [c_vp, c_dbl, c_i64, c_i64, c_vp, c_vp, c_vp]
         L.orc_philox4x32_10.argtypes = [c_vp, c_vp, c_vp]
+        L.orc_sample_candidate.argtypes = [P(Space), ctypes.c_uint64, c_i64, c_vp]
+        L.orc_sample_free.restype = c_i64
+        L.orc_sample_free.argtypes = [P(Checker), P(Space), c_i64, ctypes.c_uint64, c_i64, c_vp, P(c_i64)]
         L.orc_det_log.restype = c_dbl
         L.orc_det_log.argtypes = [c_dbl]
         L.orc_det_exp.restype = c_dbl
@@ -235,6 +238,22 @@ def states_free(obs, space, Pts):
     cc = obs.checker()
     lib().orc_states_free(ctypes.byref(cc), ctypes.byref(space.c), _p(Pts), len(Pts), _p(out))
     return out.astype(bool)
+
+
+def sample_free(obs, space, N, seed, max_candidates=None):
+    """first N free candidates of the Philox candidate stream (oracle/sample.c) -> (V[N x n], candidates used)"""
+    V = np.zeros((N, space.n))
+    cc = obs.checker()
+    used = c_i64(0)
+    mc = int(max_candidates) if max_candidates is not None else (1 << 62)
+    got = lib().orc_sample_free(ctypes.byref(cc), ctypes.byref(space.c), N, seed, mc, _p(V), ctypes.byref(used))
+    return V[:got], used.value
+
+
+def sample_candidate(space, seed, c):
+    x = np.zeros(space.n)
+    lib().orc_sample_candidate(ctypes.byref(space.c), seed, c, _p(x))
+    return x
 
 
 def motions_free_straight(obs, space, V, W):

@@ -140,3 +140,39 @@ def test_mc_zero_and_one_rollout(gpu, orc):
     assert r1["n"] == 1
     one = mp.collision_probability(P, Bx, 1, seed=3, first=41, per_rollout=True)
     assert one["hit"][0] == whole["hit"][41] and one["w"][0] == whole["w"][41]
+
+
+@pytest.mark.parametrize("case", ["sat2d", "sat2d_fixed", "boxes3d", "di_view"])
+def test_device_sample_free_matches_the_oracle_stream(gpu, orc, case):
+    """mpb200_sample_free: the device-generated sample set is bit-identical to oracle/sample.c --
+    same candidates, same acceptance, same order -- whatever the chunking"""
+    mp = gpu
+    if case.startswith("sat2d"):
+        fixed = case.endswith("fixed")
+        CC, R = mp.PointRobot2D(mp.obstaclesets.ISRR_2H(), fixed_point_test=fixed), orc.Obstacles2D(fx.ISRR_2H, fixed_point_test=fixed)
+        SSp, SSo = mp.UnitHypercube(2), orc.StateSpace([0, 0], [1, 1])
+    elif case == "boxes3d":
+        CC, R = mp.PointRobotNDBoxes([mp.BoxBounds(b) for b in fx.BOXES3D]), orc.Boxes(fx.BOXES3D)
+        SSp, SSo = mp.UnitHypercube(3), orc.StateSpace([0, 0, 0], [1, 1, 1])
+    else:  # 4-D double-integrator states, collision checked on the position coordinates only
+        CC, R = mp.PointRobot2D(mp.obstaclesets.ISRR_2H(), fixed_point_test=True), orc.Obstacles2D(fx.ISRR_2H, fixed_point_test=True)
+        lo, hi = [0, 0, -1.5, -1.5], [1, 1, 1.5, 1.5]
+        SSp = mp.BoundedStateSpace(lo, hi, mp.Euclidean(), mp.VectorView(1, 2))
+        SSo = orc.StateSpace(lo, hi, ("view", [1, 2]))
+    for N, seed in ((1, 3), (777, 4), (60_000, 5)):
+        NN = mp.MetricNN.sample_free(CC, SSp, N, seed=seed)
+        V, used = orc.sample_free(R, SSo, N, seed)
+        assert NN.candidates == used and NN.V.tobytes() == V.tobytes()
+        assert unpack_bits(NN.points_free(CC, SSp), N).all()            # the handle really holds those samples
+        if N == 777 and SSp.dim <= 3:
+            D = NN.precompute(0.08).D
+            ec, er, ez = orc.rball_brute(V, 0.08)
+            assert np.array_equal(D.colptr, ec) and np.array_equal(D.rowval, er) and np.array_equal(D.nzval, ez)
+        NN.close()
+
+
+def test_device_sample_free_with_no_free_space_fails_loudly(gpu):
+    mp = gpu
+    CC = mp.PointRobotNDBoxes([mp.BoxBounds(np.array([-1.0, -1.0]), np.array([2.0, 2.0]))])   # covers the whole square
+    with pytest.raises(mp.MPB200Error):
+        mp.MetricNN.sample_free(CC, mp.UnitHypercube(2), 100, seed=1)
