@@ -135,10 +135,12 @@ def sample_free_goal(P, rng):
             return v
 
 
-def sample_free(P, N, ensure_goal=True, ensure_goal_ct=5, seed=0, batch=None):
+def sample_free(P, N, ensure_goal=True, ensure_goal_ct=5, seed=0, batch=None, device=False):
     """sample_free!(P, N; ensure_goal_ct): sampling.jl:11-45.  Sample 1 is the init state, the last
     ensure_goal_ct samples are goal samples; the rest are uniform states that pass is_free_state,
-    accepted in draw order.  Returns volume(SS) like the reference (:44)."""
+    accepted in draw order.  Returns volume(SS) like the reference (:44).
+    device=True draws the uniform bulk with mpb200_sample_free (Philox candidate stream, generated and
+    filtered on the GPU) instead of the host generator + batched validity."""
     if N <= 0:
         return volume(P.SS)
     rng = np.random.Generator(np.random.PCG64(seed))
@@ -150,6 +152,12 @@ def sample_free(P, N, ensure_goal=True, ensure_goal_ct=5, seed=0, batch=None):
     if not have_init:
         W[0] = P.init
         count = 1
+    if device and N - count > 0:
+        from .nearneighbors import MetricNN
+        bulk = MetricNN.sample_free(P.CC, SS, N - count, seed=seed)
+        W[count:] = bulk.V
+        bulk.close()
+        count = N
     batch = batch or max(1024, int(1.5 * N))
     while count < N:
         cand = SS.lo + rng.random((batch, SS.dim)) * (SS.hi - SS.lo)
