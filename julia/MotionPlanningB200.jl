@@ -88,6 +88,22 @@ end
 #   k = P.V.cache.D.colptr[x] - 1 + findnth(H[rowvals_of_column_x], y_idx)   # position of y_min in column x
 #   if E[k]                                       # was: is_free_motion(P.V[y_min], P.V[x], P.CC, P.SS)
 
+# ---- sample_free! on the device (sampling.jl:23-37) -------------------------------------------------------
+# The uniform bulk of the sample set is drawn, filtered with is_free_state and compacted on the GPU; the handle
+# is kept for the table builds, the host copy feeds P.V.  (Own Philox stream: deterministic in `seed`, not
+# Julia's global RNG.)
+function sample_free_b200{T}(SS::StateSpace{T}, CC::B200PointRobot2D, N::Int, seed::UInt64)
+    d = dim(SS)
+    M = Array(Float64, d, N)
+    h = Ref{Ptr{Void}}(C_NULL); used = Ref{Int64}(0)
+    check(ccall((:mpb200_sample_free, LIB), Cint,
+                (Ptr{Void}, Ptr{Void}, Int64, UInt64, Ref{Ptr{Void}}, Ptr{Float64}, Ref{Int64}),
+                CC.h, space_desc(SS), N, seed, h, M, used))
+    s = B200Samples(h[])                              # adopt the handle
+    finalizer(s, x -> ccall((:mpb200_samples_destroy, LIB), Cint, (Ptr{Void},), x.h))
+    reinterpret(SVector{d,Float64}, M, (N,)), s, used[]
+end
+
 # ---- linear-quadratic (ControlNN) ---------------------------------------------------------------------
 function helper_data_structures{S}(V::Vector{S}, M::LinearQuadratic, backend::Type{Val{:b200}})
     s = B200Samples(V)

@@ -112,7 +112,7 @@ struct mpb200_samples {
     mpb::DevBuf V;           // f64 d x N column-major (AoS), as the caller gave it
     // uniform grid (built per radius by mpb200_inball_build)
     mpb::DevBuf cell_start;  // int32 ncells+1
-    mpb::DevBuf cell_fill;   // int32 ncells (scatter cursors)
+    mpb::DevBuf cell_fill;   // int32 ncells+1: per-cell histogram (its atomics hand out the in-cell ranks)
     mpb::DevBuf sorted_idx;  // int32 N   original index of the k-th point in cell order
     mpb::DevBuf sorted_pos;  // f64 d x N positions in cell order (AoS)
     mpb::DevBuf pt_order;    // int32 (q1-q0): the shard's samples (relative to q0) in grid-cell order, from the last grid build
