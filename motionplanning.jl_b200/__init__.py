@@ -13,6 +13,7 @@ from .statespaces import (BoundedEuclideanStateSpace, BoundedStateSpace, Euclide
                           OutputMatrix, UnitHypercube, VectorView, dim, is_free_motion, is_free_path,
                           is_free_state, segments_free, state2workspace, states_free, volume)
 from .nearneighbors import (ImmutableNNC, MetricNN, QuasiMetricNN, SampleSet, SparseMatrixCSC, SparseVectorView,  # noqa: F401
+                            loadNN, saveNN,
                             addpoints, filter_neighborhood, inball, inballB, inballF, nonzeroinds,
                             nonzeros, viewcol)
 from .linearquadratic import (DoubleIntegrator, LinearQuadratic, LinearQuadraticQuasiMetricSpace,  # noqa: F401

@@ -73,6 +73,40 @@ class ImmutableNNC:
         self.r = r
 
 
+def saveNN(path, cache, edge_chunks=None, point_chunks=None):
+    """On-disk form of a precomputed neighbour table and its validity sidecars.  The reference
+    exports the names only (`# export saveNN, loadNN!`, nearneighbors.jl:8; the "Serialization" section :114-116
+    is empty); the format here is the SparseMatrixCSC fields as they cross the C ABI (1-based Int64 colptr /
+    rowval, Float64 nzval) plus the BitVector chunks of the edge and point validity tables, in one .npz."""
+    D = cache.D
+    arrays = dict(m=np.int64(D.m), n=np.int64(D.n), r=np.float64(cache.r), colptr=np.asarray(D.colptr, dtype=np.int64),
+                  rowval=np.asarray(D.rowval, dtype=np.int64), nzval=np.asarray(D.nzval, dtype=np.float64))
+    if edge_chunks is not None:
+        arrays["edge_chunks"] = np.asarray(edge_chunks, dtype=np.uint64)
+    if point_chunks is not None:
+        arrays["point_chunks"] = np.asarray(point_chunks, dtype=np.uint64)
+    np.savez(path, **arrays)
+
+
+def loadNN(path, NN=None):
+    """Inverse of saveNN -> (ImmutableNNC, edge_chunks or None, point_chunks or None); installs the cache into
+    `NN` (a MetricNN) when given, like loadNN! would."""
+    with np.load(path) as z:
+        D = SparseMatrixCSC(int(z["m"]), int(z["n"]), z["colptr"], z["rowval"], z["nzval"])
+        cache = ImmutableNNC(D, float(z["r"]))
+        edge = z["edge_chunks"] if "edge_chunks" in z.files else None
+        pts = z["point_chunks"] if "point_chunks" in z.files else None
+    if D.colptr[0] != 1 or len(D.colptr) != D.n + 1 or D.nnz != len(D.rowval) or D.nnz != len(D.nzval):
+        raise ValueError("%s does not hold a consistent CSC table" % path)
+    if edge is not None and len(edge) != (D.nnz + 63) // 64:
+        raise ValueError("edge validity sidecar does not match the table")
+    if NN is not None:
+        if len(NN) != D.m:
+            raise ValueError("table is for %d samples, the sample set has %d" % (D.m, len(NN)))
+        NN.cache = cache
+    return cache, edge, pts
+
+
 class DeviceTable:
     """Owner of a device-resident CSC table handle (mpb200_table)."""
 

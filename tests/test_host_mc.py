@@ -1,5 +1,6 @@
 """Host-side pieces of the Monte-Carlo path (no GPU): LQG closed loop, noise maps, closest points."""
 import numpy as np
+import pytest
 
 import fixtures as fx
 
@@ -63,3 +64,28 @@ def test_with_proposal_builds_normalised_mixture(mp):
             if any(abs(w[1] - 0.19) < 1e-6 and 0.4 - 1e-6 <= w[0] <= 0.5 + 1e-6 for _ in [0]):
                 touched += 1
     assert touched >= 1
+
+
+def test_save_load_nn_roundtrip(tmp_path):
+    """saveNN / loadNN (names only in the reference, nearneighbors.jl:8): the CSC fields and the validity
+    sidecars survive the round trip; inconsistent files are rejected"""
+    import mpb200
+    rng = np.random.Generator(np.random.PCG64(3))
+    n = 50
+    counts = rng.integers(0, 6, size=n)
+    colptr = np.concatenate([[1], 1 + np.cumsum(counts)]).astype(np.int64)
+    nnz = int(colptr[-1] - 1)
+    rowval = np.concatenate([np.sort(rng.choice(n, c, replace=False)) + 1 for c in counts]).astype(np.int64) if nnz else np.zeros(0, np.int64)
+    nzval = rng.random(nnz)
+    cache = mpb200.ImmutableNNC(mpb200.SparseMatrixCSC(n, n, colptr, rowval, nzval), 0.25)
+    edge = rng.integers(0, 2**63, size=(nnz + 63) // 64, dtype=np.uint64)
+    pts = rng.integers(0, 2**63, size=1, dtype=np.uint64)
+    path = str(tmp_path / "nn.npz")
+    mpb200.saveNN(path, cache, edge, pts)
+    c2, e2, p2 = mpb200.loadNN(path)
+    assert c2.r == 0.25 and c2.D.m == n and c2.D.n == n
+    assert np.array_equal(c2.D.colptr, colptr) and np.array_equal(c2.D.rowval, rowval)
+    assert c2.D.nzval.tobytes() == nzval.tobytes() and np.array_equal(e2, edge) and np.array_equal(p2, pts)
+    mpb200.saveNN(path, cache, edge[:-1] if len(edge) > 1 else np.zeros(len(edge) + 1, np.uint64))
+    with pytest.raises(ValueError):
+        mpb200.loadNN(path)
