@@ -460,6 +460,7 @@ __device__ __forceinline__ void bitonic64(unsigned &k0, unsigned &k1, int lane) 
 // Measured alternatives: (r1o) prefetching the next column group's hit byte -> position -> index/point chain
 // one group ahead (software pipeline) changed nothing (297 us for U = 1, 2, 4): the kernel is bound by LSU
 // wavefronts + issue slots, not by the latency of that chain, although half the stall samples sit on it.
+// Visiting the tile's columns longest-first (so that groups needing the 64-key network cluster): fill 288 -> 320 us.
 // (r1m) ranking each index against the column's indices read back from
 // shared memory four at a time (no shuffles, rows stored at base + rank) halves the LSU
 // wavefronts of the sort but costs ~2.3 ALU instructions per comparison: 269M warp
