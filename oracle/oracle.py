@@ -69,7 +69,9 @@ def lib():
         L.orc_philox4x32_10.argtypes = [c_vp, c_vp, c_vp]
         L.orc_sample_candidate.argtypes = [P(Space), ctypes.c_uint64, c_i64, c_vp]
         L.orc_sample_free.restype = c_i64
-        L.orc_sample_free.argtypes = [P(Checker), P(Space), c_i64, ctypes.c_uint64, c_i64, c_vp, P(c_i64)]
+        L.orc_sample_free.argtypes = [P(Checker), P(Space), c_i64, ctypes.c_uint64, c_i64, ctypes.c_int, c_vp, P(c_i64)]
+        L.orc_morton_key.restype = ctypes.c_uint64
+        L.orc_morton_key.argtypes = [P(Space), c_vp]
         L.orc_det_log.restype = c_dbl
         L.orc_det_log.argtypes = [c_dbl]
         L.orc_det_exp.restype = c_dbl
@@ -240,13 +242,19 @@ def states_free(obs, space, Pts):
     return out.astype(bool)
 
 
-def sample_free(obs, space, N, seed, max_candidates=None):
-    """first N free candidates of the Philox candidate stream (oracle/sample.c) -> (V[N x n], candidates used)"""
+def morton_key(space, x):
+    x = _f64(x)
+    return int(lib().orc_morton_key(ctypes.byref(space.c), _p(x)))
+
+
+def sample_free(obs, space, N, seed, max_candidates=None, order=0):
+    """first N free candidates of the Philox candidate stream (oracle/sample.c) -> (V[N x n], candidates used);
+    order=1: stably sorted by Morton key"""
     V = np.zeros((N, space.n))
     cc = obs.checker()
     used = c_i64(0)
     mc = int(max_candidates) if max_candidates is not None else (1 << 62)
-    got = lib().orc_sample_free(ctypes.byref(cc), ctypes.byref(space.c), N, seed, mc, _p(V), ctypes.byref(used))
+    got = lib().orc_sample_free(ctypes.byref(cc), ctypes.byref(space.c), N, seed, mc, int(order), _p(V), ctypes.byref(used))
     return V[:got], used.value
 
 

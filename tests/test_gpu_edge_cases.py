@@ -163,6 +163,10 @@ def test_device_sample_free_matches_the_oracle_stream(gpu, orc, case):
         NN = mp.MetricNN.sample_free(CC, SSp, N, seed=seed)
         V, used = orc.sample_free(R, SSo, N, seed)
         assert NN.candidates == used and NN.V.tobytes() == V.tobytes()
+        NM = mp.MetricNN.sample_free(CC, SSp, N, seed=seed, order="morton")      # same set, Z-order numbering
+        VM, _ = orc.sample_free(R, SSo, N, seed, order=1)
+        assert NM.candidates == used and NM.V.tobytes() == VM.tobytes()
+        NM.close()
         assert unpack_bits(NN.points_free(CC, SSp), N).all()            # the handle really holds those samples
         if N == 777 and SSp.dim <= 3:
             D = NN.precompute(0.08).D

@@ -31,3 +31,22 @@ def test_sample_free_keeps_exactly_the_free_candidates_in_order(orc):
     # a budget of candidates that is too small returns what was found
     V2, used2 = orc.sample_free(O, S, 3000, 99, max_candidates=100)
     assert used2 == 100 and len(V2) == free[:100].sum()
+
+
+def test_morton_order_is_a_stable_spatial_sort_of_the_same_set(orc):
+    O = orc.Obstacles2D(fx.ISRR_2H, fixed_point_test=True)
+    S = orc.StateSpace([0, 0], [1, 1])
+    V, used = orc.sample_free(O, S, 5000, 5)
+    M, used_m = orc.sample_free(O, S, 5000, 5, order=1)
+    assert used_m == used
+    keys = np.array([orc.morton_key(S, v) for v in V], dtype=np.uint64)
+    assert M.tobytes() == V[np.argsort(keys, kind="stable")].tobytes()
+    # known answers of the key: coordinate 0 in the least significant position, 20 bits per coordinate
+    assert orc.morton_key(S, [0.0, 0.0]) == 0
+    assert orc.morton_key(S, [2.0 ** -20, 0.0]) == 1 and orc.morton_key(S, [0.0, 2.0 ** -20]) == 2
+    assert orc.morton_key(S, [3 * 2.0 ** -20, 0.0]) == 0b1001
+    assert orc.morton_key(S, [1.0, 1.0]) == orc.morton_key(S, [1 - 2.0 ** -21, 1 - 2.0 ** -21])   # clamped to 2^20 - 1
+    S3 = orc.StateSpace([0, 0, 0, -1], [2, 2, 2, 1])
+    assert orc.morton_key(S3, [0.0, 0.0, 2.0 ** -19, 0.7]) == 4      # only the first three coordinates count
+    # spatial coherence: consecutive samples are much closer than in draw order
+    assert np.linalg.norm(np.diff(M, axis=0), axis=1).mean() < 0.1 * np.linalg.norm(np.diff(V, axis=0), axis=1).mean()
