@@ -180,3 +180,41 @@ def test_device_sample_free_with_no_free_space_fails_loudly(gpu):
     CC = mp.PointRobotNDBoxes([mp.BoxBounds(np.array([-1.0, -1.0]), np.array([2.0, 2.0]))])   # covers the whole square
     with pytest.raises(mp.MPB200Error):
         mp.MetricNN.sample_free(CC, mp.UnitHypercube(2), 100, seed=1)
+
+
+@pytest.mark.parametrize("name", ["ISRR_2H", "ISRR_POLY", "TRI_BALLS"])
+@pytest.mark.parametrize("fixed", [False, True])
+def test_edge_validity_shortcuts_next_to_obstacle_boundaries(gpu, orc, name, fixed):
+    """The classify pass settles whole columns from the r-box of the column point (clear of every cull box ->
+    all free; inside one convex polygon by a margin -> all colliding).  Samples are placed ON and within
+    1e-13 .. r of every obstacle AABB edge, polygon vertex and state-space bound, where those shortcuts must
+    hand over to the exact per-edge test: bits and check counts have to stay identical to the oracle's."""
+    mp = gpu
+    spec = fx.ALL_2D[name]
+    CC = mp.PointRobot2D(fx.product_shape(mp, spec), fixed_point_test=fixed)
+    O = orc.Obstacles2D(spec, fixed_point_test=fixed)
+    SSp, SSo = mp.UnitHypercube(2), orc.StateSpace([0, 0], [1, 1])
+    rng = np.random.Generator(np.random.PCG64(17))
+    xs, ys = [0.0, 1.0], [0.0, 1.0]
+    for s in spec[1]:
+        if s[0] == "polygon":
+            P = np.array(s[1]); xs += list(P[:, 0]); ys += list(P[:, 1])
+        else:
+            (cx, cy), rad = s[1], s[2]; xs += [cx - rad, cx, cx + rad]; ys += [cy - rad, cy, cy + rad]
+    for r in (1e-3, 0.02):
+        offs = np.array([0.0, 1e-13, -1e-13, 1e-9, -1e-9, r, -r, r * (1 + 1e-9), -r * (1 + 1e-9), 0.5 * r, -0.5 * r])
+        gx = np.unique(np.clip(np.add.outer(np.array(xs), offs).ravel(), 0.0, 1.0))
+        gy = np.unique(np.clip(np.add.outer(np.array(ys), offs).ravel(), 0.0, 1.0))
+        V = np.array([[x, y] for x in gx for y in gy])
+        V = np.vstack([V, V[rng.integers(0, len(V), 4000)] + (rng.random((4000, 2)) - 0.5) * 2 * r])   # neighbours within r
+        V = np.clip(V, 0.0, 1.0)
+        NN = mp.MetricNN(V)
+        D = NN.precompute(r).D
+        F = unpack_bits(NN.points_free(CC, SSp), len(V))
+        assert np.array_equal(F, orc.states_free(O, SSo, V))
+        bits, checks = NN.edges_free(NN.table, CC, SSp)
+        exp, cnt = orc.edges_free_csc(O, SSo, V, D.colptr, D.rowval)
+        got = unpack_bits(bits, D.nnz)
+        assert np.array_equal(got, exp.astype(bool)), "first mismatch at stored entry %d" % int(np.argmax(got != exp.astype(bool)))
+        assert checks == cnt and D.nnz > 1000
+        NN.close()
