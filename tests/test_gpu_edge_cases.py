@@ -218,3 +218,26 @@ def test_edge_validity_shortcuts_next_to_obstacle_boundaries(gpu, orc, name, fix
         assert np.array_equal(got, exp.astype(bool)), "first mismatch at stored entry %d" % int(np.argmax(got != exp.astype(bool)))
         assert checks == cnt and D.nnz > 1000
         NN.close()
+
+
+@pytest.mark.parametrize("d,boxes", [(2, "BOXES2D"), (3, "BOXES3D")])
+def test_box_edge_validity_shortcuts_next_to_faces(gpu, orc, d, boxes):
+    """same idea for the N-d box checker: samples on and next to every box face and state-space bound"""
+    mp = gpu
+    B = getattr(fx, boxes)
+    CC, R = mp.PointRobotNDBoxes([mp.BoxBounds(b) for b in B]), orc.Boxes(B)
+    SSp, SSo = mp.UnitHypercube(d), orc.StateSpace([0] * d, [1] * d)
+    rng = np.random.Generator(np.random.PCG64(23))
+    r = 0.01 if d == 2 else 0.03
+    offs = np.array([0.0, 1e-13, -1e-13, r, -r, r * (1 + 1e-9), -r * (1 + 1e-9)])
+    faces = [np.unique(np.clip(np.add.outer(np.concatenate([[0.0, 1.0]] + [np.asarray(b)[i] for b in B]), offs).ravel(), 0, 1))
+             for i in range(d)]
+    base = np.stack([f[rng.integers(0, len(f), 6000)] for f in faces], axis=1)      # every coordinate on/near a face
+    V = np.clip(np.vstack([base, base[rng.integers(0, len(base), 6000)] + (rng.random((6000, d)) - 0.5) * 2 * r]), 0, 1)
+    NN = mp.MetricNN(V)
+    D = NN.precompute(r).D
+    assert np.array_equal(unpack_bits(NN.points_free(CC, SSp), len(V)), orc.states_free(R, SSo, V))
+    bits, checks = NN.edges_free(NN.table, CC, SSp)
+    exp, cnt = orc.edges_free_csc(R, SSo, V, D.colptr, D.rowval)
+    assert np.array_equal(unpack_bits(bits, D.nnz), exp.astype(bool)) and checks == cnt and D.nnz > 1000
+    NN.close()
