@@ -441,7 +441,7 @@ static int check_obstacles(const mpb200_obstacles *o, int dw) {
 int points_free_device(const double *dV, int64_t n, int d, const mpb200_obstacles *o, const mpb200_space_desc *ss,
                        uint32_t *d_bits32, uint8_t *d_bytes, const int *order) {
     SpaceDev S;
-    int dw;
+    int dw = 0;
     if (int rc = make_space(ss, d, &S, &dw)) return rc;
     if (int rc = check_obstacles(o, dw)) return rc;
     LaunchCfg L = make_cfg(o, n);
@@ -465,7 +465,7 @@ int edges_free_device_cols(const double *dV, int d, const mpb200_table *t, const
 int edges_free_device(const double *dV, int d, const mpb200_table *t, const mpb200_obstacles *o,
                       const mpb200_space_desc *ss, uint32_t *d_bits32, unsigned long long *d_checks) {
     SpaceDev S;
-    int dw;
+    int dw = 0;
     if (int rc = make_space(ss, d, &S, &dw)) return rc;
     if (int rc = check_obstacles(o, dw)) return rc;
     static const bool no_classify = getenv("MPB200_NO_CLASSIFY") != nullptr;
@@ -531,7 +531,7 @@ int edges_free_device_cols(const double *dV, int d, const mpb200_table *t, const
 int segments_free_device(const double *dA, const double *dB, int64_t n, int d, const mpb200_obstacles *o,
                          const mpb200_space_desc *ss, uint8_t *d_out) {
     SpaceDev S;
-    int dw;
+    int dw = 0;
     if (int rc = make_space(ss, d, &S, &dw)) return rc;
     if (int rc = check_obstacles(o, dw)) return rc;
     LaunchCfg L = make_cfg(o, n);
@@ -553,7 +553,7 @@ int segments_free_device(const double *dA, const double *dB, int64_t n, int d, c
 int sample_free_device(const mpb200_obstacles *o, const mpb200_space_desc *ss, int64_t n_want, uint64_t seed,
                        double *dV, DevBuf &scratch, DevBuf &tmp, int64_t *h_used) {
     SpaceDev S;
-    int dw;
+    int dw = 0;
     if (int rc = make_space(ss, ss ? ss->n : 0, &S, &dw)) return rc;
     if (int rc = check_obstacles(o, dw)) return rc;
     Context &c = ctx();

@@ -612,7 +612,7 @@ int lq_edges_free_device(const mpb200_samples *s, const mpb200_table *t, const m
                          const mpb200_obstacles *o, const mpb200_space_desc *ss, uint32_t *d_bits32,
                          unsigned long long *d_checks) {
     SpaceDev S;
-    int dw;
+    int dw = 0;
     if (int rc = make_space(ss, s->d, &S, &dw)) return rc;
     if (s->d != 2 * lq->d) return fail(MPB200_EARG, "sample dimension %d != 2 x %d", s->d, lq->d);
     if (o->kind == 1 && o->d != dw) return fail(MPB200_EARG, "box dimension %d != workspace dimension %d", o->d, dw);
@@ -640,7 +640,7 @@ int lq_motions_free_device(const mpb200_lq *lq, double r, const double *dA, cons
                            const mpb200_obstacles *o, const mpb200_space_desc *ss, uint8_t *d_out,
                            unsigned long long *d_checks) {
     SpaceDev S;
-    int dw;
+    int dw = 0;
     if (int rc = make_space(ss, d_state, &S, &dw)) return rc;
     if (d_state != 2 * lq->d) return fail(MPB200_EARG, "state dimension %d != 2 x %d", d_state, lq->d);
     if (o->kind == 1 && o->d != dw) return fail(MPB200_EARG, "box dimension %d != workspace dimension %d", o->d, dw);

@@ -55,7 +55,7 @@ int make_space(const mpb200_space_desc *ss, int d_state, SpaceDev *out, int *dw)
 int morton_reorder_device(double *dV, int64_t N, const mpb200_space_desc *ss, DevBuf &scratch) {
     if (N <= 1) return 0;
     SpaceDev S;
-    int dw;
+    int dw = 0;
     if (int rc = make_space(ss, ss->n, &S, &dw)) return rc;
     const int n = ss->n;
     cudaStream_t st = ctx().stream;
