@@ -226,6 +226,7 @@ int mpb200_init(int device) {
         for (int i = 0; i <= kMaxPhases; ++i) MPB_CUDA(cudaEventCreate(&c.ev[b][i]));
     MPB_CUDA(cudaEventCreateWithFlags(&c.ev_scalar, cudaEventDisableTiming));
     MPB_CUDA(cudaMalloc(&c.d_scalar, sizeof(int64_t) * 16));
+    MPB_CUDA(cudaMemset(c.d_scalar, 0, sizeof(int64_t) * 16));  // slots are read back in groups; none is ever undefined
     MPB_CUDA(cudaMallocHost(&c.h_scalar, sizeof(int64_t) * 16));
     c.launches = 0;
     c.ready = true;
