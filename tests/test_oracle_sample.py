@@ -50,3 +50,22 @@ def test_morton_order_is_a_stable_spatial_sort_of_the_same_set(orc):
     assert orc.morton_key(S3, [0.0, 0.0, 2.0 ** -19, 0.7]) == 4      # only the first three coordinates count
     # spatial coherence: consecutive samples are much closer than in draw order
     assert np.linalg.norm(np.diff(M, axis=0), axis=1).mean() < 0.1 * np.linalg.norm(np.diff(V, axis=0), axis=1).mean()
+
+
+def test_candidate_stream_matches_the_pinned_golden_file(orc):
+    """tests/golden/sample_stream.json (gen_sample_golden.py): the stream's definition must not drift"""
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(__file__), "golden", "sample_stream.json")) as f:
+        G = json.load(f)
+    spaces = {"unit2": ([0.0, 0.0], [1.0, 1.0]), "box3": ([-1.0, 2.0, 0.0], [1.0, 5.0, 0.5]),
+              "di4": ([0.0, 0.0, -1.5, -1.5], [1.0, 1.0, 1.5, 1.5])}
+    for key, hexes in G["candidates"].items():
+        name, seed, c = key.split("/")
+        S = orc.StateSpace(*spaces[name])
+        x = orc.sample_candidate(S, int(seed), int(c))
+        assert [float(v).hex() for v in x] == hexes, key
+    for key, k in G["morton"].items():
+        name, c = key.split("/")
+        S = orc.StateSpace(*spaces[name])
+        assert orc.morton_key(S, orc.sample_candidate(S, 1, int(c))) == k, key
