@@ -12,7 +12,9 @@
  *    mpb200_last_error() returns the thread-local message.  No CPU fallback:
  *    without a usable sm_100 GPU every compute entry point fails.
  *  - host buffers are caller-owned (Julia GC / numpy); the library copies inputs
- *    at *_create and writes outputs only between call and return.
+ *    at *_create and writes outputs only between call and return.  Calls that hand
+ *    data back wait for it; calls whose result pointers are all NULL only enqueue
+ *    work on the launching stream (noted at each entry point).
  *  - samples cross as the reference stores them: Vector{SVector{d,Float64}} ==
  *    column-major d x N Float64 (primitivetypes.jl:21-23, statevec2mat).
  *  - neighbour tables cross as Julia SparseMatrixCSC{Float64,Int64} fields:
@@ -53,11 +55,11 @@ int mpb200_version(void);
  * library's own; pass NULL to return to the library stream. */
 int mpb200_set_stream(void *cuda_stream);
 int mpb200_synchronize(void);
-/* Pinned host memory for result buffers (fast D2H); plain malloc'ed buffers work too. */
 /* Device arrays released by the library (destroyed tables / sample sets, outgrown buffers) are parked
  * in a free list and reused by later calls instead of going through cudaFree / cudaMalloc (milliseconds
  * each, device-synchronising).  This returns every parked block to the driver. */
 int mpb200_release_cached(void);
+/* Pinned host memory for result buffers (fast D2H); plain malloc'ed buffers work too. */
 int mpb200_host_alloc(uint64_t bytes, void **out);
 int mpb200_host_free(void *p);
 /* Number of kernels this library has launched since mpb200_init (bench "gpu_launches"). */
