@@ -36,12 +36,28 @@ def build_lib(force=False, verbose=False):
         return LIB
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found; libmpb200.so cannot be built")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + srcs
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    if verbose:
-        print(res.stderr)
+    # one nvcc per translation unit, in parallel (no relocatable device code: device functions are header-inline,
+    # only host functions cross translation units), then one link
+    import tempfile
+    from concurrent.futures import ThreadPoolExecutor
+    compile_flags = [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else [])
+    with tempfile.TemporaryDirectory(prefix="mpb200_build_") as tmp:
+        objs = [os.path.join(tmp, os.path.basename(src)[:-3] + ".o") for src in srcs]
+
+        def compile_one(args):
+            src, obj = args
+            return subprocess.run([nvcc] + compile_flags + ["-c", src, "-o", obj], capture_output=True, text=True)
+
+        with ThreadPoolExecutor(max_workers=min(len(srcs), os.cpu_count() or 1)) as pool:
+            results = list(pool.map(compile_one, zip(srcs, objs)))
+        for src, res in zip(srcs, results):
+            if res.returncode != 0:
+                raise RuntimeError("nvcc failed on %s:\n%s%s" % (os.path.basename(src), res.stdout, res.stderr))
+            if verbose:
+                print(res.stderr)
+        res = subprocess.run([nvcc, "-shared", "-o", LIB] + objs, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("link failed:\n" + res.stdout + res.stderr)
     return LIB
 
 
