@@ -8,10 +8,17 @@ point validity (K6) + validity of every stored edge (K7: column classify + per-e
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-N > 1: launched by torch.distributed.run, one rank per GPU; weak scaling -- the sample set grows
-to N x 1M (replicated on every GPU), rank g owns the query columns [g*1M, (g+1)*1M); the per-rank
-CSC shards concatenate, and every step ends with the one exchange the host planner needs: an
-NCCL all-gather of the shard colptrs and edge-validity words (no other data-path collective).
+N > 1: launched by torch.distributed.run, one rank per GPU.  The headline line is WEAK scaling -- the
+sample set grows to N x 1M (replicated on every GPU, stripe order), rank g owns the query columns
+[g*1M, (g+1)*1M); the per-rank CSC shards concatenate, and every step ends with the one exchange the host
+planner needs: the shard column lengths and edge-validity words of every rank on every rank (direct peer
+stores over NVLink + a device flag barrier, csrc/xchg.cu; NCCL all-gather as the fallback).  The same line
+carries, as sub-objects, the two multi-GPU configurations BASELINE.json names literally:
+  "strong_scaling" -- N = 1M samples IN TOTAL sharded over the N GPUs (configs[1]),
+  "mc"             -- 1e8 importance-sampled rollouts sharded by rollout id + all-reduce (configs[4]),
+and at N = 1 a "secondary" block with configs C3 / C4 / C5 (own roofline + cpu_baseline each).
+After the timed region every rank count checks the tables it just timed against the CPU oracle on
+sampled column windows ("parity_checked": columns) -- including the GATHERED global colptr / validity bits.
 """
 import argparse
 import json
@@ -32,13 +39,18 @@ METRIC = "collision_checked_edges_per_sec"
 UNIT = "edges/s"
 
 
+def workload_name(n_total, r):
+    """the ONE workload string both arms print (the driver compares the two config blocks)"""
+    return "C2: FMT* 2-D unit square, ISRR_2H, N=%d uniform samples (%d query columns per GPU), r=%.7f" % (
+        n_total, SAMPLES_PER_GPU, r)
+
+
 def fill_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of rball_fill<2, U> on this workload, from the
     committed `ncu --set full` capture of the newest round (profiles/rN/traffic.json, scripts/ncu_traffic.py);
     None when no capture is committed.  Measured under the profiler, so it is traffic only, never a time."""
     import glob
-    for path in sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r*", "traffic.json")),
-                       reverse=True):
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*", "traffic.json")), reverse=True):
         try:
             with open(path) as f:
                 t = json.load(f)
@@ -69,8 +81,13 @@ def fmt_radius(N, d, rm=1.0, vol=1.0):
     return rm * 2 * (1 / d * vol / (math.pi ** (d / 2) / math.gamma(d / 2 + 1)) * math.log(N) / N) ** (1 / d)
 
 
-def make_samples(n_total):
-    return np.random.Generator(np.random.PCG64(SEED)).random((n_total, 2))
+def make_samples(n_total, stripe_order):
+    V = np.random.Generator(np.random.PCG64(SEED)).random((n_total, 2))
+    if stripe_order:
+        # stripe order: each rank's query range is then a spatial stripe and its grid covers only the
+        # stripe + r (FMT* is invariant to the order of i.i.d. samples; N = 1 keeps the raw order)
+        V = V[np.argsort(V[:, 0], kind="stable")]
+    return np.ascontiguousarray(V)
 
 
 def peaks():
@@ -188,7 +205,7 @@ def reference_arm(args, rank, world):
     if rank != 0:
         return
     n_total = SAMPLES_PER_GPU * world
-    V = make_samples(n_total)
+    V = make_samples(n_total, world > 1)
     r = fmt_radius(n_total, 2)
     threads = host_threads()
     # bounded sample: a contiguous block of query columns, sized from one probe so that
@@ -217,15 +234,198 @@ def reference_arm(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C2: FMT* 2-D unit square, ISRR_2H, N=%d uniform samples, r=%.7f" % (n_total, r),
-                   "sample_columns": ncols},
+        "config": {"workload": workload_name(n_total, r)},
+        "reference_sample_columns": ncols,
         "nn_queries_per_sec": ncols / (ms / 1e3),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": "%d of %d query columns (kd-tree inball + point + edge checks), tree build charged pro rata"
+                         "sample": "%d of %d query columns (kd-tree inball + point + edge checks), tree build charged pro rata; "
+                                   "the reference itself is single-threaded -- this arm uses every host thread"
                                    % (ncols, n_total)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+class Job:
+    """One sharded C2 precompute: sample set on the device, checker, exchange, and the step function."""
+
+    def __init__(self, mp, V, q0, q1, world, tag):
+        from mpb200 import sharding
+        import torch
+        import torch.distributed as dist
+        self.mp, self.V, self.q0, self.q1, self.world = mp, V, q0, q1, world
+        self.r = fmt_radius(len(V), 2)
+        self.CC = mp.PointRobot2D(mp.obstaclesets.ISRR_2H())
+        self.SS = mp.UnitHypercube(2)
+        self.CC.handle()
+        self.NN = mp.MetricNN(V)
+        self.NN.set_query_range(q0, q1)
+        self.NN.handle()  # inputs resident in HBM before the timed region
+        self.exchange = None
+        self.exchange_kind = None
+        if world > 1:
+            nnz0 = self.NN.build_table(self.r)
+            self.exchange = sharding.make_exchange(q1 - q0, (nnz0 * 21 // 20 + 63) // 64 + 2)
+            self.exchange_kind = "peer-stores" if isinstance(self.exchange, sharding.PeerExchange) else "nccl-allgather"
+        self.nnz = 0
+
+    def step(self):
+        # the three calls of a planning step, issued back to back: only build_table waits (for nnz, once,
+        # between count and fill); the validity calls enqueue their kernels and return
+        NN = self.NN
+        NN.points_free(self.CC, self.SS, fetch=False)           # K6
+        self.nnz = NN.build_table(self.r)                       # K1 + K2
+        NN.edges_free(NN.table, self.CC, self.SS, fetch=False, count=False)  # K7
+        if self.exchange is not None:
+            self.exchange.run(NN.table)          # column lengths + validity words of every rank -> every rank
+
+    def close(self):
+        if self.exchange is not None and hasattr(self.exchange, "close"):
+            self.exchange.close()
+        self.NN.close()
+
+
+def timed_steps(job, lib, stream, flush, steps, warmup, world, sampler=None, phases_out=None):
+    """W untimed + K timed steps, each bracketed by CUDA events on the launching stream, L2 flushed between
+    iterations (outside the event pairs).  Returns (sum of step ms on this rank, launches, wall seconds)."""
+    import torch
+    import torch.distributed as dist
+    from mpb200 import _lib
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    launches0 = 0
+    t_wall0 = 0.0
+    for it in range(warmup + steps):
+        if it == warmup:
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            if sampler is not None:
+                sampler.start()
+            launches0 = lib.mpb200_launch_count()
+            t_wall0 = time.perf_counter()
+        flush.zero_()  # L2 flush between iterations (outside the event pair)
+        if it >= warmup:
+            ev[it - warmup][0].record(stream)
+        job.step()
+        if it >= warmup:
+            ev[it - warmup][1].record(stream)
+            if phases_out is not None:
+                # per-kernel times of THIS step (events recorded inside the calls, read after the step's end event)
+                phases_out["table"] += np.array([lib.mpb200_last_ms_of(_lib.OP_TABLE, k) for k in range(5)])
+                phases_out["points"].append(lib.mpb200_last_ms_of(_lib.OP_POINTS, 1))
+                phases_out["edges"].append(lib.mpb200_last_ms_of(_lib.OP_EDGES, 1))
+                if job.exchange_kind == "peer-stores":
+                    phases_out["exchange"].append(lib.mpb200_last_ms_of(_lib.OP_OTHER, 1))
+            if sampler is not None and sampler.nv and (it - warmup) % 8 == 0:
+                sampler._sample()   # also from this thread, between steps (outside the event pairs): the region is short
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t_wall = time.perf_counter() - t_wall0
+    launches = lib.mpb200_launch_count() - launches0
+    return float(np.sum([a.elapsed_time(b) for a, b in ev])), int(launches), t_wall
+
+
+def parity_check(job, rank, world, windows=4, width=256):
+    """After the timed region: the table this rank just built (and, for N > 1, the GATHERED global colptr and
+    validity bits) against the CPU oracle on sampled column windows.  Raises on any mismatch."""
+    import torch
+    from oracle import oracle as orc
+    import fixtures as fx
+    from mpb200 import sharding
+    V, r, q0, q1 = job.V, job.r, job.q0, job.q1
+    N = len(V)
+    tree = orc.KDTree(V)
+    O = orc.Obstacles2D(fx.ISRR_2H)
+    So = orc.StateSpace([0, 0], [1, 1])
+    colptr, rowval, nzval, words = sharding.table_device_tensors(job.NN.table)
+    cp = colptr.cpu().numpy()
+    bits = np.unpackbits(words.cpu().numpy().view(np.uint8), bitorder="little") if words is not None else np.zeros(0, np.uint8)
+    checked = 0
+    gcol = gbits = None
+    if world > 1:
+        gcol, gchunks = job.exchange.assemble()
+        gbits = np.unpackbits(gchunks.view(np.uint8), bitorder="little")
+        if len(gcol) != N + 1:
+            raise RuntimeError("PARITY FAILURE: gathered colptr has %d entries for %d samples" % (len(gcol), N))
+    ncols = q1 - q0
+    starts = [int(x) for x in np.linspace(0, max(ncols - width, 0), windows)]
+    for a in starts:
+        b = min(a + width, ncols)
+        ref_cp, ref_rv, ref_nz = tree.rball(r, q0 + a, q0 + b)
+        lo, hi = int(cp[a]) - 1, int(cp[b]) - 1
+        ok = np.array_equal(cp[a:b + 1] - cp[a], ref_cp - ref_cp[0])
+        ok = ok and np.array_equal(rowval[lo:hi].cpu().numpy(), ref_rv)
+        ok = ok and nzval[lo:hi].cpu().numpy().tobytes() == np.ascontiguousarray(ref_nz).tobytes()
+        exp, _ = orc.edges_free_csc(O, So, V, ref_cp, ref_rv, q0 + a)
+        ok = ok and np.array_equal(bits[lo:hi], np.asarray(exp, dtype=np.uint8))
+        if not ok:
+            raise RuntimeError("PARITY FAILURE (rank %d): shard columns [%d, %d) differ from the oracle" % (rank, q0 + a, q0 + b))
+        checked += b - a
+    if world > 1:
+        # the gathered global structures, on windows inside EVERY rank's range (this is what proves the exchange)
+        for g in range(world):
+            g0, g1 = sharding.shard_range(N, g, world)
+            for a in (g0, max(g1 - width, g0)):
+                b = min(a + width, g1)
+                ref_cp, ref_rv, _ = tree.rball(r, a, b)
+                ok = np.array_equal(gcol[a:b + 1] - gcol[a], ref_cp - ref_cp[0])
+                exp, _ = orc.edges_free_csc(O, So, V, ref_cp, ref_rv, a)
+                lo, hi = int(gcol[a]) - 1, int(gcol[b]) - 1
+                ok = ok and np.array_equal(gbits[lo:hi], np.asarray(exp, dtype=np.uint8))
+                if not ok:
+                    raise RuntimeError("PARITY FAILURE (rank %d): gathered columns [%d, %d) of rank %d differ from the oracle"
+                                       % (rank, a, b, g))
+                checked += b - a
+    return checked
+
+
+def allreduce_max_sum(vals_max, vals_sum, world):
+    import torch
+    import torch.distributed as dist
+    tm = torch.tensor(vals_max, dtype=torch.float64, device="cuda")
+    ts = torch.tensor(vals_sum, dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+    return [float(x) for x in tm], [float(x) for x in ts]
+
+
+def mc_leg(mp, lib, rank, world, n_total=100_000_000):
+    """configs[4]: 1e8 importance-sampled rollouts sharded by rollout id (Philox keyed by the global id: the
+    shard layout does not change any draw), sums all-reduced.  Device-timed: the rollout kernel's own CUDA events
+    (max over ranks) + the all-reduce between events."""
+    import torch
+    import torch.distributed as dist
+    import bench_configs as bc
+    from mpb200 import _lib, sharding
+    P, CC, _ = bc.c5_problem(mp)
+    a, b = sharding.shard_range(n_total, rank, world)
+    mp.collision_probability(P, CC, 200_000, first=a)       # warm-up
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    res = mp.collision_probability(P, CC, b - a, first=a)
+    k_ms = lib.mpb200_last_ms_of(_lib.OP_OTHER, 0)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    tot = sharding.allreduce_mc(res) if world > 1 else dict(res)
+    e1.record()
+    torch.cuda.synchronize()
+    (k_max, r_max), _ = allreduce_max_sum([k_ms, e0.elapsed_time(e1)], [0.0], world)
+    ms = k_max + (r_max if world > 1 else 0.0)
+    n = max(int(tot["n"]), 1)
+    p = tot["S1"] / n
+    return {"config": "C5 / configs[4]: Monte-Carlo collision probability, T=%d, K=%d, %d rollouts sharded by rollout id x%d + all-reduce of (S1, S2, S0, n, hits)"
+                      % (P.T, P.K, n_total, world),
+            "metric": "rollouts_per_sec", "value": n_total / (ms / 1e3), "unit": "rollouts/s", "ms": ms,
+            "kernel_ms_max_over_ranks": k_max, "allreduce_ms": r_max if world > 1 else 0.0,
+            "rollouts": int(tot["n"]), "hits": int(tot["hits"]), "p": p,
+            "se": (max(tot["S2"] / n - p * p, 0.0) / n) ** 0.5, "S1": tot["S1"],
+            "note": "hits is an integer count and must be identical for every GPU count; S1/S2 agree to summation order"}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -237,6 +437,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the C3/C4/C5 secondary block (N = 1) and the MC leg")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="headline line: weak (N x 1M samples) or strong (1M samples in total); the other one is still reported as a sub-object")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -251,105 +454,68 @@ def main():
     import torch
     import torch.distributed as dist
     import mpb200
-    from mpb200 import _lib
+    from mpb200 import _lib, sharding
 
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = mpb200.init(local)
     # ONE explicit stream for everything in the timed region: the L2 flush, the timing events, the library's
-    # kernels and (N > 1) the NCCL exchange.  (torch's default stream has handle 0, which mpb200_set_stream
+    # kernels and (N > 1) the exchange.  (torch's default stream has handle 0, which mpb200_set_stream
     # reads as "use the library's own non-blocking stream": the flush would then overlap the step.)
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     _lib.check(lib.mpb200_set_stream(_lib.c_vp(stream.cuda_stream)))
-
-    n_total = SAMPLES_PER_GPU * world
-    r = fmt_radius(n_total, 2)
-    samples = make_samples(n_total)
-    if world > 1:
-        # stripe order: each rank's query range is then a spatial stripe and its grid covers only the
-        # stripe + r (FMT* is invariant to the order of i.i.d. samples; N = 1 keeps the raw order)
-        samples = samples[np.argsort(samples[:, 0], kind="stable")]
-    V_host = torch.from_numpy(np.ascontiguousarray(samples)).pin_memory()
-    V = V_host.numpy()
-    q0, q1 = rank * SAMPLES_PER_GPU, (rank + 1) * SAMPLES_PER_GPU
-    CC = mpb200.PointRobot2D(mpb200.obstaclesets.ISRR_2H())
-    SS = mpb200.UnitHypercube(2)
-    CC.handle()
-
-    NN = mpb200.MetricNN(V)
-    NN.set_query_range(q0, q1)
-    NN.handle()  # inputs resident in HBM before the timed region
     flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
-    exchange = None
-    if world > 1:
-        from mpb200 import sharding
-        nnz0 = NN.build_table(r)
-        cap = torch.tensor([nnz0], dtype=torch.int64, device="cuda")
-        dist.all_reduce(cap, op=dist.ReduceOp.MAX)
-        exchange = sharding.ValidityExchange(SAMPLES_PER_GPU, (int(cap) * 21 // 20 + 63) // 64)
 
-    phases = np.zeros(6)
-    edge_ms, point_ms = [], []
-    launches0 = launches1 = 0
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    def build_job(n_total, tag):
+        samples = make_samples(n_total, world > 1)
+        V = torch.from_numpy(samples).pin_memory().numpy()
+        q0, q1 = sharding.shard_range(n_total, rank, world)
+        return Job(mpb200, V, q0, q1, world, tag)
+
+    # ---- the two multi-GPU readings of C2: weak (headline by default) and strong (configs[1] literally)
+    n_weak, n_strong = SAMPLES_PER_GPU * world, SAMPLES_PER_GPU
+    head_n = n_weak if args.scaling == "weak" else n_strong
+    job = build_job(head_n, "head")
+    phases = {"table": np.zeros(5), "points": [], "edges": [], "exchange": []}
     sampler = ClockSampler(local)
-    nnz = 0
-    for it in range(args.warmup + args.steps):
-        if it == args.warmup:
-            torch.cuda.synchronize()
-            if world > 1:
-                dist.barrier()
-            torch.cuda.synchronize()
-            sampler.start()
-            launches0 = lib.mpb200_launch_count()
-            t_wall0 = time.perf_counter()
-        flush.zero_()  # L2 flush between iterations (outside the event pair)
-        if it >= args.warmup:
-            ev[it - args.warmup][0].record(stream)
-        # the three calls of a planning step, issued back to back: only build_table waits (for nnz, once,
-        # between count and fill); the validity calls enqueue their kernels and return
-        NN.points_free(CC, SS, fetch=False)           # K6
-        nnz = NN.build_table(r)                       # K1 + K2
-        NN.edges_free(NN.table, CC, SS, fetch=False, count=False)  # K7
-        if exchange is not None:
-            exchange.run(NN.table)          # NCCL all-gather of shard colptrs + validity words
-        if it >= args.warmup:
-            ev[it - args.warmup][1].record(stream)
-            # per-kernel times of THIS step (events recorded inside the calls, read after the step's end event)
-            phases[:5] += [lib.mpb200_last_ms_of(_lib.OP_TABLE, k) for k in range(5)]
-            point_ms.append(lib.mpb200_last_ms_of(_lib.OP_POINTS, 1))
-            edge_ms.append(lib.mpb200_last_ms_of(_lib.OP_EDGES, 1))
-            if sampler.nv and (it - args.warmup) % 8 == 0:
-                sampler._sample()   # also from this thread, between steps (outside the event pairs): the region is short
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t_wall = time.perf_counter() - t_wall0
-    launches1 = lib.mpb200_launch_count()
+    total_ms, launches, t_wall = timed_steps(job, lib, stream, flush, args.steps, args.warmup, world, sampler, phases)
     clocks = sampler.stop()
-    step_ms = [a.elapsed_time(b) for a, b in ev]
-    total_ms = float(np.sum(step_ms))
-    tt = torch.tensor([total_ms, float(nnz)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        tmax = tt.clone()
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = tt.clone()
-        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        total_ms, edges_all = float(tmax[0]), float(tsum[1])
-    else:
-        edges_all = float(nnz)
-    ms_per_step = total_ms / args.steps
+    nnz = job.nnz
+    (total_ms_max,), (edges_all,) = allreduce_max_sum([total_ms], [float(nnz)], world)
+    ms_per_step = total_ms_max / args.steps
     value = edges_all / (ms_per_step / 1e3)
-    queries_all = SAMPLES_PER_GPU * world
+    parity_cols = parity_check(job, rank, world)
+    (_,), (parity_all,) = allreduce_max_sum([0.0], [float(parity_cols)], world)
+
+    other = None
+    if world > 1:
+        # the other scaling mode, same code path, fewer steps
+        o_n = n_strong if args.scaling == "weak" else n_weak
+        ojob = build_job(o_n, "other")
+        o_steps = max(10, args.steps // 2)
+        o_ms, _, _ = timed_steps(ojob, lib, stream, flush, o_steps, 3, world)
+        (o_max,), (o_edges,) = allreduce_max_sum([o_ms], [float(ojob.nnz)], world)
+        o_par = parity_check(ojob, rank, world, windows=2)
+        (_,), (o_par_all,) = allreduce_max_sum([0.0], [float(o_par)], world)
+        other = {"scaling": "strong" if args.scaling == "weak" else "weak", "n_samples_total": o_n,
+                 "query_columns_per_gpu": o_n // world, "steps": o_steps, "ms_per_step": o_max / o_steps,
+                 "value": o_edges / (o_max / o_steps / 1e3), "unit": UNIT,
+                 "nn_queries_per_sec": o_n / (o_max / o_steps / 1e3), "edges_per_step": o_edges,
+                 "exchange": ojob.exchange_kind, "parity_checked": int(o_par_all)}
+        ojob.close()
+
+    mc = None
+    if not args.no_secondary:
+        mc = mc_leg(mpb200, lib, rank, world)
 
     # ---- auxiliary figure: the SAME samples numbered along a Z-order curve (what mpb200_sample_free's Morton
     # option produces).  FMT* does not care how i.i.d. samples are numbered; the kernels do (column writes and
     # gathers become local).  Reported beside the headline, never instead of it.
     renumbered = None
     if world == 1:
+        V = job.V
         NNm = mpb200.MetricNN(np.ascontiguousarray(V[morton_order(V)]))
         NNm.handle()
         evm = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
@@ -357,9 +523,9 @@ def main():
             flush.zero_()
             if it >= 3:
                 evm[it - 3][0].record(stream)
-            NNm.points_free(CC, SS, fetch=False)
-            nnz_m = NNm.build_table(r)
-            NNm.edges_free(NNm.table, CC, SS, fetch=False, count=False)
+            NNm.points_free(job.CC, job.SS, fetch=False)
+            nnz_m = NNm.build_table(job.r)
+            NNm.edges_free(NNm.table, job.CC, job.SS, fetch=False, count=False)
             if it >= 3:
                 evm[it - 3][1].record(stream)
         torch.cuda.synchronize()
@@ -370,56 +536,62 @@ def main():
 
     # ---- end to end through the public API with HOST buffers (H2D + D2H inside the timed region)
     e2e_times = []
+    V = job.V
     h2d = V.nbytes
     d2h = 0
+    pool = _lib.PinnedPool(reuse=True)    # the benchmark loop's explicit opt-in: result buffers reused across steps
     for it in range(2 + args.e2e_steps):
         NN2 = mpb200.MetricNN(V)          # fresh sample set: H2D of the inputs is inside
-        NN2.pool = NN.pool                # result buffers (pinned) are reused across steps
-        NN2.set_query_range(q0, q1)
+        NN2.pool = pool
+        NN2.set_query_range(job.q0, job.q1)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
-        cache, Eb, _ = NN2.precompute_checked(r, CC, SS)   # H2D samples, fused build, D2H colptr/rowval/nzval/edge bits
-        Fb = NN2.points_free(CC, SS)      # D2H point bits
+        cache, Eb, _ = NN2.precompute_checked(job.r, job.CC, job.SS)   # H2D samples, fused build, D2H colptr/rowval/nzval/edge bits
+        Fb = NN2.points_free(job.CC, job.SS)      # D2H point bits
         t1 = time.perf_counter()
         if it >= 2:
             e2e_times.append(t1 - t0)
         d2h = cache.D.colptr.nbytes + cache.D.rowval.nbytes + cache.D.nzval.nbytes + Fb.nbytes + Eb.nbytes
         NN2.pool = _lib.PinnedPool()
         NN2.close()
-    e2e_t = torch.tensor([float(np.mean(e2e_times))], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e_value = edges_all / float(e2e_t[0])
+    (e2e_s,), _ = allreduce_max_sum([float(np.mean(e2e_times))], [0.0], world)
+    e2e_value = edges_all / e2e_s
 
     if rank == 0:
         peak, peak_kind = peaks()
-        deg = nnz / SAMPLES_PER_GPU
-        fill_ms = phases[4] / args.steps
-        alg_bytes = (8 * 2 + 8 + 16 * deg) * SAMPLES_PER_GPU   # 8d + 8 + 16*deg per query
+        ncols = job.q1 - job.q0
+        deg = nnz / ncols
+        fill_ms = phases["table"][4] / args.steps
+        alg_bytes = (8 * 2 + 8 + 16 * deg) * ncols   # 8d + 8 + 16*deg per query
         achieved = alg_bytes / (fill_ms / 1e3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "C2: FMT* 2-D unit square, ISRR_2H, N=%d uniform samples (%d query columns per GPU), r=%.7f"
-                                   % (n_total, SAMPLES_PER_GPU, r),
+            "config": {"workload": workload_name(head_n, job.r),
                        "l2": "512 MiB flush between timed iterations", "index_type": "int64 (reference ABI)",
                        "parallelism": "query-range shards x%d (samples in stripe order when x > 1), samples+obstacles replicated%s"
-                                      % (world, ", NCCL all-gather of colptr + validity words per step" if world > 1 else "")},
-            "nn_queries_per_sec": queries_all / (ms_per_step / 1e3),
+                                      % (world, ", per step: column lengths + validity words of every rank to every rank (%s)"
+                                         % job.exchange_kind if world > 1 else "")},
+            "nn_queries_per_sec": head_n / (ms_per_step / 1e3),
             "edges_per_step": edges_all, "mean_degree": deg,
-            "phase_ms": {"grid_build": phases[1] / args.steps, "count_scan": phases[2] / args.steps,
-                         "host_gap": phases[3] / args.steps, "fill": fill_ms,
-                         "points_kernel": float(np.mean(point_ms)), "edges_kernels": float(np.mean(edge_ms)),
-                         "inball_total": phases[0] / args.steps},
-            "gpu_launches": int(launches1 - launches0),
+            "phase_ms": {"grid_build": phases["table"][1] / args.steps, "count_scan": phases["table"][2] / args.steps,
+                         "host_gap": phases["table"][3] / args.steps, "fill": fill_ms,
+                         "points_kernel": float(np.mean(phases["points"])), "edges_kernels": float(np.mean(phases["edges"])),
+                         "inball_total": phases["table"][0] / args.steps,
+                         "exchange": float(np.mean(phases["exchange"])) if phases["exchange"] else None},
+            "exchange": job.exchange_kind,
+            "parity_checked": int(parity_all),
+            "gpu_launches": launches,
             "renumbered_samples": renumbered,
+            "strong_scaling" if args.scaling == "weak" else "weak_scaling": other,
+            "mc": mc,
             "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": 1e3 * float(e2e_t[0]), "steps": args.e2e_steps},
+                    "ms_per_step": 1e3 * e2e_s, "steps": args.e2e_steps},
             "roofline": {"kernel": "rball_fill<2>", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": fill_traffic(), "peak_kind": peak_kind,
                          "algorithmic_bytes_per_launch": alg_bytes},
@@ -427,15 +599,42 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             # the oracle port on this box's host cores: full workload, single thread (the reference is
             # single-threaded) -- reported baseline only
-            e1, tb1, tq1 = run_oracle(V, r, 0, SAMPLES_PER_GPU, 1)
+            e1, tb1, tq1 = run_oracle(V, job.r, 0, SAMPLES_PER_GPU, 1)
             line["cpu_baseline"] = {"value": e1 / (tb1 + tq1), "unit": UNIT, "cores": 1, "kind": "port",
                                     "sample": "full workload: kd-tree build %.2fs + %d query columns, %d edges in %.2fs"
                                               % (tb1, SAMPLES_PER_GPU, e1, tq1),
                                     "host_cores_available": host_threads()}
+    job.close()
+    if rank == 0:
+        if world == 1 and not args.no_secondary:
+            line["secondary"] = secondary_block(mpb200, lib)
         print(json.dumps(line), flush=True)
-    NN.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def secondary_block(mp, lib):
+    """BASELINE.json configs C3 / C4 / C5 at full size on this GPU: device-resident time, own roofline, own
+    cpu_baseline (oracle port, bounded sample), parity against the oracle on the sample.  Each entry is
+    self-describing; a failure of one config is reported, not hidden."""
+    import types
+    import bench_configs as bc
+    from oracle import oracle as orc
+    import fixtures as fx
+    from mpb200 import _lib
+    _lib.check(lib.mpb200_release_cached())
+    out = {}
+    args = types.SimpleNamespace(scale=1.0)
+    for name, fn in (("C3", bc.c3), ("C4", bc.c4), ("C5", bc.c5)):
+        try:
+            out[name] = fn(mp, orc, fx, args)
+        except Exception as e:   # noqa: BLE001 -- report and go on: the headline line must still print
+            out[name] = {"config": name, "error": "%s: %s" % (type(e).__name__, e)}
+        _lib.check(lib.mpb200_release_cached())
+    out["peaks"] = {"fp64_dadd_dmul_gops": bc.pipe_peak(lib, 0) / 1e9, "fp64_dfma_gflops": bc.pipe_peak(lib, 1) / 1e9,
+                    "fp32_ffma_gflops": bc.pipe_peak(lib, 2) / 1e9,
+                    "how": "mpb200_pipe_peak: register-resident dependency-free streams on every SM, CUDA-event timed (csrc/peaks.cu)"}
+    return out
 
 
 if __name__ == "__main__":

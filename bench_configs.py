@@ -34,6 +34,40 @@ def timed(f, reps=1):
     return best, out
 
 
+def peaks_json():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
+def pipe_peak(lib, kind):
+    """mpb200_pipe_peak: measured operations / s of an arithmetic pipe (0 = DADD+DMUL no-FMA, 1 = DFMA, 2 = FFMA)"""
+    import ctypes
+    v = ctypes.c_double(0.0)
+    rc = lib.mpb200_pipe_peak(int(kind), ctypes.byref(v))
+    if rc != 0:
+        raise RuntimeError("mpb200_pipe_peak failed")
+    return v.value
+
+
+def table_parity(mp, NN, table, ref, c0, c1):
+    """columns [c0, c1) of a device table against oracle columns ref = (colptr, rowval, nzval): byte-equal.
+    Returns the number of columns checked; raises on a mismatch (a fast table that differs is not a result)."""
+    from mpb200 import sharding
+    colptr, rowval, nzval, _ = sharding.table_device_tensors(table)
+    cp = colptr[c0:c1 + 1].cpu().numpy()
+    lo, hi = int(cp[0]) - 1, int(cp[-1]) - 1
+    rv = rowval[lo:hi].cpu().numpy() if hi > lo else np.zeros(0, dtype=np.int64)
+    nz = nzval[lo:hi].cpu().numpy() if hi > lo else np.zeros(0)
+    ok = (np.array_equal(cp - cp[0], ref[0] - ref[0][0]) and np.array_equal(rv, ref[1])
+          and nz.tobytes() == np.ascontiguousarray(ref[2]).tobytes())
+    if not ok:
+        raise RuntimeError("PARITY FAILURE: device table differs from the oracle on columns [%d, %d)" % (c0, c1))
+    return int(c1 - c0)
+
+
 def c1(mp, orc, fx, args):
     """FMT* 2-D, ISRR_2H, N=1000, end to end (planner included)"""
     N = 1000
@@ -72,16 +106,28 @@ def c3(mp, orc, fx, args):
     ph = [lib.mpb200_last_ms_of(_lib.OP_TABLE, k) for k in range(5)]
     t_e, (_, checks) = timed(lambda: NN.edges_free(NN.table, CC, SS, fetch=False), reps=2)
     # oracle port on a bounded sample of query columns (brute-force truth; the kd-tree degenerates in 10-D)
-    q = 64
+    q = 256
     t_cpu, ref = timed(lambda: orc.rball_brute(V, r, 0, 0, q))
     B = orc.Boxes(boxes)
     So = orc.StateSpace(np.zeros(d), np.ones(d))
     t_cpu_e, _ = timed(lambda: orc.edges_free_csc(B, So, V, ref[0], ref[1], 0))
-    out = dict(config="C3", N=N, d=d, r=r, nnz=int(nnz), mean_degree=nnz / N,
-               nn_gpu_s=t_nn, nn_queries_per_s=N / t_nn, pair_tests_per_s=float(N) * N * 2 / t_nn, phase_ms=ph,
-               edges_gpu_s=t_e, edges_per_s=nnz / t_e, checks=int(checks),
-               cpu_port=dict(sample_queries=q, nn_queries_per_s=q / t_cpu, edges_per_s=len(ref[1]) / max(t_cpu_e, 1e-9),
-                             cores=1, note="brute-force oracle on %d query columns, extrapolated" % q))
+    # parity at full size (bench "parity_checked"): the oracle's brute-force columns against the device table
+    parity = table_parity(mp, NN, NN.table, ref, 0, q)
+    bf16 = peaks_json().get("bf16_tflops_sustained")
+    flops = 2.0 * float(N) * float(N) * d        # the dense contraction 2 N^2 d
+    out = dict(config="C3", workload="10-D unit hypercube, 64 random hyperboxes (seed 20240613), N=%d, r=%.5f: all-pairs r-ball table + box edge checks" % (N, r),
+               N=N, d=d, r=r, nnz=int(nnz), mean_degree=nnz / N,
+               nn_gpu_s=t_nn, nn_queries_per_s=N / t_nn, pair_tests_per_s=float(N) * N / t_nn, phase_ms=ph,
+               edges_gpu_s=t_e, edges_per_s=nnz / t_e, checks=int(checks), parity_checked=parity,
+               metric="nn_queries_per_sec", value=N / t_nn, unit="queries/s",
+               roofline=dict(kernel="tc_rball_kernel<10>", bound="tensor", achieved=flops / t_nn / 1e12, peak=bf16,
+                             unit="TFLOP/s", frac=(flops / t_nn / 1e12 / bf16) if bf16 else None, traffic=None,
+                             peak_kind="measured bf16 sustained (MEASURED_PEAKS.json); the kernel issues TF32 MMAs, whose dense rate is half of bf16",
+                             algorithmic_flops_per_launch=flops,
+                             note="bounded in practice by the TMEM read-back of every FP32 accumulator (DESIGN.md 10), not by the tensor pipe"),
+               cpu_baseline=dict(value=q / t_cpu, unit="queries/s", cores=1, kind="port",
+                                 sample="brute-force oracle on %d of %d query columns; edges %.3g/s on their %d stored edges"
+                                        % (q, N, len(ref[1]) / max(t_cpu_e, 1e-9), len(ref[1]))))
     NN.close()
     return out
 
@@ -111,44 +157,84 @@ def c4(mp, orc, fx, args):
     t_nn, (nF, nB) = timed(lambda: NN.build_tables(r), reps=2)   # best of 2: the first call also allocates
     ph = [lib.mpb200_last_ms_of(_lib.OP_TABLE, k) for k in range(4)]
     t_e, (_, checks) = timed(lambda: NN.lq_edges_free(CC, SS, fetch=False), reps=2)
-    q = 8
+    q = 16
     t_cpu, ref = timed(lambda: L.inball(V, r, False, 0, q))
     C = np.hstack([np.eye(2), np.zeros((2, 2))])
     So = orc.StateSpace(SS.lo, SS.hi, ("matrix", C))
     t_cpu_e, _ = timed(lambda: L.edges_free_csc(orc.Obstacles2D(fx.ISRR_2H), So, r, V, ref[0], ref[1], 0))
-    out = dict(config="C4", N=N, r=r, nnzF=int(nF), nnzB=int(nB), mean_degree=nB / N,
-               nn_gpu_s=t_nn, nn_queries_per_s=2 * N / t_nn, ordered_pairs_per_s=2.0 * N * N * 2 / t_nn, phase_ms=ph,
-               edges_gpu_s=t_e, edges_per_s=nB / t_e, segment_checks=int(checks),
-               cpu_port=dict(sample_queries=q, nn_queries_per_s=q / t_cpu, edges_per_s=len(ref[1]) / max(t_cpu_e, 1e-9),
-                             cores=1, note="oracle on %d backward columns (one direction), extrapolated" % q))
+    parity = table_parity(mp, NN, NN.tableB, ref, 0, q)
+    peak = pipe_peak(lib, 0)                       # measured no-FMA FP64 rate (DADD + DMUL), operations / s
+    ops = 58.0 * 0.5 * float(N) * float(N)         # ~58 non-FMA FP64 operations per unordered pair (stage 1)
+    out = dict(config="C4", workload="double integrator (4-D state), ISRR_2H, N=%d, r=%.5f (mean out-degree ~64): ControlNN tables both directions + swept LQ edge checks" % (N, r),
+               N=N, r=r, nnzF=int(nF), nnzB=int(nB), mean_degree=nB / N,
+               nn_gpu_s=t_nn, nn_queries_per_s=2 * N / t_nn, ordered_pairs_per_s=float(N) * N / t_nn, phase_ms=ph,
+               edges_gpu_s=t_e, edges_per_s=nB / t_e, segment_checks=int(checks), parity_checked=parity,
+               metric="nn_queries_per_sec", value=2 * N / t_nn, unit="queries/s",
+               roofline=dict(kernel="lq_inball_kernel", bound="fp64", achieved=ops / t_nn / 1e9, peak=peak / 1e9, unit="GFLOP/s",
+                             frac=ops / t_nn / peak, traffic=None,
+                             peak_kind="measured live: mpb200_pipe_peak(DADD_DMUL), the no-FMA FP64 rate the parity arithmetic is bound by",
+                             algorithmic_flops_per_launch=ops),
+               cpu_baseline=dict(value=q / t_cpu, unit="queries/s", cores=1, kind="port",
+                                 sample="oracle steer_pairwise on %d of %d backward columns (one direction); edges %.3g/s"
+                                        % (q, N, len(ref[1]) / max(t_cpu_e, 1e-9))))
     NN.close()
     return out
 
 
-def c5(mp, orc, fx, args):
-    """Monte-Carlo collision probability, LQG-tracked double integrator past ISRR_2H, 1e8 rollouts"""
+def c5_problem(mp):
+    """C5's problem (LQG-tracked double integrator past ISRR_2H, T = 100, defensive mixture proposal) -> (P, CC, naive)"""
     T, dt = 100, 0.05
     A = np.block([[np.eye(2), dt * np.eye(2)], [np.zeros((2, 2)), np.eye(2)]])
     B = np.vstack([0.5 * dt * dt * np.eye(2), dt * np.eye(2)])
     C = np.hstack([np.eye(2), np.zeros((2, 2))])
     F, G = mp.montecarlo.lqg_closed_loop(A, B, C, np.eye(4), 0.1 * np.eye(2), 1e-4 * np.eye(4), 1e-4 * np.eye(2), T)
     Wz = np.hstack([np.eye(2), np.zeros((2, 6))])
-    # nominal path: along y = 0.165 under box 2, then up the corridor x = 0.6 between boxes 2 and 5
     s = np.linspace(0, 1, T + 1)
     wbar = np.stack([0.30 + 0.35 * s, 0.135 + 0.0 * s], axis=1)          # 0.055 below box 2
     CC = mp.PointRobot2D(mp.obstaclesets.ISRR_2H(), fixed_point_test=True)
-    P = mp.montecarlo.with_proposal(mp.MCProblem(F, G, Wz, wbar), CC, r2=36.0, max_components=8)
+    naive = mp.MCProblem(F, G, Wz, wbar)
+    P = mp.montecarlo.with_proposal(naive, CC, r2=36.0, max_components=8)
+    return P, CC, naive
+
+
+def mc_flops_per_rollout(P):
+    """algorithmic FP64 operations of one rollout: per step the closed-loop update
+    2 nz^2 + 2 nz q, the workspace map 2 dw nz, q/2 Box-Muller pairs (log 34, sincos 46, sqrt + 4) and the K
+    mixture inner products 2 q K; per rollout K exp (36 each) for the weight."""
+    nz, q, dw, K, T = P.F.shape[1], P.G.shape[2], P.Wz.shape[0], P.K, P.F.shape[0]
+    per_step = 2 * nz * nz + 2 * nz * q + 2 * dw * nz + (q // 2) * (34 + 46 + 6) + 2 * q * K
+    return T * per_step + 36 * K + 2 * K
+
+
+def c5(mp, orc, fx, args):
+    """Monte-Carlo collision probability, LQG-tracked double integrator past ISRR_2H, 1e8 rollouts"""
+    P, CC, naive_problem = c5_problem(mp)
+    T = P.F.shape[0]
     n = int(1e8 * args.scale)
     mp.collision_probability(P, CC, 100_000)
     t, res = timed(lambda: mp.collision_probability(P, CC, n))
     O = orc.Obstacles2D(fx.ISRR_2H, fixed_point_test=True)
     spec = orc.McSpec(P.F, P.G, P.Wz, P.wbar, P.alpha, P.mu if P.K else None)
     nq = 20000
-    t_cpu, ref = timed(lambda: orc.mc_run(spec, O, 20240605, 0, nq))
-    naive = mp.collision_probability(mp.MCProblem(F, G, Wz, wbar), CC, min(n, 10_000_000), seed=7)
-    return dict(config="C5", rollouts=n, T=T, K=P.K, p=res["p"], se=res["se"], hits=res["hits"],
+    t_cpu, ref = timed(lambda: orc.mc_run(spec, O, 20240605, 0, nq, per_rollout=True))
+    naive = mp.collision_probability(naive_problem, CC, min(n, 10_000_000), seed=7)
+    lib = mp.load()
+    peak = pipe_peak(lib, 0)
+    ops = float(mc_flops_per_rollout(P)) * n
+    # parity of the sample against the oracle: per-rollout hit bits and weights byte-equal
+    dev = mp.collision_probability(P, CC, nq, per_rollout=True)
+    same = bool(np.array_equal(dev["hit"], np.asarray(ref["hit"]).astype(bool)) and dev["w"].tobytes() == ref["w"].tobytes())
+    if not same:
+        raise RuntimeError("PARITY FAILURE: Monte-Carlo rollouts differ from the oracle")
+    return dict(config="C5", workload="Monte-Carlo collision probability, LQG-tracked double integrator past ISRR_2H, T=%d, K=%d mixture components, %d rollouts" % (T, P.K, n),
+                rollouts=n, T=T, K=P.K, p=res["p"], se=res["se"], hits=res["hits"],
                 naive_p=naive["p"], naive_se=naive["se"], gpu_s=t, rollouts_per_s=n / t,
-                cpu_port=dict(sample_rollouts=nq, rollouts_per_s=nq / t_cpu, cores=1))
+                metric="rollouts_per_sec", value=n / t, unit="rollouts/s", parity_checked=nq,
+                roofline=dict(kernel="mc_rollout_kernel", bound="fp64", achieved=ops / t / 1e9, peak=peak / 1e9, unit="GFLOP/s",
+                              frac=ops / t / peak, traffic=None,
+                              peak_kind="measured live: mpb200_pipe_peak(DADD_DMUL)", algorithmic_flops_per_launch=ops),
+                cpu_baseline=dict(value=nq / t_cpu, unit="rollouts/s", cores=1, kind="port",
+                                  sample="%d rollouts of the same problem (oracle/mc.c)" % nq))
 
 
 def f1(mp, orc, fx, args):

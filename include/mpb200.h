@@ -251,6 +251,41 @@ int mpb200_mc_collision_probability(const mpb200_mc_problem *p, const mpb200_obs
                                     int64_t first, int64_t n, mpb200_mc_result *out, uint8_t *hit_out,
                                     double *w_out);
 
+/* ---- multi-GPU exchange by direct peer stores (one process per GPU, one box) ----------
+ * The reference has no distributed layer; this is the exchange step of the query-range-sharded
+ * precompute: after a rank has built its table shard and the validity of its
+ * edges, ONE call stores the shard's int32 column lengths and validity words into slot `rank` of
+ * every peer's receive buffer over NVLink (CUDA IPC mapped memory, no NCCL, no staging copies) and
+ * runs a device-side flag barrier, all stream-ordered and asynchronous.
+ *   create  -> allocates this rank's receive buffer (2 alternating sets x world slots) and returns
+ *              its 64-byte CUDA IPC handle; the caller exchanges the handles of all ranks by any
+ *              means (torch.distributed all_gather, MPI, a file) and hands them to connect.
+ *   push    -> enqueue pack + peer stores + barrier for the current contents of `t`
+ *              (needs mpb200_edges_free / mpb200_lq_edges_free on it first).
+ *   view    -> device pointer of the newest complete set: world slots of slot_bytes each;
+ *              slot g = [int64 ncols, int64 nnz, int64 epoch, pad to 64 B | int32 counts at
+ *              counts_off | uint64 validity words at words_off].  With status != NULL the call
+ *              waits for the enqueued pushes and returns 0, or 1 + the rank that never arrived.
+ * A set stays valid until this rank's second-next push. */
+typedef struct mpb200_xchg mpb200_xchg;
+#define MPB200_IPC_HANDLE_BYTES 64
+#define MPB200_XCHG_MAX_WORLD 16
+int mpb200_xchg_create(int rank, int world, int64_t max_ncols, int64_t word_cap, mpb200_xchg **out, void *ipc_handle);
+int mpb200_xchg_connect(mpb200_xchg *x, const void *handles /* world x 64 bytes, rank order */);
+int mpb200_xchg_push(mpb200_xchg *x, const mpb200_table *t);
+int mpb200_xchg_view(const mpb200_xchg *x, void **recv, int64_t *slot_bytes, int64_t *counts_off, int64_t *words_off,
+                     int64_t *status);
+int mpb200_xchg_destroy(mpb200_xchg *x);
+
+/* ---- measured arithmetic-pipe peaks (roofline denominators for the FP64 / FP32 kernels) ----
+ * Runs a register-resident instruction stream on every SM and returns operations per second
+ * (an FMA counts as two), CUDA-event timed.  DADD_DMUL is the no-FMA rate the parity kernels
+ * are bound by (one rounding per operation, as the reference computes). */
+#define MPB200_PEAK_DADD_DMUL 0
+#define MPB200_PEAK_DFMA 1
+#define MPB200_PEAK_FFMA 2
+int mpb200_pipe_peak(int kind, double *ops_per_s);
+
 #ifdef __cplusplus
 }
 #endif

@@ -88,6 +88,12 @@ SIGNATURES = {
     "mpb200_lq_edges_free": (ctypes.c_int, [c_vp, c_vp, c_vp, c_dbl, c_vp, P(SpaceDesc), c_vp, P(c_i64)]),
     "mpb200_mc_collision_probability": (ctypes.c_int, [P(McProblem), c_vp, ctypes.c_uint64, c_i64, c_i64, P(McResult),
                                                        c_vp, c_vp]),
+    "mpb200_xchg_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, c_i64, c_i64, P(c_vp), c_vp]),
+    "mpb200_xchg_connect": (ctypes.c_int, [c_vp, c_vp]),
+    "mpb200_xchg_push": (ctypes.c_int, [c_vp, c_vp]),
+    "mpb200_xchg_view": (ctypes.c_int, [c_vp, P(c_vp), P(c_i64), P(c_i64), P(c_i64), P(c_i64)]),
+    "mpb200_xchg_destroy": (ctypes.c_int, [c_vp]),
+    "mpb200_pipe_peak": (ctypes.c_int, [ctypes.c_int, P(c_dbl)]),
     "mpb200_lq_motions_free": (ctypes.c_int, [c_vp, c_dbl, c_vp, c_vp, c_i64, c_vp, P(SpaceDesc), c_vp, P(c_i64)]),
 }
 
@@ -144,28 +150,52 @@ def ptr(a):
     return a.ctypes.data_as(c_vp)
 
 
-class PinnedPool:
-    """Reusable pinned host buffers for result arrays (D2H at PCIe speed)."""
+class _PinnedBlock:
+    """One cudaMallocHost allocation, freed when the last numpy array over it is collected (the arrays
+    keep this object as their base), so a result array can never outlive its memory."""
 
-    def __init__(self):
+    def __init__(self, nbytes):
+        self.nbytes = int(nbytes)
+        p = c_vp()
+        check(lib().mpb200_host_alloc(self.nbytes, ctypes.byref(p)))
+        self.ptr = p.value
+        self.__array_interface__ = {"shape": (self.nbytes,), "typestr": "|u1", "data": (self.ptr, False), "version": 3}
+
+    def __del__(self):
+        try:
+            if self.ptr and _lib is not None:
+                _lib.mpb200_host_free(c_vp(self.ptr))
+        except Exception:
+            pass
+        self.ptr = None
+
+
+class PinnedPool:
+    """Pinned host result arrays (D2H at PCIe speed).
+
+    Default: every array() call returns a freshly allocated, OWNING array -- it stays valid for as long as
+    the caller keeps it, whatever happens to the sample set, the pool or later precomputes (ImmutableNNC is
+    immutable).  reuse=True is the explicit opt-in of the benchmark loop: arrays with the same key alias ONE
+    buffer that the next request overwrites in place; the memory itself still lives until the last array
+    over it is dropped (reference counted), so even then nothing dangles."""
+
+    def __init__(self, reuse=False):
+        self.reuse = bool(reuse)
         self._bufs = {}
 
     def array(self, key, n, dtype):
         dtype = np.dtype(dtype)
         nbytes = max(int(n) * dtype.itemsize, 8)
-        ent = self._bufs.get(key)
-        if ent is None or ent[1] < nbytes:
-            if ent is not None:
-                check(lib().mpb200_host_free(ent[0]))
-            cap = nbytes + nbytes // 8
-            p = c_vp()
-            check(lib().mpb200_host_alloc(cap, ctypes.byref(p)))
-            ent = (p, cap)
-            self._bufs[key] = ent
-        buf = (ctypes.c_char * ent[1]).from_address(ent[0].value)
-        return np.frombuffer(buf, dtype=dtype, count=int(n))
+        if not self.reuse:
+            if nbytes < (1 << 20):   # small results: a pageable array (pinning costs more than it saves)
+                return np.empty(int(n), dtype=dtype)
+            block = _PinnedBlock(nbytes)
+        else:
+            block = self._bufs.get(key)
+            if block is None or block.nbytes < nbytes:
+                block = _PinnedBlock(nbytes + nbytes // 8)   # the outgrown block is dropped, not freed under its views
+                self._bufs[key] = block
+        return np.asarray(block)[:int(n) * dtype.itemsize].view(dtype)
 
     def release(self):
-        for p, _ in self._bufs.values():
-            load().mpb200_host_free(p)
         self._bufs.clear()

@@ -187,6 +187,7 @@ int lq_motions_free_device(const mpb200_lq *lq, double r, const double *dA, cons
                            const mpb200_obstacles *o, const mpb200_space_desc *ss, uint8_t *d_out,
                            unsigned long long *d_checks);
 
+int pipe_peak_device(int kind, double *ops_per_s);
 int mc_run_device(const mpb200_mc_problem *p, const mpb200_obstacles *o, unsigned long long seed, long long first,
                   long long n, double *h_out4, uint8_t *h_hit, double *h_w);
 
@@ -286,6 +287,16 @@ double mpb200_last_ms_of(int op, int phase) {
     return ctx().last_ms[op][phase];
 }
 double mpb200_last_ms(int phase) { return mpb200_last_ms_of(ctx().bank, phase); }
+
+// Host -> device copy ordered on the library's stream (the block cache hands out parked blocks without
+// waiting, on the premise that ALL buffer traffic is on that one stream), complete on return: the source
+// may be a temporary.
+static int upload_sync(void *dst, const void *src, size_t bytes) {
+    cudaStream_t st = ctx().stream;
+    MPB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+    MPB_CUDA(cudaStreamSynchronize(st));
+    return MPB200_OK;
+}
 
 // ---- samples -----------------------------------------------------------------------
 // bounding box + x-sortedness of a sample set whose V is already on the device; leaves the stream idle
@@ -396,12 +407,15 @@ int mpb200_inball_build(mpb200_samples *s, double r, mpb200_table **table, int64
         if (!t) return fail(MPB200_ENOMEM, "out of host memory");
         fresh = true;
     }
+    t->edge_bits_valid = false;  // bits of an earlier build do not describe the new table
+    t->src_N = s->N;
+    t->src_d = s->d;
     int rc;
     if (s->N == 0) {
         rc = t->colptr.reserve(sizeof(int64_t));
         if (!rc) {
             int64_t one = 1;
-            cudaMemcpy(t->colptr.p, &one, sizeof(one), cudaMemcpyHostToDevice);
+            rc = upload_sync(t->colptr.p, &one, sizeof(one));
             t->ncols = 0; t->col0 = 0; t->nnz = 0; t->r = r; t->euclid = true; t->has_order = false;
         }
     } else if (s->d <= 3 && s->d >= 2) {
@@ -428,7 +442,8 @@ int mpb200_inball_build_checked(mpb200_samples *s, double r, const mpb200_obstac
 int mpb200_table_fetch_edge_bits(const mpb200_table *t, uint64_t *bitchunks) {
     MPB_REQUIRE_INIT();
     MPB_CHECK_ARG(t != nullptr && bitchunks != nullptr, "NULL argument");
-    MPB_CHECK_ARG(t->edge_bits.p != nullptr || t->nnz == 0, "no edge validity has been computed for this table");
+    if (t->nnz > 0 && !(t->edge_bits_valid && t->edge_bits_nnz == t->nnz))
+        return fail(MPB200_ESTATE, "no edge validity has been computed for the current contents of this table");
     const size_t words = (size_t)ceil_div(t->nnz, 64);
     cudaStream_t st = ctx().stream;
     if (words) MPB_CUDA(cudaMemcpyAsync(bitchunks, t->edge_bits.p, sizeof(uint64_t) * words, cudaMemcpyDeviceToHost, st));
@@ -446,7 +461,7 @@ int mpb200_table_device_view(const mpb200_table *t, void **colptr, void **rowval
     if (colptr) *colptr = t->colptr.p;
     if (rowval) *rowval = t->rowval.p;
     if (nzval) *nzval = t->nzval.p;
-    if (edge_bits) *edge_bits = t->edge_bits.p;
+    if (edge_bits) *edge_bits = (t->edge_bits_valid && t->edge_bits_nnz == t->nnz) ? t->edge_bits.p : nullptr;  // never stale bits
     return MPB200_OK;
 }
 int mpb200_table_fetch(const mpb200_table *t, int64_t *colptr, int64_t *rowval, double *nzval) {
@@ -542,8 +557,8 @@ int mpb200_obstacles2d_create(const mpb200_obstacles2d_desc *d, mpb200_obstacles
     o->table_words = base + data_words;
     o->M = 0; o->d = 2;
     int rc = o->table.reserve(sizeof(double) * T.size());
-    if (rc) { delete o; return rc; }
-    MPB_CUDA(cudaMemcpy(o->table.p, T.data(), sizeof(double) * T.size(), cudaMemcpyHostToDevice));
+    if (!rc) rc = upload_sync(o->table.p, T.data(), sizeof(double) * T.size());
+    if (rc) { o->table.release(); delete o; return rc; }
     *out = o;
     return MPB200_OK;
 }
@@ -558,8 +573,8 @@ int mpb200_boxes_create(const double *lo, const double *hi, int M, int d, mpb200
     if (!o) return fail(MPB200_ENOMEM, "out of host memory");
     o->kind = 1; o->M = M; o->d = d; o->table_words = 2 * M * d;
     int rc = o->table.reserve(sizeof(double) * T.size());
-    if (rc) { delete o; return rc; }
-    MPB_CUDA(cudaMemcpy(o->table.p, T.data(), sizeof(double) * T.size(), cudaMemcpyHostToDevice));
+    if (!rc) rc = upload_sync(o->table.p, T.data(), sizeof(double) * T.size());
+    if (rc) { o->table.release(); delete o; return rc; }
     *out = o;
     return MPB200_OK;
 }
@@ -602,10 +617,12 @@ int mpb200_edges_free(const mpb200_samples *s, const mpb200_table *t_, const mpb
     MPB_REQUIRE_INIT();
     MPB_CHECK_ARG(s != nullptr && t_ != nullptr, "NULL handle");
     mpb200_table *t = const_cast<mpb200_table *>(t_);
+    MPB_CHECK_ARG(t->src_N == s->N && t->src_d == s->d, "the table was not built from this sample set");
     Context &c = ctx();
     cudaStream_t st = c.stream;
     const size_t words = (size_t)ceil_div(t->nnz, 64);
     if (int rc = t->edge_bits.reserve(sizeof(uint64_t) * (words + 1))) return rc;
+    t->edge_bits_valid = false;
     phase_bank(MPB200_OP_EDGES);
     phase_mark(0);
     MPB_CUDA(cudaMemsetAsync(t->edge_bits.p, 0, sizeof(uint64_t) * (words + 1), st));
@@ -613,6 +630,8 @@ int mpb200_edges_free(const mpb200_samples *s, const mpb200_table *t_, const mpb
     if (int rc = edges_free_device(s->V.as<double>(), s->d, t, o, ss, t->edge_bits.as<uint32_t>(),
                                    reinterpret_cast<unsigned long long *>(c.d_scalar + 4)))
         return rc;
+    t->edge_bits_valid = true;
+    t->edge_bits_nnz = t->nnz;
     phase_mark(1);
     phases_collect(1);
     if (bitchunks || checks) {  // both NULL: asynchronous, the bits stay on the device
@@ -704,6 +723,9 @@ int mpb200_lq_inball_build(mpb200_samples *s, const mpb200_lq *lq, double r, mpb
     if (!tF) tF = new (std::nothrow) mpb200_table();
     if (!tB) tB = new (std::nothrow) mpb200_table();
     if (!tF || !tB) return fail(MPB200_ENOMEM, "out of host memory");
+    tF->edge_bits_valid = tB->edge_bits_valid = false;
+    tF->src_N = tB->src_N = s->N;
+    tF->src_d = tB->src_d = s->d;
     int rc = lq_inball_build(s, lq, r, tF, tB);
     if (rc) {
         if (freshF) mpb200_table_destroy(tF);
@@ -744,10 +766,12 @@ int mpb200_lq_edges_free(const mpb200_samples *s, const mpb200_table *t_, const 
     MPB_REQUIRE_INIT();
     MPB_CHECK_ARG(s && t_ && lq && o, "NULL handle");
     mpb200_table *t = const_cast<mpb200_table *>(t_);
+    MPB_CHECK_ARG(t->src_N == s->N && t->src_d == s->d, "the table was not built from this sample set");
     Context &c = ctx();
     cudaStream_t st = c.stream;
     const size_t words = (size_t)ceil_div(t->nnz, 64);
     if (int rc = t->edge_bits.reserve(sizeof(uint64_t) * (words + 1))) return rc;
+    t->edge_bits_valid = false;
     phase_bank(MPB200_OP_EDGES);
     phase_mark(0);
     MPB_CUDA(cudaMemsetAsync(t->edge_bits.p, 0, sizeof(uint64_t) * (words + 1), st));
@@ -755,6 +779,8 @@ int mpb200_lq_edges_free(const mpb200_samples *s, const mpb200_table *t_, const 
     if (int rc = lq_edges_free_device(s, t, lq, r, o, ss, t->edge_bits.as<uint32_t>(),
                                       reinterpret_cast<unsigned long long *>(c.d_scalar + 4)))
         return rc;
+    t->edge_bits_valid = true;
+    t->edge_bits_nnz = t->nnz;
     phase_mark(1);
     phases_collect(1);
     if (bitchunks || checks) {  // both NULL: asynchronous, the bits stay on the device
@@ -792,6 +818,13 @@ int mpb200_lq_motions_free(const mpb200_lq *lq, double r, const double *v, const
     MPB_CUDA(cudaStreamSynchronize(st));
     if (checks) *checks = c.h_scalar[5];
     return MPB200_OK;
+}
+
+int mpb200_pipe_peak(int kind, double *ops_per_s) {
+    MPB_REQUIRE_INIT();
+    MPB_CHECK_ARG(ops_per_s != nullptr, "ops_per_s is NULL");
+    MPB_CHECK_ARG(kind >= MPB200_PEAK_DADD_DMUL && kind <= MPB200_PEAK_FFMA, "unknown peak kind");
+    return pipe_peak_device(kind, ops_per_s);
 }
 
 // ---- Monte-Carlo collision probability ---------------------------------------------------------

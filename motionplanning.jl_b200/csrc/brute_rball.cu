@@ -150,7 +150,8 @@ static int brute_build(mpb200_samples *s, double r, mpb200_table *t) {
     // tensor-core prefilter (tc_rball.cu) for 4 <= d <= 14; MPB200_NO_TC=1 selects the FP32 CUDA-core sweep
     static const bool no_tc = getenv("MPB200_NO_TC") != nullptr;
     constexpr bool kTcDim = (D >= 4 && D <= 14);
-    const bool use_tc = kTcDim && !no_tc;
+    // ... and it is used only while its error band stays tight: otherwise the CUDA-core form
+    const bool use_tc = kTcDim && !no_tc && tc_band_is_tight(s, r);
     TcPlan plan = {nullptr, nullptr, 0, 0.0f};
     phase_bank(MPB200_OP_TABLE);
     phase_mark(0);

@@ -103,6 +103,10 @@ struct mpb200_table {
     mpb::DevBuf col_list;  // int32 ncols + counter: columns that need per-edge checks
     mpb::DevBuf col_order; // int32 ncols: the shard's columns in grid-cell order (spatially coherent warps)
     bool has_order = false;
+    bool edge_bits_valid = false;  // edge_bits describes the CURRENT table contents (cleared by every build)
+    int64_t edge_bits_nnz = 0;
+    int64_t src_N = -1;            // the sample set the table was built from (rowval addresses its samples)
+    int src_d = 0;
 };
 
 struct mpb200_samples {

@@ -1,0 +1,77 @@
+// peaks.cu -- measured arithmetic-pipe peaks of the device this process drives.
+//
+// MEASURED_PEAKS.json (driver-written) holds an HBM copy bandwidth and a bf16 tensor peak only; the
+// FP64 kernels of this library (K5 ControlNN tables, K9 LQ edges, K10 Monte-Carlo rollouts) are bound
+// by the FP64 CUDA-core pipe, and the parity rule (one rounding per operation) forbids FMA contraction
+// in them, so their roofline denominator is the NO-FMA rate: separate DADD and DMUL instructions.
+// mpb200_pipe_peak runs a register-resident dependency-free instruction stream per kind and returns
+// operations per second (an FMA counts as 2), timed with CUDA events on the launching stream:
+//   MPB200_PEAK_DADD_DMUL  alternating __dadd_rn / __dmul_rn   (what the parity kernels can reach)
+//   MPB200_PEAK_DFMA       __fma_rn double                     (the advertised FP64 figure / 2 per FMA)
+//   MPB200_PEAK_FFMA       __fmaf_rn                           (FP32 CUDA-core peak, for the FP32 prefilter)
+#include "common.cuh"
+
+namespace mpb {
+
+constexpr int kPeakChains = 8;      // independent accumulators per thread (covers the pipe latency)
+constexpr int kPeakInner = 64;      // unrolled operations per chain per outer iteration
+
+template <int KIND>
+__global__ void __launch_bounds__(256) pipe_peak_kernel(int iters, double seed, double *__restrict__ sink) {
+    double a[kPeakChains];
+    float f[kPeakChains];
+#pragma unroll
+    for (int c = 0; c < kPeakChains; ++c) {
+        a[c] = seed + 1e-3 * (threadIdx.x + c);
+        f[c] = (float)a[c];
+    }
+    const double m = 1.0000001, s = 1e-9;
+    const float mf = 1.0000001f, sf = 1e-9f;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < kPeakInner; ++k) {
+#pragma unroll
+            for (int c = 0; c < kPeakChains; ++c) {
+                if (KIND == MPB200_PEAK_DADD_DMUL) a[c] = (k & 1) ? __dmul_rn(a[c], m) : __dadd_rn(a[c], s);
+                if (KIND == MPB200_PEAK_DFMA) a[c] = __fma_rn(a[c], m, s);
+                if (KIND == MPB200_PEAK_FFMA) f[c] = __fmaf_rn(f[c], mf, sf);
+            }
+        }
+    }
+    double t = 0;
+#pragma unroll
+    for (int c = 0; c < kPeakChains; ++c) t += a[c] + (double)f[c];
+    if (t == 123.456) sink[0] = t;  // never true: keeps the chains alive
+}
+
+int pipe_peak_device(int kind, double *ops_per_s) {
+    Context &c = ctx();
+    cudaStream_t st = c.stream;
+    static DevBuf sink;
+    if (int rc = sink.reserve(64)) return rc;
+    const int blocks = c.sm_count * 8, iters = 400;
+    cudaEvent_t e0, e1;
+    MPB_CUDA(cudaEventCreate(&e0));
+    MPB_CUDA(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {  // first repetition warms up; best of the rest
+        MPB_CUDA(cudaEventRecord(e0, st));
+        if (kind == MPB200_PEAK_DADD_DMUL) pipe_peak_kernel<MPB200_PEAK_DADD_DMUL><<<blocks, 256, 0, st>>>(iters, 1.0, sink.as<double>());
+        else if (kind == MPB200_PEAK_DFMA) pipe_peak_kernel<MPB200_PEAK_DFMA><<<blocks, 256, 0, st>>>(iters, 1.0, sink.as<double>());
+        else pipe_peak_kernel<MPB200_PEAK_FFMA><<<blocks, 256, 0, st>>>(iters, 1.0, sink.as<double>());
+        MPB_LAUNCHED();
+        MPB_CUDA(cudaEventRecord(e1, st));
+        MPB_CUDA(cudaEventSynchronize(e1));
+        float ms = 0;
+        MPB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    const double per_op = (kind == MPB200_PEAK_DADD_DMUL) ? 1.0 : 2.0;
+    const double ops = (double)blocks * 256.0 * iters * kPeakInner * kPeakChains * per_op;
+    *ops_per_s = ops / (best * 1e-3);
+    return 0;
+}
+
+}  // namespace mpb

@@ -265,17 +265,34 @@ static float tc_delta(double r, int D, double Rmax2) {
 }
 
 
-template <int D>
-int tc_prepare_operands(mpb200_samples *s, double r, TcPlan *plan) {
-    Context &c = ctx();
-    cudaStream_t st = c.stream;
-    const int64_t N = s->N, Npad = (N + 127) & ~int64_t(127);
-    double center[16], Rmax2 = 0;
+// centre of the samples' bounding box and the squared radius of the centred cloud
+static double tc_center(const mpb200_samples *s, int D, double *center) {
+    double Rmax2 = 0;
     for (int k = 0; k < D; ++k) {
         center[k] = 0.5 * (s->h_bbox[k] + s->h_bbox[D + k]);
         const double h = fmax(fabs(s->h_bbox[k] - center[k]), fabs(s->h_bbox[D + k] - center[k]));
         Rmax2 += h * h;
     }
+    return Rmax2;
+}
+
+// The tensor-core test accepts  s <= r^2 + 2 delta.  When 2 delta is not small against r^2 (a wide, sparse
+// cloud with a small radius) nearly every 32-column chunk becomes a candidate and the exact recheck does the
+// all-pairs work: correct, but slower than the FP32 CUDA-core sweep, whose slack scales with |x| r instead of
+// |x|^2.  The caller then takes that path.
+bool tc_band_is_tight(const mpb200_samples *s, double r) {
+    double center[16];
+    const double Rmax2 = tc_center(s, s->d, center);
+    return 2.0 * (double)tc_delta(r, s->d, Rmax2) <= 0.25 * r * r;
+}
+
+template <int D>
+int tc_prepare_operands(mpb200_samples *s, double r, TcPlan *plan) {
+    Context &c = ctx();
+    cudaStream_t st = c.stream;
+    const int64_t N = s->N, Npad = (N + 127) & ~int64_t(127);
+    double center[16];
+    const double Rmax2 = tc_center(s, D, center);
     if (int rc = s->sorted_pos.reserve(sizeof(float) * (size_t)(kTcK + 1) * (size_t)Npad + 256)) return rc;
     if (int rc = s->aux.reserve(sizeof(double) * 32)) return rc;
     float *opB = s->sorted_pos.as<float>();

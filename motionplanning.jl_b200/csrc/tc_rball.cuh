@@ -10,6 +10,8 @@ struct TcPlan {
     int64_t Npad;
     float delta;       // error allowance of the tensor-core test quantity
 };
+// false: the error allowance of the TF32 test is not small against r^2 -- use the FP32 CUDA-core prefilter instead
+bool tc_band_is_tight(const mpb200_samples *s, double r);
 template <int D> int tc_prepare_operands(mpb200_samples *s, double r, TcPlan *plan);
 // sweep the first nq_run query columns of the shard; cap > 0: also append hits to the slabs
 template <int D> int tc_sweep(mpb200_samples *s, const TcPlan &P, double r, int64_t nq_run, int *counts, int cap,

@@ -136,49 +136,135 @@ def table_device_tensors(table):
             device_tensor(eb.value, words, "<i8") if (eb.value and words) else None)
 
 
+def _assemble(world, slots_counts, slots_words, ncols_of):
+    """global 1-based colptr + BitVector chunks from per-rank (int32 counts, uint64 words)"""
+    counts = [np.asarray(slots_counts[g][:ncols_of[g]], dtype=np.int64) for g in range(world)]
+    allc = np.concatenate(counts) if counts else np.zeros(0, dtype=np.int64)
+    colptr = np.empty(len(allc) + 1, dtype=np.int64)
+    colptr[0] = 1
+    np.cumsum(allc, out=colptr[1:])
+    colptr[1:] += 1
+    parts = [(slots_words[g], int(counts[g].sum())) for g in range(world)]
+    return colptr, concat_bitvectors(parts)
+
+
 class ValidityExchange:
-    """Reusable buffers for the per-step exchange the host planner needs from every GPU: the
-    shard column lengths and the edge-validity words (padded to a common capacity), packed into
-    ONE all-gather per step: [ncols x int32 counts | cap x uint64 words] per rank (the Int64 colptr
-    is a prefix sum the receiver redoes; sending 4-byte counts instead of 8-byte offsets cuts the
-    payload by a third).  Measured alternative: sending the lengths on a side stream under the edge
-    kernels and the words afterwards (two collectives) -- 0.93 ms per step on 8 GPUs against 0.84 ms for
-    the single packed all-gather; the per-collective latency outweighs the overlap."""
+    """NCCL / gloo form of the per-step exchange the host planner needs from every GPU (the fallback when CUDA IPC
+    peer mapping is unavailable, and the form the CPU tests exercise): the shard column lengths and the
+    edge-validity words, packed into ONE all-gather per step: [int64 ncols | int32 counts x max_ncols | uint64 words
+    x cap] per rank.  Shards may have different column counts (N % world != 0): the capacities are agreed
+    collectively (all-reduce MAX) at construction and each rank's true ncols travels in the payload."""
 
     def __init__(self, ncols, word_capacity, group=None):
         self.group = group
         self.world = dist.get_world_size(group)
-        dev = torch.device("cuda", torch.cuda.current_device())
-        self.ncols = int(ncols)
-        self.cap = int(word_capacity)
+        dev = _dev()
+        caps = torch.tensor([int(ncols), int(word_capacity)], dtype=torch.int64, device=dev)
+        dist.all_reduce(caps, op=dist.ReduceOp.MAX, group=group)   # every rank enters this: no rank can run ahead alone
+        self.ncols = int(caps[0])                                   # capacity in columns (max over ranks)
+        self.cap = int(caps[1])
         self.cnt_words = (self.ncols + 1) // 2            # int32 counts, padded to whole 8-byte words
-        self.stride = self.cnt_words + self.cap           # int64 words per rank
+        self.stride = 1 + self.cnt_words + self.cap       # int64 words per rank
         self.send = torch.zeros(self.stride, dtype=torch.int64, device=dev)
         self.recv = torch.empty(self.world * self.stride, dtype=torch.int64, device=dev)
+
+    def run_arrays(self, colptr, words):
+        """colptr: int64 tensor (ncols_g + 1); words: int64 tensor of validity words or None"""
+        n = colptr.numel() - 1
+        if n > self.ncols:
+            raise RuntimeError("validity exchange built for <= %d columns per rank, table has %d" % (self.ncols, n))
+        if words is not None and words.numel() > self.cap:
+            raise RuntimeError("validity exchange capacity exceeded")
+        self.send[0] = n
+        counts = self.send[1:1 + self.cnt_words].view(torch.int32)[:n]
+        counts.copy_(colptr[1:] - colptr[:-1])             # int64 differences -> int32 (column lengths fit easily)
+        if words is not None:
+            self.send[1 + self.cnt_words:1 + self.cnt_words + words.numel()].copy_(words)
+        dist.all_gather_into_tensor(self.recv, self.send, group=self.group)
 
     def run(self, table):
         """Stream-ordered on torch's current stream: either make that the library's launching stream
         (mpb200_set_stream) or use the waiting forms of the validity calls before calling this."""
         colptr, _, _, words = table_device_tensors(table)
-        if colptr.numel() != self.ncols + 1:
-            raise RuntimeError("validity exchange built for %d columns, table has %d" % (self.ncols, colptr.numel() - 1))
-        counts = self.send[:self.cnt_words].view(torch.int32)[:self.ncols]
-        counts.copy_(colptr[1:] - colptr[:-1])             # int64 differences -> int32 (column lengths fit easily)
-        if words is not None:
-            if words.numel() > self.cap:
-                raise RuntimeError("validity exchange capacity exceeded")
-            self.send[self.cnt_words:self.cnt_words + words.numel()].copy_(words)
-        dist.all_gather_into_tensor(self.recv, self.send, group=self.group)
+        self.run_arrays(colptr, words)
 
     def assemble(self):
         """host-side: global colptr + BitVector chunks from the gathered shards"""
         buf = self.recv.cpu().numpy().reshape(self.world, self.stride)
-        counts = np.concatenate([buf[g, :self.cnt_words].view(np.int32)[:self.ncols].astype(np.int64)
-                                 for g in range(self.world)])
-        colptr = np.empty(len(counts) + 1, dtype=np.int64)
-        colptr[0] = 1
-        np.cumsum(counts, out=colptr[1:])
-        colptr[1:] += 1
-        per_rank = counts.reshape(self.world, self.ncols).sum(axis=1)
-        parts = [(buf[g, self.cnt_words:].view(np.uint64), int(per_rank[g])) for g in range(self.world)]
-        return colptr, concat_bitvectors(parts)
+        ncols_of = [int(buf[g, 0]) for g in range(self.world)]
+        counts = [buf[g, 1:1 + self.cnt_words].view(np.int32) for g in range(self.world)]
+        words = [buf[g, 1 + self.cnt_words:].view(np.uint64) for g in range(self.world)]
+        return _assemble(self.world, counts, words, ncols_of)
+
+
+class PeerExchange:
+    """The same exchange as direct peer stores over NVLink (mpb200_xchg_*, csrc/xchg.cu): one pack-and-store kernel
+    + a device-side flag barrier per step, no NCCL call and no staging copies in the data path.  torch.distributed
+    is used once, at construction, to agree on capacities and to swap the CUDA IPC handles."""
+
+    def __init__(self, ncols, word_capacity, group=None):
+        import ctypes
+        from . import _lib
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        caps = torch.tensor([int(ncols), int(word_capacity)], dtype=torch.int64, device=_dev())
+        dist.all_reduce(caps, op=dist.ReduceOp.MAX, group=group)
+        self.ncols, self.cap = int(caps[0]), int(caps[1])
+        lib = _lib.lib()
+        self.h = _lib.c_vp()
+        handle = (ctypes.c_char * 64)()
+        _lib.check(lib.mpb200_xchg_create(self.rank, self.world, self.ncols, self.cap, ctypes.byref(self.h), handle))
+        mine = torch.frombuffer(bytearray(bytes(handle)), dtype=torch.uint8).to(_dev())
+        allh = torch.empty(self.world * 64, dtype=torch.uint8, device=mine.device)
+        dist.all_gather_into_tensor(allh, mine, group=group)
+        blob = bytes(allh.cpu().numpy().tobytes())
+        buf = (ctypes.c_char * len(blob)).from_buffer_copy(blob)
+        _lib.check(lib.mpb200_xchg_connect(self.h, buf))
+        dist.barrier(group=group)   # every rank has mapped every buffer before the first push
+
+    def run(self, table):
+        from . import _lib
+        _lib.check(_lib.lib().mpb200_xchg_push(self.h, table.h))
+
+    def assemble(self):
+        import ctypes
+        from . import _lib
+        recv, slot, coff, woff, status = _lib.c_vp(), _lib.c_i64(), _lib.c_i64(), _lib.c_i64(), _lib.c_i64()
+        _lib.check(_lib.lib().mpb200_xchg_view(self.h, ctypes.byref(recv), ctypes.byref(slot), ctypes.byref(coff),
+                                               ctypes.byref(woff), ctypes.byref(status)))
+        if status.value:
+            raise RuntimeError("peer exchange: rank %d never arrived at the barrier" % (status.value - 1))
+        raw = device_tensor(recv.value, self.world * slot.value, "|u1").cpu().numpy().reshape(self.world, slot.value)
+        ncols_of = [int(raw[g, :8].view(np.int64)[0]) for g in range(self.world)]
+        counts = [raw[g, coff.value:coff.value + 4 * self.ncols].view(np.int32) for g in range(self.world)]
+        words = [raw[g, woff.value:woff.value + 8 * self.cap].view(np.uint64) for g in range(self.world)]
+        return _assemble(self.world, counts, words, ncols_of)
+
+    def close(self):
+        from . import _lib
+        if self.h:
+            torch.cuda.synchronize()
+            dist.barrier(group=self.group)   # no peer may still be storing into a buffer that is about to be freed
+            _lib.load().mpb200_xchg_destroy(self.h)
+            self.h = _lib.c_vp()
+
+
+def make_exchange(ncols, word_capacity, group=None, kind=None):
+    """PeerExchange when the GPUs can map each other's memory, else the NCCL all-gather form.  The choice is
+    collective (all ranks agree).  kind = "peer" / "nccl" forces one."""
+    import os
+    kind = kind or os.environ.get("MPB200_EXCHANGE", "auto")
+    if kind != "nccl" and dist.get_backend(group) == "nccl":
+        ok = torch.ones(1, dtype=torch.int64, device=_dev())
+        ex = None
+        try:
+            ex = PeerExchange(ncols, word_capacity, group)
+        except Exception:
+            if kind == "peer":
+                raise
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok):
+            return ex
+    return ValidityExchange(ncols, word_capacity, group)

@@ -158,4 +158,8 @@ def is_free_path(path, CC, SS=None):
     P = _states(path)
     if P.shape[0] < 2:
         return True
+    if SS is not None and not isinstance(SS.dist, Euclidean):
+        # is_free_motion(p[i], p[i+1], CC, SS) per pair: the waypoints of the optimal trajectory, not a chord
+        from .linearquadratic import lq_motions_free
+        return bool(np.all(lq_motions_free(P[:-1], P[1:], CC, SS)))
     return bool(np.all(segments_free(P[:-1], P[1:], CC, SS)))

@@ -11,7 +11,7 @@ r = fmt_radius(N, 2)
 V_host = torch.from_numpy(np.ascontiguousarray(make_samples(N))).pin_memory()
 V = V_host.numpy()
 CC = mpb200.PointRobot2D(mpb200.obstaclesets.ISRR_2H()); SS = mpb200.UnitHypercube(2); CC.handle()
-pool = _lib.PinnedPool()
+pool = _lib.PinnedPool(reuse=True)
 def T():
     lib.mpb200_synchronize(); return time.perf_counter()
 # raw PCIe numbers with the library's pinned buffers
@@ -28,6 +28,6 @@ for it in range(4):
     D = NN.fetch_table(NN.table); t.append(T())
     Eb = NN.fetch_edge_bits(); t.append(T())
     Fb = NN.points_free(CC, SS); t.append(T())
-    NN.pool = _lib.PinnedPool(); NN.close(); t.append(T())
+    NN.pool = _lib.PinnedPool(reuse=True); NN.close(); t.append(T())
     names = ["create+H2D", "build_checked", "fetch_table", "fetch_edge_bits", "points_free+D2H", "close"]
     print("  ".join("%s %.2f" % (n, (b - a) * 1e3) for n, a, b in zip(names, t[:-1], t[1:])), " total(ex close) %.2f ms" % ((t[-2] - t[0]) * 1e3))

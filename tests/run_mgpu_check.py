@@ -21,32 +21,34 @@ def main():
     from mpb200 import _lib, sharding
     import fixtures as fx
     lib = mpb200.init(local)
-    _lib.check(lib.mpb200_set_stream(_lib.c_vp(torch.cuda.current_stream().cuda_stream)))
-    N = 200_000
+    stream = torch.cuda.Stream()                           # one explicit stream for the library AND torch (as bench.py)
+    torch.cuda.set_stream(stream)
+    _lib.check(lib.mpb200_set_stream(_lib.c_vp(stream.cuda_stream)))
+    N = 200_001                                            # uneven shards on purpose
     V = fx.uniform_samples(N, 2, 4242)
+    V = V[np.argsort(V[:, 0], kind="stable")]              # stripe order, as bench.py shards
     r = fx.fmt_radius(N, 2)
     q0, q1 = sharding.shard_range(N, rank, world)
     NN = mpb200.MetricNN(V)
     NN.set_query_range(q0, q1)
-    nnz = NN.build_table(r)
     CC = mpb200.PointRobot2D(mpb200.obstaclesets.ISRR_2H())
     SS = mpb200.UnitHypercube(2)
-    NN.edges_free(NN.table, CC, SS, fetch=False)
-    cap = torch.tensor([nnz], dtype=torch.int64, device="cuda")
-    dist.all_reduce(cap, op=dist.ReduceOp.MAX)
-    ncols = torch.tensor([q1 - q0], dtype=torch.int64, device="cuda")
-    dist.all_reduce(ncols, op=dist.ReduceOp.MIN)
     ok = True
-    if int(ncols) == q1 - q0 and N % world == 0:           # equal shards: the device-resident exchange
-        ex = sharding.ValidityExchange(q1 - q0, (int(cap) + 63) // 64)
-        ex.run(NN.table)
+    results = {}
+    for kind in ("peer", "nccl"):                          # direct peer stores (csrc/xchg.cu) and the NCCL all-gather form
+        nnz = NN.build_table(r)
+        NN.edges_free(NN.table, CC, SS, fetch=False)
+        ex = sharding.make_exchange(q1 - q0, (nnz + 63) // 64 + 1, kind=kind)
+        for _ in range(3):                                 # several epochs: the alternating buffer sets and the flag barrier
+            NN.build_table(r)
+            NN.edges_free(NN.table, CC, SS, fetch=False, count=False)
+            ex.run(NN.table)
         torch.cuda.synchronize()
-        gcol, gbits = ex.assemble()
-    else:                                                  # uneven shards: host path
-        D = NN.fetch_table(NN.table)
-        bits, _ = NN.edges_free(NN.table, CC, SS)
-        gcol, _ = sharding.allgather_colptr(D.colptr)
-        gbits = sharding.allgather_bits(bits, D.nnz)
+        results[kind] = ex.assemble()
+        if hasattr(ex, "close"):
+            ex.close()
+    gcol, gbits = results["peer"]
+    ok = ok and np.array_equal(gcol, results["nccl"][0]) and np.array_equal(gbits, results["nccl"][1])
     # MC: shard the rollout ids, reduce in rank order
     Bx = mpb200.PointRobotNDBoxes([mpb200.BoxBounds(np.array([0.5, -10.0]), np.array([10.0, 10.0]))])
     P = mpb200.MCProblem(np.eye(2)[None], (np.eye(2) * 0.1)[None], np.eye(2), np.array([[0.2, 0.0]] * 2), [0.3, 0.7],
@@ -59,7 +61,7 @@ def main():
         fc, fr, fz = orc.KDTree(V).rball(r)
         fv, _ = orc.edges_free_csc(orc.Obstacles2D(fx.ISRR_2H), orc.StateSpace([0, 0], [1, 1]), V, fc, fr)
         got = np.unpackbits(gbits.view(np.uint8), bitorder="little")[:len(fv)]
-        ok = np.array_equal(gcol, fc) and np.array_equal(got, fv)
+        ok = ok and np.array_equal(gcol, fc) and np.array_equal(got, fv)
         whole = mpb200.collision_probability(P, Bx, n_tot, seed=9)
         ok = ok and mc["hits"] == whole["hits"] and abs(mc["S1"] - whole["S1"]) <= 1e-12 * whole["S1"]
         print("MGPU_OK" if ok else "MGPU_FAIL", "world", world, "nnz", len(fv), "mc_p", mc["p"], flush=True)

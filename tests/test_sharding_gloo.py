@@ -35,11 +35,17 @@ def _worker(rank, world, port, tmp):
     gcol, offs = sharding.allgather_colptr(colptr)
     gbits = sharding.allgather_bits(chunks, len(valid))
     grow, gnz = sharding.allgather_table(rowval, nzval)
+    # the packed per-step exchange with UNEVEN shards (4001 columns over 2 ranks): capacities agreed collectively,
+    # true column counts in the payload
+    import torch
+    ex = sharding.ValidityExchange(q1 - q0, (len(valid) + 63) // 64)
+    ex.run_arrays(torch.from_numpy(colptr.copy()), torch.from_numpy(chunks.view(np.int64).copy()))
+    xcol, xbits = ex.assemble()
     mc = sharding.allreduce_mc(dict(S1=0.1 * (rank + 1), S2=0.01 * (rank + 1), S0=10.0 + rank, n=10, hits=rank + 1))
     # reference: the unsharded oracle
     fc, fr, fz = tree.rball(r)
     fv, _ = orc.edges_free_csc(O, So, V, fc, fr)
-    ok = (np.array_equal(gcol, fc) and np.array_equal(grow, fr) and gnz.tobytes() == fz.tobytes()
+    ok = (np.array_equal(gcol, fc) and np.array_equal(xcol, fc) and np.array_equal(xbits, gbits) and np.array_equal(grow, fr) and gnz.tobytes() == fz.tobytes()
           and np.array_equal(np.unpackbits(gbits.view(np.uint8), bitorder="little")[:len(fv)], fv)
           and offs[rank] == fc[q0] - 1 and mc["n"] == 10 * world and mc["hits"] == sum(range(1, world + 1))
           and abs(mc["S1"] - 0.1 * sum(range(1, world + 1))) < 1e-15)
@@ -86,30 +92,34 @@ def test_world2_gloo_allgathers(tmp_path):
 
 
 def test_validity_exchange_wire_format_roundtrip():
-    """ValidityExchange packs [int32 column lengths | uint64 validity words] per rank; assemble() must rebuild
-    the global colptr and the concatenated BitVector from the gathered buffer (host logic, no GPU/NCCL)."""
+    """ValidityExchange packs [int64 ncols | int32 column lengths | uint64 validity words] per rank; assemble() must
+    rebuild the global colptr and the concatenated BitVector from the gathered buffer, with a different column
+    count on every rank (host logic, no GPU/NCCL)."""
     import torch
     from mpb200 import sharding
     rng = np.random.Generator(np.random.PCG64(5))
-    world, ncols = 3, 7                                  # odd column count: the int32 block is padded to 8 bytes
-    counts = rng.integers(0, 40, size=(world, ncols)).astype(np.int64)
-    nnz = counts.sum(axis=1)
-    cap = int((nnz.max() + 63) // 64) + 2
+    world, cap_cols = 3, 7                               # odd capacity: the int32 block is padded to 8 bytes
+    ncols_of = [7, 6, 4]
+    counts = [rng.integers(0, 40, size=n).astype(np.int64) for n in ncols_of]
+    nnz = [int(c.sum()) for c in counts]
+    cap = (max(nnz) + 63) // 64 + 2
     ex = sharding.ValidityExchange.__new__(sharding.ValidityExchange)
-    ex.world, ex.ncols, ex.cap = world, ncols, cap
-    ex.cnt_words = (ncols + 1) // 2
-    ex.stride = ex.cnt_words + cap
+    ex.world, ex.ncols, ex.cap = world, cap_cols, cap
+    ex.cnt_words = (cap_cols + 1) // 2
+    ex.stride = 1 + ex.cnt_words + cap
     buf = np.zeros((world, ex.stride), dtype=np.int64)
     bits = []
     for g in range(world):
-        buf[g, :ex.cnt_words].view(np.int32)[:ncols] = counts[g]
-        b = rng.integers(0, 2, size=int(nnz[g])).astype(np.uint8)
+        buf[g, 0] = ncols_of[g]
+        buf[g, 1:1 + ex.cnt_words].view(np.int32)[:ncols_of[g]] = counts[g]
+        buf[g, 1:1 + ex.cnt_words].view(np.int32)[ncols_of[g]:] = 99        # stale padding must be ignored
+        b = rng.integers(0, 2, size=nnz[g]).astype(np.uint8)
         bits.append(b)
         words = np.packbits(np.concatenate([b, np.zeros((-len(b)) % 64, np.uint8)]), bitorder="little").view(np.uint64)
-        buf[g, ex.cnt_words:ex.cnt_words + len(words)] = words.view(np.int64)
+        buf[g, 1 + ex.cnt_words:1 + ex.cnt_words + len(words)] = words.view(np.int64)
     ex.recv = torch.from_numpy(buf.reshape(-1).copy())
     colptr, chunks = ex.assemble()
-    exp_colptr = np.concatenate([[1], 1 + np.cumsum(counts.reshape(-1))])
+    exp_colptr = np.concatenate([[1], 1 + np.cumsum(np.concatenate(counts))])
     assert np.array_equal(colptr, exp_colptr)
     allbits = np.concatenate(bits)
     got = np.unpackbits(chunks.view(np.uint8), bitorder="little")[:len(allbits)]
