@@ -60,6 +60,8 @@ void *cache_take(size_t bytes, size_t *cap) {
 }
 }  // namespace
 
+size_t cache_parked_bytes() { return g_cached_bytes; }
+
 void cache_release_all() {
     for (const Block &b : g_blocks) cudaFree(b.p);
     g_blocks.clear();

@@ -197,8 +197,11 @@ static int brute_build(mpb200_samples *s, double r, mpb200_table *t) {
         cap = (probe == nq) ? h_max : (h_max + h_max / 2 + 64);
         cap = (cap + 31) & ~31;
         // slabs must leave room for the table itself; otherwise use the two-sweep path
+        // ... counting what a rebuild can reuse: the table's own buffers and the blocks parked in the cache
         const double need = 12.0 * (double)cap * (double)nq + 16.0 * 0.8 * (double)cap * (double)nq;
-        if (cap == 0 || need > 0.8 * (double)free_b) cap = 0;
+        const double avail = (double)free_b + (double)cache_parked_bytes() + (double)t->scratch.cap +
+                             (double)t->rowval.cap + (double)t->nzval.cap;
+        if (cap == 0 || need > 0.8 * avail) cap = 0;
     }
     bool single = cap > 0;
     if (single) {

@@ -74,6 +74,8 @@ struct DevBuf {
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
+size_t cache_parked_bytes();  // device bytes parked in the block cache (free for the next reserve)
+
 // timing phases: phase_begin(0) ... phase_end(0) record events on the launching stream
 void phase_bank(int op);               // select the event bank of the operation that starts now
 int phase_mark(int i);                 // record event i

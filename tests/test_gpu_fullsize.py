@@ -53,7 +53,7 @@ def test_full_size_c3_table_and_box_edges(gpu, orc):
         assert np.array_equal(got[dev[3]:dev[3] + len(ref[1])], exp.astype(bool))
         cols += 16
     assert cols == 128
-    assert 0.05 < 1.0 - got[:2_000_000].mean() < 0.95     # both outcomes occur
+    assert 0 < int((~got).sum()) < nnz                     # both outcomes occur (hyperboxes are thin in 10-D: ~0.1% collide)
     NN.close()
 
 
