@@ -188,11 +188,16 @@ int mpb200_sample_free(const mpb200_obstacles *o, const mpb200_space_desc *ss, i
                        mpb200_samples **out, double *V_host, int64_t *candidates);
 
 /* ---- linear-quadratic steering cost ("ControlNN") --------------------------------
- * Replaces LinearQuadratic(A, B, c, R) / LinearQuadratic2BVP (linearquadratic.jl:6-39,126-157).
- * A (n x n), B (n x m), R (m x m) column-major, c (n).  The reference's expAt handles nilpotent
- * A only (:94-98) and DoubleIntegrator (:46-53) is its one shipped instance; this library
- * accepts exactly that family: n = 2m, A = [0 I; 0 0], B = [0; I], c = 0, R symmetric positive
- * definite, m = 1..3.  Anything else returns MPB200_EARG. */
+ * Replaces LinearQuadratic(A, B, c, R) / LinearQuadratic2BVP (linearquadratic.jl:6-39,126-157) for
+ * xdot = A x + B u + c, cost int (1 + u'Ru).  A (n x n), B (n x m), R (m x m) column-major, c (n); n, m <= 6.
+ * As in the reference, A must be nilpotent (expAt, :94-98); R symmetric positive definite; (A, B)
+ * controllable.  Two evaluation paths, chosen here:
+ *   - the DoubleIntegrator family (:46-53: n = 2m, A = [0 I; 0 0], B = [0; I], c = 0, m = 1..3) uses the
+ *     closed form cost(t) = t + alpha/t^3 - beta/t^2 + gamma/t (csrc/lq.cu);
+ *   - every other system (drift c != 0, integrator chains, general B) evaluates G(t), xbar(t) and the
+ *     cost derivatives numerically from per-system tables (csrc/lq_general.cu; spec in oracle/lq_general.c,
+ *     pinned to the reference's SymPy construction by tests/golden/lq_general.json).
+ * Anything the reference rejects returns MPB200_EARG with the reference's message. */
 int mpb200_lq_create(const double *A, const double *B, const double *c, const double *R, int n, int m,
                      mpb200_lq **out);
 int mpb200_lq_destroy(mpb200_lq *lq);

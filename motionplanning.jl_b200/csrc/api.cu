@@ -190,6 +190,17 @@ int lq_motions_free_device(const mpb200_lq *lq, double r, const double *dA, cons
                            unsigned long long *d_checks);
 
 int pipe_peak_device(int kind, double *ops_per_s);
+int lqg_setup_host(int n, int m, const double *A, const double *B, const double *c, const double *R, LqgHost *S);
+int lqg_upload(mpb200_lq *lq);
+int lqg_inball_build(mpb200_samples *s, const mpb200_lq *lq, double r, mpb200_table *tF, mpb200_table *tB);
+int lqg_steer_device(const mpb200_lq *lq, const double *dA, const double *dB, int64_t n, double r, double *d_cost,
+                     double *d_topt);
+int lqg_edges_free_device(const mpb200_samples *s, const mpb200_table *t, const mpb200_lq *lq, double r,
+                          const mpb200_obstacles *o, const mpb200_space_desc *ss, uint32_t *d_bits32,
+                          unsigned long long *d_checks);
+int lqg_motions_free_device(const mpb200_lq *lq, double r, const double *dA, const double *dB, int64_t n, int d_state,
+                            const mpb200_obstacles *o, const mpb200_space_desc *ss, uint8_t *d_out,
+                            unsigned long long *d_checks);
 int mc_run_device(const mpb200_mc_problem *p, const mpb200_obstacles *o, unsigned long long seed, long long first,
                   long long n, double *h_out4, uint8_t *h_hit, double *h_w);
 
@@ -684,33 +695,54 @@ int mpb200_segments_free(const double *v_aos, const double *w_aos, int64_t n, in
 // ---- linear-quadratic steering --------------------------------------------------------------------
 int mpb200_lq_create(const double *A, const double *B, const double *c, const double *R, int n, int m, mpb200_lq **out) {
     MPB_CHECK_ARG(A && B && c && R && out, "NULL argument");
-    MPB_CHECK_ARG(m >= 1 && m <= 3 && n == 2 * m, "only double-integrator systems (n = 2m, m = 1..3) are built in");
-    // expAt handles nilpotent A only (linearquadratic.jl:94-98); accept the DoubleIntegrator family (:46-53)
-    for (int j = 0; j < n; ++j)
-        for (int i = 0; i < n; ++i)
-            MPB_CHECK_ARG(A[i + j * n] == ((j == i + m) ? 1.0 : 0.0), "A must be [0 I; 0 0] (double integrator)");
-    for (int j = 0; j < m; ++j)
-        for (int i = 0; i < n; ++i)
-            MPB_CHECK_ARG(B[i + j * n] == ((i == j + m) ? 1.0 : 0.0), "B must be [0; I] (double integrator)");
-    for (int i = 0; i < n; ++i) MPB_CHECK_ARG(c[i] == 0.0, "drift c must be zero");
-    bool scalar = true;
+    MPB_CHECK_ARG(n >= 1 && n <= kLqgMaxN && m >= 1 && m <= kLqgMaxN, "state / control dimension out of range (1..6)");
     for (int i = 0; i < m; ++i)
-        for (int j = 0; j < m; ++j) {
-            MPB_CHECK_ARG(R[i + j * m] == R[j + i * m], "R must be symmetric");
-            if (i != j && R[i + j * m] != 0.0) scalar = false;
-            if (i == j && R[i + j * m] != R[0]) scalar = false;
-        }
-    for (int i = 0; i < m; ++i) MPB_CHECK_ARG(R[i + i * m] > 0.0, "R must be positive definite");
+        for (int j = 0; j < m; ++j) MPB_CHECK_ARG(R[i + j * m] == R[j + i * m], "R must be symmetric");
+    // the double-integrator family (linearquadratic.jl:46-53: A = [0 I; 0 0], B = [0; I], c = 0, m = 1..3) keeps its
+    // closed form and the two-stage kernel of lq.cu; every other nilpotent (A, B, c) takes the numeric path
+    bool di = (n == 2 * m) && m <= 3;
+    for (int j = 0; di && j < n; ++j)
+        for (int i = 0; i < n; ++i) di = di && (A[i + j * n] == ((j == i + m) ? 1.0 : 0.0));
+    for (int j = 0; di && j < m; ++j)
+        for (int i = 0; i < n; ++i) di = di && (B[i + j * n] == ((i == j + m) ? 1.0 : 0.0));
+    for (int i = 0; di && i < n; ++i) di = di && (c[i] == 0.0);
     mpb200_lq *lq = new (std::nothrow) mpb200_lq();
     if (!lq) return fail(MPB200_ENOMEM, "out of host memory");
-    lq->d = m;
-    lq->scalar_R = scalar;
-    for (int i = 0; i < m; ++i)
-        for (int j = 0; j < m; ++j) lq->R[i * m + j] = R[i + j * m];
+    if (di) {
+        bool scalar = true;
+        for (int i = 0; i < m; ++i)
+            for (int j = 0; j < m; ++j) {
+                if (i != j && R[i + j * m] != 0.0) scalar = false;
+                if (i == j && R[i + j * m] != R[0]) scalar = false;
+            }
+        for (int i = 0; i < m; ++i)
+            if (!(R[i + i * m] > 0.0)) { delete lq; return fail(MPB200_EARG, "R must be positive definite"); }
+        lq->d = m;
+        lq->scalar_R = scalar;
+        for (int i = 0; i < m; ++i)
+            for (int j = 0; j < m; ++j) lq->R[i * m + j] = R[i + j * m];
+    } else {
+        MPB_REQUIRE_INIT();
+        // column-major (Julia) -> row-major tables; expAt's nilpotency check (linearquadratic.jl:94-98) is inside
+        double Ar[kLqgMaxN * kLqgMaxN], Br[kLqgMaxN * kLqgMaxN], Rr[kLqgMaxN * kLqgMaxN];
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < n; ++j) Ar[i * n + j] = A[i + j * n];
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < m; ++j) Br[i * m + j] = B[i + j * n];
+        for (int i = 0; i < m; ++i)
+            for (int j = 0; j < m; ++j) Rr[i * m + j] = R[i + j * m];
+        lq->general = true;
+        int rc = lqg_setup_host(n, m, Ar, Br, c, Rr, &lq->gen);
+        if (!rc) rc = lqg_upload(lq);
+        if (rc) { lq->gen_dev.release(); delete lq; return rc; }
+    }
     *out = lq;
     return MPB200_OK;
 }
 int mpb200_lq_destroy(mpb200_lq *lq) {
+    if (!lq) return MPB200_OK;
+    if (ctx().ready) cudaStreamSynchronize(ctx().stream);
+    lq->gen_dev.release();
     delete lq;
     return MPB200_OK;
 }
@@ -728,7 +760,7 @@ int mpb200_lq_inball_build(mpb200_samples *s, const mpb200_lq *lq, double r, mpb
     tF->edge_bits_valid = tB->edge_bits_valid = false;
     tF->src_N = tB->src_N = s->N;
     tF->src_d = tB->src_d = s->d;
-    int rc = lq_inball_build(s, lq, r, tF, tB);
+    int rc = lq->general ? lqg_inball_build(s, lq, r, tF, tB) : lq_inball_build(s, lq, r, tF, tB);
     if (rc) {
         if (freshF) mpb200_table_destroy(tF);
         if (freshB) mpb200_table_destroy(tB);
@@ -748,14 +780,16 @@ int mpb200_lq_steer(const mpb200_lq *lq, const double *v, const double *w, int64
     if (n == 0) return MPB200_OK;
     cudaStream_t st = ctx().stream;
     static DevBuf bufA, bufB, bufC, bufT;
-    const size_t bytes = sizeof(double) * (size_t)(n * 2 * lq->d);
+    const int ns = lq->general ? lq->gen.n : 2 * lq->d;
+    const size_t bytes = sizeof(double) * (size_t)(n * ns);
     if (int rc = bufA.reserve(bytes)) return rc;
     if (int rc = bufB.reserve(bytes)) return rc;
     if (int rc = bufC.reserve(sizeof(double) * (size_t)n)) return rc;
     if (int rc = bufT.reserve(sizeof(double) * (size_t)n)) return rc;
     MPB_CUDA(cudaMemcpyAsync(bufA.p, v, bytes, cudaMemcpyHostToDevice, st));
     MPB_CUDA(cudaMemcpyAsync(bufB.p, w, bytes, cudaMemcpyHostToDevice, st));
-    if (int rc = lq_steer_device(lq, bufA.as<double>(), bufB.as<double>(), n, r, bufC.as<double>(), bufT.as<double>()))
+    if (int rc = (lq->general ? lqg_steer_device : lq_steer_device)(lq, bufA.as<double>(), bufB.as<double>(), n, r,
+                                                                    bufC.as<double>(), bufT.as<double>()))
         return rc;
     MPB_CUDA(cudaMemcpyAsync(cost, bufC.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
     MPB_CUDA(cudaMemcpyAsync(topt, bufT.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
@@ -778,8 +812,8 @@ int mpb200_lq_edges_free(const mpb200_samples *s, const mpb200_table *t_, const 
     phase_mark(0);
     MPB_CUDA(cudaMemsetAsync(t->edge_bits.p, 0, sizeof(uint64_t) * (words + 1), st));
     MPB_CUDA(cudaMemsetAsync(c.d_scalar + 4, 0, sizeof(int64_t), st));
-    if (int rc = lq_edges_free_device(s, t, lq, r, o, ss, t->edge_bits.as<uint32_t>(),
-                                      reinterpret_cast<unsigned long long *>(c.d_scalar + 4)))
+    if (int rc = (lq->general ? lqg_edges_free_device : lq_edges_free_device)(
+            s, t, lq, r, o, ss, t->edge_bits.as<uint32_t>(), reinterpret_cast<unsigned long long *>(c.d_scalar + 4)))
         return rc;
     t->edge_bits_valid = true;
     t->edge_bits_nnz = t->nnz;
@@ -804,7 +838,7 @@ int mpb200_lq_motions_free(const mpb200_lq *lq, double r, const double *v, const
     Context &c = ctx();
     cudaStream_t st = c.stream;
     static DevBuf bufA, bufB, bufO;
-    const int ns = 2 * lq->d;
+    const int ns = lq->general ? lq->gen.n : 2 * lq->d;
     const size_t bytes = sizeof(double) * (size_t)(n * ns);
     if (int rc = bufA.reserve(bytes)) return rc;
     if (int rc = bufB.reserve(bytes)) return rc;
@@ -812,8 +846,9 @@ int mpb200_lq_motions_free(const mpb200_lq *lq, double r, const double *v, const
     MPB_CUDA(cudaMemcpyAsync(bufA.p, v, bytes, cudaMemcpyHostToDevice, st));
     MPB_CUDA(cudaMemcpyAsync(bufB.p, w, bytes, cudaMemcpyHostToDevice, st));
     MPB_CUDA(cudaMemsetAsync(c.d_scalar + 5, 0, sizeof(int64_t), st));
-    if (int rc = lq_motions_free_device(lq, r, bufA.as<double>(), bufB.as<double>(), n, ns, o, ss, bufO.as<uint8_t>(),
-                                        reinterpret_cast<unsigned long long *>(c.d_scalar + 5)))
+    if (int rc = (lq->general ? lqg_motions_free_device : lq_motions_free_device)(
+            lq, r, bufA.as<double>(), bufB.as<double>(), n, ns, o, ss, bufO.as<uint8_t>(),
+            reinterpret_cast<unsigned long long *>(c.d_scalar + 5)))
         return rc;
     MPB_CUDA(cudaMemcpyAsync(out, bufO.p, (size_t)n, cudaMemcpyDeviceToHost, st));
     MPB_CUDA(cudaMemcpyAsync(c.h_scalar + 5, c.d_scalar + 5, sizeof(int64_t), cudaMemcpyDeviceToHost, st));

@@ -148,8 +148,22 @@ struct mpb200_obstacles {
     int M = 0, d = 0;
 };
 
+namespace mpb {
+constexpr int kLqgMaxN = 6;  // state / control dimension limit of the general linear-affine path
+// per-system tables of the general path (lq_general.cu; same content as the oracle's orc_lqg), row-major
+struct LqgHost {
+    int n = 0, np = 0;
+    double A[kLqgMaxN * kLqgMaxN], c[kLqgMaxN], BRB[kLqgMaxN * kLqgMaxN];
+    double Ak[kLqgMaxN][kLqgMaxN * kLqgMaxN], dk[kLqgMaxN][kLqgMaxN];
+    double Gp[2 * kLqgMaxN][kLqgMaxN * kLqgMaxN];
+};
+}  // namespace mpb
+
 struct mpb200_lq {
-    int d = 0;              // position dimension; state dimension n = 2 d
+    int d = 0;              // double-integrator closed form (lq.cu): position dimension; state dimension n = 2 d
     bool scalar_R = false;  // R == rho * I
     double R[9] = {};       // d x d row-major (symmetric)
+    bool general = false;   // any other nilpotent (A, B, c): numeric 2BVP of lq_general.cu
+    mpb::LqgHost gen;       // its tables on the host ...
+    mpb::DevBuf gen_dev;    // ... and on the device (layout LqgTab<n>)
 };

@@ -2,8 +2,9 @@
 
 Mirror of src/statespaces/linearquadratic.jl: LinearQuadratic (:28-39), DoubleIntegrator (:46-53),
 steer / steer_pairwise (:191-225), collision_waypoints (:85-88).  The 2BVP is solved on the GPU
-(libmpb200, lq.cu); as in the reference only nilpotent-A systems are possible (:94-98) and the
-double-integrator family is what is built in.
+(libmpb200): the double-integrator family through its closed form (lq.cu), every other linear-affine
+system with nilpotent A -- drift c, integrator chains, general B and R -- numerically (lq_general.cu);
+as in the reference only nilpotent A is possible (:94-98).
 """
 import ctypes
 

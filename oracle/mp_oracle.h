@@ -118,6 +118,28 @@ void orc_lq_edges_free_csc(const orc_checker *CC, const orc_space *S, int d, con
                            const double *V, const int64_t *colptr, const int64_t *rowval, int64_t c0, int64_t c1,
                            uint8_t *out, int64_t *count);
 
+/* lq_general.c : general linear-affine systems xdot = A x + B u + c, nilpotent A (linearquadratic.jl:94-225).
+ * All matrices row-major.  Tables: Ak[k] = A^k / k!, dk[k] = Ak[k] c / (k+1), BRB = B R^-1 B',
+ * Gp[p-1] = coefficient of t^p in G(t). */
+#define ORC_LQG_MAXN 6
+typedef struct {
+    int n, np;
+    double A[ORC_LQG_MAXN * ORC_LQG_MAXN], c[ORC_LQG_MAXN], BRB[ORC_LQG_MAXN * ORC_LQG_MAXN];
+    double Ak[ORC_LQG_MAXN][ORC_LQG_MAXN * ORC_LQG_MAXN], dk[ORC_LQG_MAXN][ORC_LQG_MAXN];
+    double Gp[2 * ORC_LQG_MAXN][ORC_LQG_MAXN * ORC_LQG_MAXN];
+} orc_lqg;
+int orc_lqg_setup(int n, int m, const double *A, const double *B, const double *c, const double *R, orc_lqg *S);
+int orc_lqg_cost_terms(const orc_lqg *S, const double *x, const double *y, double t, double *out3);
+void orc_lqg_steer(const orc_lqg *S, const double *x0, const double *x1, double r, double *cost, double *topt);
+void orc_lqg_state(const orc_lqg *S, const double *x0, const double *x1, double t, double s, double *out);
+void orc_lqg_inball(const orc_lqg *S, const double *V, int64_t N, double r, int forwards, int64_t q0, int64_t q1,
+                    int64_t *colptr, int64_t *rowval, double *nzval);
+int orc_lqg_is_free_motion(const orc_checker *CC, const orc_space *Sp, const orc_lqg *S, double r, const double *v,
+                           const double *w, int64_t *count);
+void orc_lqg_edges_free_csc(const orc_checker *CC, const orc_space *Sp, const orc_lqg *S, double r, const double *V,
+                            const int64_t *colptr, const int64_t *rowval, int64_t c0, int64_t c1, uint8_t *out,
+                            int64_t *count);
+
 /* ---- Philox4x32-10 (mc.c) and batched free-state sampling (sample.c; sampling.jl:23-37) ---- */
 void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 void orc_sample_candidate(const orc_space *S, uint64_t seed, int64_t c, double *x);

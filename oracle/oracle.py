@@ -78,6 +78,16 @@ def lib():
         L.orc_det_exp.argtypes = [c_dbl]
         L.orc_det_sincos2pi.argtypes = [c_dbl, P(c_dbl), P(c_dbl)]
         L.orc_mc_run.argtypes = [P(McProblem), P(Checker), ctypes.c_uint64, c_i64, c_i64, c_vp, P(c_i64), c_vp, c_vp]
+        L.orc_lqg_setup.argtypes = [ctypes.c_int, ctypes.c_int, c_vp, c_vp, c_vp, c_vp, c_vp]
+        L.orc_lqg_setup.restype = ctypes.c_int
+        L.orc_lqg_cost_terms.argtypes = [c_vp, c_vp, c_vp, c_dbl, c_vp]
+        L.orc_lqg_steer.argtypes = [c_vp, c_vp, c_vp, c_dbl, P(c_dbl), P(c_dbl)]
+        L.orc_lqg_state.argtypes = [c_vp, c_vp, c_vp, c_dbl, c_dbl, c_vp]
+        L.orc_lqg_inball.argtypes = [c_vp, c_vp, c_i64, c_dbl, ctypes.c_int, c_i64, c_i64, c_vp, c_vp, c_vp]
+        L.orc_lqg_is_free_motion.argtypes = [P(Checker), P(Space), c_vp, c_dbl, c_vp, c_vp, P(c_i64)]
+        L.orc_lqg_is_free_motion.restype = ctypes.c_int
+        L.orc_lqg_edges_free_csc.argtypes = [P(Checker), P(Space), c_vp, c_dbl, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp,
+                                             P(c_i64)]
         L.orc_lq_steer.argtypes = [ctypes.c_int, c_vp, c_vp, c_vp, c_dbl, P(c_dbl), P(c_dbl)]
         L.orc_lq_cost_terms.argtypes = [ctypes.c_int, c_vp, c_vp, c_vp, c_dbl, c_vp]
         L.orc_lq_state.argtypes = [ctypes.c_int, c_vp, c_vp, c_dbl, c_dbl, c_vp]
@@ -383,6 +393,73 @@ class DoubleIntegratorLQ:
         cnt = c_i64(0)
         lib().orc_lq_edges_free_csc(ctypes.byref(cc), ctypes.byref(space.c), self.d, _p(self.R), float(r), _p(V),
                                     _p(colptr), _p(rowval), c0, c0 + len(colptr) - 1, _p(out), ctypes.byref(cnt))
+        return out, cnt.value
+
+
+class LqgTables(ctypes.Structure):
+    _MAXN = 6
+    _fields_ = [("n", c_i32), ("np", c_i32), ("A", c_dbl * 36), ("c", c_dbl * 6), ("BRB", c_dbl * 36),
+                ("Ak", (c_dbl * 36) * 6), ("dk", (c_dbl * 6) * 6), ("Gp", (c_dbl * 36) * 12)]
+
+
+class LinearQuadraticGeneral:
+    """xdot = A x + B u + c with nilpotent A (oracle/lq_general.c); same methods as DoubleIntegratorLQ."""
+
+    def __init__(self, A, B, c, R):
+        A, B, c, R = _f64(A), _f64(B), _f64(c), _f64(R)
+        self.n, self.m = A.shape[0], B.shape[1]
+        self.S = LqgTables()
+        rc = lib().orc_lqg_setup(self.n, self.m, _p(A), _p(B), _p(c), _p(R), ctypes.byref(self.S))
+        if rc != 0:
+            raise ValueError("orc_lqg_setup failed (%d): A not nilpotent / R not SPD / size out of range" % rc)
+
+    def steer(self, x0, x1, r):
+        x0, x1 = _f64(x0), _f64(x1)
+        c, t = c_dbl(0), c_dbl(0)
+        lib().orc_lqg_steer(ctypes.byref(self.S), _p(x0), _p(x1), float(r), ctypes.byref(c), ctypes.byref(t))
+        return c.value, t.value
+
+    def cost_terms(self, x0, x1, t):
+        x0, x1 = _f64(x0), _f64(x1)
+        out = np.zeros(3)
+        lib().orc_lqg_cost_terms(ctypes.byref(self.S), _p(x0), _p(x1), float(t), _p(out))
+        return out
+
+    def state(self, x0, x1, t, s):
+        x0, x1 = _f64(x0), _f64(x1)
+        out = np.zeros(self.n)
+        lib().orc_lqg_state(ctypes.byref(self.S), _p(x0), _p(x1), float(t), float(s), _p(out))
+        return out
+
+    def inball(self, V, r, forwards, q0=0, q1=None):
+        V = _f64(V)
+        N = V.shape[0]
+        q1 = N if q1 is None else q1
+        colptr = np.zeros(q1 - q0 + 1, dtype=np.int64)
+        lib().orc_lqg_inball(ctypes.byref(self.S), _p(V), N, float(r), int(forwards), q0, q1, _p(colptr), None, None)
+        nnz = int(colptr[-1] - 1)
+        rowval, nzval = np.zeros(nnz, dtype=np.int64), np.zeros(nnz)
+        lib().orc_lqg_inball(ctypes.byref(self.S), _p(V), N, float(r), int(forwards), q0, q1, _p(colptr), _p(rowval),
+                             _p(nzval))
+        return colptr, rowval, nzval
+
+    def is_free_motion(self, obs, space, r, v, w):
+        v, w = _f64(v), _f64(w)
+        cc = obs.checker()
+        cnt = c_i64(0)
+        ok = lib().orc_lqg_is_free_motion(ctypes.byref(cc), ctypes.byref(space.c), ctypes.byref(self.S), float(r), _p(v),
+                                          _p(w), ctypes.byref(cnt))
+        return bool(ok), cnt.value
+
+    def edges_free_csc(self, obs, space, r, V, colptr, rowval, c0=0):
+        V = _f64(V)
+        colptr = np.ascontiguousarray(colptr, dtype=np.int64)
+        rowval = np.ascontiguousarray(rowval, dtype=np.int64)
+        out = np.zeros(len(rowval), dtype=np.uint8)
+        cc = obs.checker()
+        cnt = c_i64(0)
+        lib().orc_lqg_edges_free_csc(ctypes.byref(cc), ctypes.byref(space.c), ctypes.byref(self.S), float(r), _p(V),
+                                     _p(colptr), _p(rowval), c0, c0 + len(colptr) - 1, _p(out), ctypes.byref(cnt))
         return out, cnt.value
 
 
