@@ -30,13 +30,18 @@ def test_steer_batch_bit_exact(gpu, orc):
         assert (topt <= r).all() and (topt[50:] > 0).all()
 
 
-def test_lq_create_rejects_other_systems(gpu):
+def test_lq_create_takes_other_nilpotent_systems_and_rejects_the_rest(gpu, orc):
     mp = gpu
-    A = np.zeros((4, 4)); A[0, 1] = 1; A[1, 2] = 1; A[2, 3] = 1      # nilpotent chain, not [0 I;0 0]
+    A = np.zeros((4, 4)); A[0, 1] = 1; A[1, 2] = 1; A[2, 3] = 1      # nilpotent chain, not [0 I;0 0]: the numeric path
     B = np.zeros((4, 2)); B[3, 0] = 1; B[2, 1] = 1
     d = mp.LinearQuadratic(A, B, np.zeros(4), np.eye(2))
-    with pytest.raises(mp.MPB200Error):
-        d.handle()
+    d.handle()
+    rng = np.random.Generator(np.random.PCG64(4))
+    X0, X1 = rng.random((64, 4)) - 0.5, rng.random((64, 4)) - 0.5
+    cost, topt = mp.linearquadratic.steer_batch(d, X0, X1, 0.8)
+    L = orc.LinearQuadraticGeneral(A, B, np.zeros(4), np.eye(2))
+    for k in range(64):
+        assert (cost[k], topt[k]) == L.steer(X0[k], X1[k], 0.8)
     with pytest.raises(NotImplementedError):                          # linearquadratic.jl:96
         mp.LinearQuadratic(np.eye(2), np.ones((2, 1)), np.zeros(2), np.eye(1))
 
