@@ -269,6 +269,9 @@ class Job:
             self.exchange = sharding.make_exchange(q1 - q0, (nnz0 * 21 // 20 + 63) // 64 + 2)
             self.exchange_kind = "peer-stores" if isinstance(self.exchange, sharding.PeerExchange) else "nccl-allgather"
         self.nnz = 0
+        self.pushes = 0
+        self.exchange_ms = []
+        self.lib = mp.load()
 
     def step(self):
         # the three calls of a planning step, issued back to back: only build_table waits (for nnz, once,
@@ -278,7 +281,13 @@ class Job:
         self.nnz = NN.build_table(self.r)                       # K1 + K2
         NN.edges_free(NN.table, self.CC, self.SS, fetch=False, count=False)  # K7
         if self.exchange is not None:
+            if self.exchange_kind == "peer-stores" and self.pushes > 0:
+                # device time of the PREVIOUS push + barrier: complete by now (this step's nnz read-back is ordered
+                # behind it), so reading it here never stalls the host; reading it at the end of its own step would
+                # make every rank's host wait for the barrier before it may enqueue the next step
+                self.exchange_ms.append(self.lib.mpb200_last_ms_of(3, 1))
             self.exchange.run(NN.table)          # column lengths + validity words of every rank -> every rank
+            self.pushes += 1
 
     def close(self):
         if self.exchange is not None and hasattr(self.exchange, "close"):
@@ -295,6 +304,15 @@ def timed_steps(job, lib, stream, flush, steps, warmup, world, sampler=None, pha
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     launches0 = 0
     t_wall0 = 0.0
+    def read_phases():
+        # per-kernel times of the step just enqueued (events recorded inside the calls).  Read AFTER the next
+        # iteration's flush has been enqueued: the host then waits for this step's last validity kernel while the
+        # GPU still has the exchange and the flush to run, instead of idling the GPU at every step boundary.
+        phases_out["table"] += np.array([lib.mpb200_last_ms_of(_lib.OP_TABLE, k) for k in range(5)])
+        phases_out["points"].append(lib.mpb200_last_ms_of(_lib.OP_POINTS, 1))
+        phases_out["edges"].append(lib.mpb200_last_ms_of(_lib.OP_EDGES, 1))
+
+    job.exchange_ms = []
     for it in range(warmup + steps):
         if it == warmup:
             torch.cuda.synchronize()
@@ -305,21 +323,20 @@ def timed_steps(job, lib, stream, flush, steps, warmup, world, sampler=None, pha
                 sampler.start()
             launches0 = lib.mpb200_launch_count()
             t_wall0 = time.perf_counter()
+            job.exchange_ms = []
         flush.zero_()  # L2 flush between iterations (outside the event pair)
+        if it > warmup and phases_out is not None:
+            read_phases()
         if it >= warmup:
             ev[it - warmup][0].record(stream)
         job.step()
         if it >= warmup:
             ev[it - warmup][1].record(stream)
-            if phases_out is not None:
-                # per-kernel times of THIS step (events recorded inside the calls, read after the step's end event)
-                phases_out["table"] += np.array([lib.mpb200_last_ms_of(_lib.OP_TABLE, k) for k in range(5)])
-                phases_out["points"].append(lib.mpb200_last_ms_of(_lib.OP_POINTS, 1))
-                phases_out["edges"].append(lib.mpb200_last_ms_of(_lib.OP_EDGES, 1))
-                if job.exchange_kind == "peer-stores":
-                    phases_out["exchange"].append(lib.mpb200_last_ms_of(_lib.OP_OTHER, 1))
             if sampler is not None and sampler.nv and (it - warmup) % 8 == 0:
                 sampler._sample()   # also from this thread, between steps (outside the event pairs): the region is short
+    if phases_out is not None:
+        read_phases()
+        phases_out["exchange"] = list(job.exchange_ms[1:])   # the first entry belongs to the last warm-up step
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()

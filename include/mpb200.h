@@ -256,6 +256,16 @@ int mpb200_mc_collision_probability(const mpb200_mc_problem *p, const mpb200_obs
                                     int64_t first, int64_t n, mpb200_mc_result *out, uint8_t *hit_out,
                                     double *w_out);
 
+/* ---- closest obstacle points under a weight matrix (Monte-Carlo proposal geometry) ----------
+ * Replaces closest(p, shape, W) / closeR(p, CC, W, r2) (SAT2D.jl:208-285; boxesND.jl:61-86; robots2D.jl:25-26)
+ * for n query points at once, each with its own SPD weight matrix W_i (dw x dw row-major; dw = 2 for 2-D
+ * obstacle sets, = box dimension <= 4 for box lists).  S = number of basic shapes (circles + polygons, or boxes).
+ * Per point: count[i] shapes lie closer than r2 (squared W-distance); d2 / shape / x list them in ascending
+ * d2 (ties in shape order), capacity S per point: d2[i*S + k], shape[i*S + k], x[(i*S + k)*dw ..].
+ * all_d2 / all_x (optional, n x S [x dw]) receive closest() for every basic shape, unsorted. */
+int mpb200_close_points(const mpb200_obstacles *o, const double *p_aos, const double *W, int64_t n, int dw, double r2,
+                        int32_t *count, double *d2, int32_t *shape, double *x, double *all_d2, double *all_x);
+
 /* ---- multi-GPU exchange by direct peer stores (one process per GPU, one box) ----------
  * The reference has no distributed layer; this is the exchange step of the query-range-sharded
  * precompute: after a rank has built its table shard and the validity of its

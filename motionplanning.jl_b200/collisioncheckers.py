@@ -58,6 +58,10 @@ class PointRobot2D(SweptCollisionChecker):
         self.fixed_point_test = bool(fixed_point_test)
         self.packed = shapes2d.pack_obstacles(obstacles, fixed_point_test)
 
+    def n_basic_shapes(self):
+        """circles + polygons of the shape tree (the S of mpb200_close_points)"""
+        return int(self.packed["n_shapes"])
+
     def _create(self):
         lib = _lib.lib()
         p = self.packed

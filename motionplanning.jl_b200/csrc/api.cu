@@ -190,6 +190,8 @@ int lq_motions_free_device(const mpb200_lq *lq, double r, const double *dA, cons
                            unsigned long long *d_checks);
 
 int pipe_peak_device(int kind, double *ops_per_s);
+int close_points_device(const mpb200_obstacles *o, const double *dP, const double *dW, int64_t n, int dw, double r2,
+                        int *d_count, double *d_d2, int *d_shape, double *d_x, double *d_all_d2, double *d_all_x);
 int lqg_setup_host(int n, int m, const double *A, const double *B, const double *c, const double *R, LqgHost *S);
 int lqg_upload(mpb200_lq *lq);
 int lqg_inball_build(mpb200_samples *s, const mpb200_lq *lq, double r, mpb200_table *tF, mpb200_table *tB);
@@ -854,6 +856,44 @@ int mpb200_lq_motions_free(const mpb200_lq *lq, double r, const double *v, const
     MPB_CUDA(cudaMemcpyAsync(c.h_scalar + 5, c.d_scalar + 5, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     MPB_CUDA(cudaStreamSynchronize(st));
     if (checks) *checks = c.h_scalar[5];
+    return MPB200_OK;
+}
+
+int mpb200_close_points(const mpb200_obstacles *o, const double *p_aos, const double *W, int64_t n, int dw, double r2,
+                        int32_t *count, double *d2, int32_t *shape, double *x, double *all_d2, double *all_x) {
+    MPB_REQUIRE_INIT();
+    MPB_CHECK_ARG(o != nullptr, "obstacle handle is NULL");
+    MPB_CHECK_ARG(n >= 0 && dw >= 1, "bad batch size / dimension");
+    MPB_CHECK_ARG(n == 0 || (p_aos && W && count && d2 && shape && x), "NULL buffers");
+    const int64_t S = o->kind == 0 ? o->n_shapes : o->M;
+    if (n == 0) return MPB200_OK;
+    if (S == 0) { memset(count, 0, sizeof(int32_t) * (size_t)n); return MPB200_OK; }
+    cudaStream_t st = ctx().stream;
+    static DevBuf bP, bW, bC, bD, bS, bX, bAD, bAX;  // reused staging (single caller thread)
+    const size_t nS = (size_t)(n * S);
+    if (int rc = bP.reserve(sizeof(double) * (size_t)(n * dw))) return rc;
+    if (int rc = bW.reserve(sizeof(double) * (size_t)(n * dw * dw))) return rc;
+    if (int rc = bC.reserve(sizeof(int) * (size_t)n)) return rc;
+    if (int rc = bD.reserve(sizeof(double) * nS)) return rc;
+    if (int rc = bS.reserve(sizeof(int) * nS)) return rc;
+    if (int rc = bX.reserve(sizeof(double) * nS * dw)) return rc;
+    if (int rc = bAD.reserve(sizeof(double) * nS)) return rc;
+    if (int rc = bAX.reserve(sizeof(double) * nS * dw)) return rc;
+    MPB_CUDA(cudaMemcpyAsync(bP.p, p_aos, sizeof(double) * (size_t)(n * dw), cudaMemcpyHostToDevice, st));
+    MPB_CUDA(cudaMemcpyAsync(bW.p, W, sizeof(double) * (size_t)(n * dw * dw), cudaMemcpyHostToDevice, st));
+    MPB_CUDA(cudaMemsetAsync(bD.p, 0, sizeof(double) * nS, st));
+    MPB_CUDA(cudaMemsetAsync(bS.p, 0xff, sizeof(int) * nS, st));
+    MPB_CUDA(cudaMemsetAsync(bX.p, 0, sizeof(double) * nS * dw, st));
+    if (int rc = close_points_device(o, bP.as<double>(), bW.as<double>(), n, dw, r2, bC.as<int>(), bD.as<double>(),
+                                     bS.as<int>(), bX.as<double>(), bAD.as<double>(), bAX.as<double>()))
+        return rc;
+    MPB_CUDA(cudaMemcpyAsync(count, bC.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    MPB_CUDA(cudaMemcpyAsync(d2, bD.p, sizeof(double) * nS, cudaMemcpyDeviceToHost, st));
+    MPB_CUDA(cudaMemcpyAsync(shape, bS.p, sizeof(int) * nS, cudaMemcpyDeviceToHost, st));
+    MPB_CUDA(cudaMemcpyAsync(x, bX.p, sizeof(double) * nS * dw, cudaMemcpyDeviceToHost, st));
+    if (all_d2) MPB_CUDA(cudaMemcpyAsync(all_d2, bAD.p, sizeof(double) * nS, cudaMemcpyDeviceToHost, st));
+    if (all_x) MPB_CUDA(cudaMemcpyAsync(all_x, bAX.p, sizeof(double) * nS * dw, cudaMemcpyDeviceToHost, st));
+    MPB_CUDA(cudaStreamSynchronize(st));
     return MPB200_OK;
 }
 

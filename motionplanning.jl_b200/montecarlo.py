@@ -195,19 +195,55 @@ def closeR(p, CC, W, r2):
     return sorted([c for c in cps if c[0] < r2], key=lambda c: c[0])
 
 
-def with_proposal(problem, CC, r2=16.0, alpha0=0.2, max_components=16):
+def close_points(P, CC, Ws, r2, want_all=False):
+    """closeR(p_i, CC, W_i, r2) for a whole batch on the GPU (mpb200_close_points, csrc/closest.cu): P is n x dw,
+    Ws n x dw x dw (one SPD weight matrix per point).  Returns (count[n], d2[n,S], shape[n,S], x[n,S,dw]) -- per point
+    the basic shapes closer than r2 in ascending squared W-distance -- and, with want_all, closest() for every
+    basic shape as (all_d2[n,S], all_x[n,S,dw])."""
+    P = np.ascontiguousarray(P, dtype=np.float64)
+    Ws = np.ascontiguousarray(Ws, dtype=np.float64)
+    n, dw = P.shape
+    S = max(len(CC.boxes) if hasattr(CC, "boxes") else CC.n_basic_shapes(), 1)
+    count = np.zeros(n, dtype=np.int32)
+    d2 = np.zeros((n, S))
+    shape = np.full((n, S), -1, dtype=np.int32)
+    x = np.zeros((n, S, dw))
+    all_d2 = np.zeros((n, S)) if want_all else None
+    all_x = np.zeros((n, S, dw)) if want_all else None
+    _lib.check(_lib.lib().mpb200_close_points(CC.handle(), _lib.ptr(P), _lib.ptr(Ws), n, dw, float(r2), _lib.ptr(count),
+                                              _lib.ptr(d2), _lib.ptr(shape), _lib.ptr(x), _lib.ptr(all_d2),
+                                              _lib.ptr(all_x)))
+    return (count, d2, shape, x) + ((all_d2, all_x) if want_all else ())
+
+
+def with_proposal(problem, CC, r2=16.0, alpha0=0.2, max_components=16, device=True):
     """Defensive mixture: one component per (step, close obstacle point), shifted by the minimum-
-    norm stacked noise whose mean trajectory touches that point; alpha_k ~ Phi(-sqrt(d2_k))."""
+    norm stacked noise whose mean trajectory touches that point; alpha_k ~ Phi(-sqrt(d2_k)).
+    The close points of ALL steps come from one batched GPU call (device=True); device=False walks the steps
+    with the host geometry above, as the reference's closeR would."""
     Ms = problem.noise_to_workspace()
     comps = []
+    steps, Wts = [], []
     for t, M in enumerate(Ms):
         Sigma = M @ M.T
         if np.linalg.matrix_rank(Sigma) < Sigma.shape[0]:
             continue
-        Wt = np.linalg.inv(Sigma)
-        for d2, x in closeR(problem.wbar[t + 1], CC, Wt, r2):
-            mu = M.T @ Wt @ (x - problem.wbar[t + 1])
-            comps.append((d2, mu))
+        steps.append(t)
+        Wts.append(np.linalg.inv(Sigma))
+    if device and steps:
+        Wts = [0.5 * (W + W.T) for W in Wts]                       # exactly symmetric, as the kernel reads W[0], W[1], W[3]
+        P = np.stack([problem.wbar[t + 1] for t in steps])
+        count, d2s, _, xs = close_points(P, CC, np.stack(Wts), r2)
+        for i, t in enumerate(steps):
+            for k in range(int(count[i])):
+                mu = Ms[t].T @ Wts[i] @ (xs[i, k] - problem.wbar[t + 1])
+                comps.append((float(d2s[i, k]), mu))
+    else:
+        for t, Wt in zip(steps, Wts):
+            M = Ms[t]
+            for d2, x in closeR(problem.wbar[t + 1], CC, Wt, r2):
+                mu = M.T @ Wt @ (x - problem.wbar[t + 1])
+                comps.append((d2, mu))
     comps.sort(key=lambda c: c[0])
     comps = comps[:max_components]
     if not comps:

@@ -140,6 +140,14 @@ void orc_lqg_edges_free_csc(const orc_checker *CC, const orc_space *Sp, const or
                             const int64_t *colptr, const int64_t *rowval, int64_t c0, int64_t c1, uint8_t *out,
                             int64_t *count);
 
+/* closest.c : closest / closeR under a weight matrix (SAT2D.jl:208-285, boxesND.jl:61-86); W row-major */
+#define ORC_CP_MAXD 4
+void orc_closest_circle(const double *p, const double *rec, const double *W, double *d2, double *x);
+void orc_closest_polygon(const double *p, const double *rec, int K, const double *W, double *d2, double *x);
+void orc_closest_box(const double *p, const double *lo, const double *hi, int d, const double *W, double *d2, double *x);
+int orc_close_points(const orc_checker *CC, const double *P, const double *Ws, int64_t n, int dw, double r2,
+                     int32_t *count, double *d2_out, int32_t *shape_out, double *x_out, double *all_d2, double *all_x);
+
 /* ---- Philox4x32-10 (mc.c) and batched free-state sampling (sample.c; sampling.jl:23-37) ---- */
 void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 void orc_sample_candidate(const orc_space *S, uint64_t seed, int64_t c, double *x);

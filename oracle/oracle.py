@@ -88,6 +88,8 @@ def lib():
         L.orc_lqg_is_free_motion.restype = ctypes.c_int
         L.orc_lqg_edges_free_csc.argtypes = [P(Checker), P(Space), c_vp, c_dbl, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp,
                                              P(c_i64)]
+        L.orc_close_points.argtypes = [P(Checker), c_vp, c_vp, c_i64, ctypes.c_int, c_dbl, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]
+        L.orc_close_points.restype = ctypes.c_int
         L.orc_lq_steer.argtypes = [ctypes.c_int, c_vp, c_vp, c_vp, c_dbl, P(c_dbl), P(c_dbl)]
         L.orc_lq_cost_terms.argtypes = [ctypes.c_int, c_vp, c_vp, c_vp, c_dbl, c_vp]
         L.orc_lq_state.argtypes = [ctypes.c_int, c_vp, c_vp, c_dbl, c_dbl, c_vp]
@@ -461,6 +463,26 @@ class LinearQuadraticGeneral:
         lib().orc_lqg_edges_free_csc(ctypes.byref(cc), ctypes.byref(space.c), ctypes.byref(self.S), float(r), _p(V),
                                      _p(colptr), _p(rowval), c0, c0 + len(colptr) - 1, _p(out), ctypes.byref(cnt))
         return out, cnt.value
+
+
+def close_points(obs, P, Ws, r2, want_all=False):
+    """closeR(p, CC, W, r2) for every row of P with its own W (oracle/closest.c) ->
+    (count[n], d2[n,S], shape[n,S], x[n,S,dw]) [+ (all_d2[n,S], all_x[n,S,dw])]"""
+    P, Ws = _f64(P), _f64(Ws)
+    n, dw = P.shape
+    cc = obs.checker()
+    S = cc.obs2d.contents.n_shapes if cc.kind == 0 else cc.M
+    count = np.zeros(n, dtype=np.int32)
+    d2 = np.full((n, max(S, 1)), np.inf)
+    shape = np.full((n, max(S, 1)), -1, dtype=np.int32)
+    x = np.zeros((n, max(S, 1), dw))
+    all_d2 = np.zeros((n, max(S, 1))) if want_all else None
+    all_x = np.zeros((n, max(S, 1), dw)) if want_all else None
+    rc = lib().orc_close_points(ctypes.byref(cc), _p(P), _p(Ws), n, dw, float(r2), _p(count), _p(d2), _p(shape), _p(x),
+                                _p(all_d2), _p(all_x))
+    if rc != 0:
+        raise ValueError("orc_close_points: unsupported workspace dimension")
+    return (count, d2, shape, x) + ((all_d2, all_x) if want_all else ())
 
 
 # ---- Monte-Carlo collision probability (spec: oracle/mc.c header; parity unpinned) -------------------
