@@ -53,7 +53,7 @@ def test_with_proposal_builds_normalised_mixture(mp):
     F = np.stack([np.eye(2)] * T)
     G = np.stack([np.eye(2) * 0.02] * T)
     wbar = np.stack([np.linspace(0.3, 0.6, T + 1), np.full(T + 1, 0.17)], axis=1)
-    P = mp.montecarlo.with_proposal(mp.MCProblem(F, G, np.eye(2), wbar), CC, r2=25.0)
+    P = mp.montecarlo.with_proposal(mp.MCProblem(F, G, np.eye(2), wbar), CC, r2=25.0, device=False)   # host geometry (no GPU here)
     assert P.K >= 1 and abs(P.alpha.sum() - 1) < 1e-12 and P.alpha[0] == 0.2
     Ms = P.noise_to_workspace()
     # every shifted mean trajectory touches an obstacle boundary point at some step
