@@ -32,8 +32,16 @@ def _bits_to_bool(chunks, n):
     return np.unpackbits(np.ascontiguousarray(chunks).view(np.uint8), bitorder="little")[:n].astype(bool)
 
 
-def fmtstar(P, N=None, rm=1.0, connections="R", r=0.0, ensure_goal_ct=1, init_idx=1, checkpts=True, seed=0):
-    """fmtstar!(P, N; rm, connections, r, ensure_goal_ct, init_idx, checkpts) -> (status, cost, elapsed)"""
+def fmtstar(P, N=None, rm=1.0, connections="R", r=0.0, ensure_goal_ct=1, init_idx=1, checkpts=True, seed=0,
+            edge_checks="table"):
+    """fmtstar!(P, N; rm, connections, r, ensure_goal_ct, init_idx, checkpts) -> (status, cost, elapsed)
+
+    edge_checks = "table": the validity of EVERY stored edge is precomputed in one pass (K7/K8/K9) and fmt.jl:75
+    becomes a bit lookup -- the right trade when the table is large and the GPU pass costs microseconds per
+    million edges.  edge_checks = "lazy": wavefront-batched lazy checking -- no edge table; the
+    candidate connections (y_min, x) of ONE expansion of z are independent of each other (H and C only change
+    after the loop, fmt.jl:69-84), so they are checked in one batched device call per expansion and the device
+    work equals what FMT* consumes ("collision_checks").  Both modes return the identical tree, path and cost."""
     t_start = time.perf_counter()
     N = len(P.V) if N is None else N
     P.CC.count = 0
@@ -58,17 +66,27 @@ def fmtstar(P, N=None, rm=1.0, connections="R", r=0.0, ensure_goal_ct=1, init_id
         setup_steering(SS, r)
 
     # ---- the batched precompute that replaces the lazy per-call hot path -----------------------
+    if edge_checks not in ("table", "lazy"):
+        raise ValueError("edge_checks must be 'table' or 'lazy'")
+    lazy = edge_checks == "lazy"
     lq = isinstance(SS.dist, LinearQuadratic)
+    ebits = None
     if lq:
         cF, cB = NN.precompute(r)
         DF, DB = cF.D, cB.D
-        ebits, _ = NN.lq_edges_free(CC, SS)
+        if not lazy:
+            ebits, _ = NN.lq_edges_free(CC, SS)
+    elif lazy:
+        DF = DB = NN.precompute(r).D
     else:
         cache, ebits, _ = NN.precompute_checked(r, CC, SS)   # K1 + K2 with K7/K8 fused
         DF = DB = cache.D
     lookups_before = CC.count
     CC.count = 0                                          # the table build is not what FMT* "asked"
-    evalid = _bits_to_bool(ebits, DB.nnz)
+    evalid = _bits_to_bool(ebits, DB.nnz) if not lazy else None
+    if lazy:
+        from .linearquadratic import lq_motions_free
+        from .statespaces import segments_free
     F = _bits_to_bool(NN.points_free(CC, SS), N) if checkpts else np.ones(N, dtype=bool)
     is_goal = goal_mask(V, P.goal, SS)
 
@@ -89,9 +107,11 @@ def fmtstar(P, N=None, rm=1.0, connections="R", r=0.0, ensure_goal_ct=1, init_id
     fcp, frv, fnz = DF.colptr, DF.rowval, DF.nzval
     bcp, brv, bnz = DB.colptr, DB.rowval, DB.nzval
     checks = 0
+    device_batches = 0
     while not is_goal[z - 1]:
         H_new = []
         fs = frv[fcp[z - 1] - 1:fcp[z] - 1]
+        todo = []                                          # (x, y_min, c_min, stored entry) of this expansion, in x order
         for x in fs[Wm[fs - 1]]:                           # nearF(V, z, r, W): unvisited, ascending
             x = int(x)
             if checkpts and not F[x - 1]:
@@ -110,7 +130,14 @@ def fmtstar(P, N=None, rm=1.0, connections="R", r=0.0, ensure_goal_ct=1, init_id
                 checks += 1                                # counted per motion; segments in metadata below
             else:
                 checks += int(inb[y_min - 1])
-            if evalid[e]:                                  # is_free_motion(V[y_min], V[x], CC, SS)
+            todo.append((x, y_min, c_min, e))
+        if lazy and todo:                                  # ONE batched device call for the whole expansion
+            ys_ = np.fromiter((t[1] for t in todo), dtype=np.int64) - 1
+            xs_ = np.fromiter((t[0] for t in todo), dtype=np.int64) - 1
+            ok = (lq_motions_free if lq else segments_free)(V[ys_], V[xs_], CC, SS)
+            device_batches += 1
+        for k, (x, y_min, c_min, e) in enumerate(todo):
+            if (ok[k] if lazy else evalid[e]):             # is_free_motion(V[y_min], V[x], CC, SS)
                 A[x - 1] = y_min
                 C[x - 1] = c_min
                 heapq.heappush(heap, (c_min, x))
@@ -138,7 +165,8 @@ def fmtstar(P, N=None, rm=1.0, connections="R", r=0.0, ensure_goal_ct=1, init_id
     meta = {
         "radius_multiplier": rm, "collision_checks": checks, "num_samples": N, "cost": float(C[z - 1]),
         "cumcost": costs, "planner": "FMTstar", "solved": solved, "tree": A, "path": sol, "r": r,
-        "precomputed_edge_checks": int(lookups_before),
+        "precomputed_edge_checks": int(lookups_before), "edge_checks": edge_checks,
+        "device_edge_batches": device_batches,
     }
     P.solution = MPSolution(P.status, float(C[z - 1]), time.perf_counter() - t_start, meta)
     return P.status, P.solution.cost, P.solution.elapsed

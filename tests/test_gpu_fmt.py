@@ -112,3 +112,43 @@ def test_fmt_double_integrator_matches_oracle(gpu, orc):
     # soft anchor: the notebook's double-integrator run (vmax=.5, r=1, N=1000) printed 5.72
     assert 3.5 < cost < 8.5
     P.V.close()
+
+
+@pytest.mark.parametrize("space", ["euclid_sat2d", "euclid_boxes", "double_integrator"])
+def test_fmt_lazy_wavefront_batched_checks_equal_the_precomputed_table(gpu, orc, space):
+    """edge_checks="lazy" checks only the candidate connections FMT* consumes, one batched device call
+    per expansion -- same tree, path, cost and "collision_checks" as the precomputed edge table."""
+    mp = gpu
+    if space == "double_integrator":
+        N, r = 1200, 1.0
+        SS = mp.DoubleIntegrator(2, vmax=0.5)
+        rng = np.random.Generator(np.random.PCG64(7))
+        cand = SS.lo + rng.random((4 * N, 4)) * (SS.hi - SS.lo)
+        B = orc.Boxes(fx.BOXES2D)
+        So = orc.StateSpace(SS.lo, SS.hi, ("matrix", np.hstack([np.eye(2), np.zeros((2, 2))])))
+        cand = cand[orc.states_free(B, So, cand)][:N - 2]
+        init, goal = np.array([0.1, 0.1, 0.0, 0.0]), np.array([0.9, 0.9, 0.0, 0.0])
+        V = np.vstack([init, cand, goal])
+        CC = mp.PointRobotNDBoxes([mp.BoxBounds(b) for b in fx.BOXES2D])
+        mk = lambda: mp.MPProblem(SS, init, mp.StateGoal(goal), CC, V=mp.QuasiMetricNN(V, SS.dist, init))
+        kw = dict(r=r)
+    else:
+        N = 3000
+        V = _c1_samples(mp, orc, N, 20240601, fx.ISRR_2H)
+        SS = mp.UnitHypercube(2)
+        CC = (mp.PointRobot2D(fx.product_shape(mp, fx.ISRR_2H)) if space == "euclid_sat2d"
+              else mp.PointRobotNDBoxes([mp.BoxBounds(b) for b in fx.BOXES2D]))
+        mk = lambda: mp.MPProblem(SS, [0.1, 0.1], mp.PointGoal([0.9, 0.9]), CC, V=mp.MetricNN(V, SS.dist, V[0]))
+        kw = dict(rm=1.0)
+    Pt, Pl = mk(), mk()
+    st_t, cost_t, _ = mp.fmtstar(Pt, edge_checks="table", **kw)
+    st_l, cost_l, _ = mp.fmtstar(Pl, edge_checks="lazy", **kw)
+    mt, ml = Pt.solution.metadata, Pl.solution.metadata
+    assert st_t == st_l == "solved" and cost_t == cost_l
+    assert mt["path"] == ml["path"] and np.array_equal(mt["tree"], ml["tree"])
+    assert mt["collision_checks"] == ml["collision_checks"] > 0
+    assert ml["precomputed_edge_checks"] == 0 < mt["precomputed_edge_checks"]
+    assert 0 < ml["device_edge_batches"] <= N and mt["device_edge_batches"] == 0
+    # the lazy mode asked the device about far fewer edges than the table holds
+    assert ml["collision_checks"] < mt["precomputed_edge_checks"]
+    Pt.V.close(); Pl.V.close()
