@@ -168,6 +168,14 @@ __device__ __forceinline__ bool lq_pair(const LqDev &L, const double *x0, const 
     return c <= r;                            // :221
 }
 
+// FP32 stage-1 constants of one table build (lq_prefilter)
+struct LqPre {
+    double center[3];  // positions are centred before the FP32 conversion (dp is translation invariant)
+    float R[9];        // D x D row-major
+    float c2, c3, c4;  // 4/r^2, 24/r^3, 36/r^4
+    float neg_delta;   // keep a pair when the FP32 dcost(r) exceeds this (< 0)
+};
+
 constexpr int kLqThreads = 128;
 constexpr int kLqTile = 128;
 
@@ -188,15 +196,16 @@ constexpr int kLqTile = 128;
 // peers (match.any + ballot), so rows still come out ascending without a sort.
 template <int D, int MODE>
 __global__ void __launch_bounds__(kLqThreads)
-lq_inball_kernel(const double *__restrict__ V, int64_t N, int64_t q0, int64_t nq, LqDev L, double r,
+lq_inball_kernel(const double *__restrict__ V, int64_t N, int64_t q0, int64_t nq, LqDev L, LqPre P, double r,
                  int *__restrict__ countsF, int *__restrict__ countsB, const int64_t *__restrict__ colptrF,
                  const int64_t *__restrict__ colptrB, int64_t *__restrict__ rowvalF, double *__restrict__ nzvalF,
                  int64_t *__restrict__ rowvalB, double *__restrict__ nzvalB, int cap, int *__restrict__ slabF_j,
                  double *__restrict__ slabF_c, int *__restrict__ slabB_j, double *__restrict__ slabB_c) {
     constexpr int NS = 2 * D;
+    constexpr int TS = (NS + 1 <= 4) ? 4 : 8;  // FP32 tile row: centred position, velocity, v'Rv, padded to float4s
     constexpr bool FILL = (MODE == 1);
     constexpr int kRing = 128;  // >= 31 waiting + 64 pushed per step
-    __shared__ double tile[kLqTile * NS];
+    __shared__ __align__(16) float tile[kLqTile * TS];
     __shared__ double s_x[kLqThreads * NS];
     __shared__ unsigned s_ring[kLqThreads / 32][kRing];
     __shared__ int s_cnt[2][kLqThreads];
@@ -204,11 +213,25 @@ lq_inball_kernel(const double *__restrict__ V, int64_t N, int64_t q0, int64_t nq
     const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = w < nq;
     const int64_t q = q0 + w;
-    double x[NS];
+    // stage-1 operands of this thread's query in FP32: centred position, velocity, R v, v'Rv
+    float xp[D], xv[D], Rxv[D], gx = 0.0f;
+    {
+        double x[NS];
 #pragma unroll
-    for (int i = 0; i < NS; ++i) {
-        x[i] = active ? V[q * NS + i] : 0.0;
-        s_x[threadIdx.x * NS + i] = x[i];
+        for (int i = 0; i < NS; ++i) {
+            x[i] = active ? V[q * NS + i] : 0.0;
+            s_x[threadIdx.x * NS + i] = x[i];
+        }
+#pragma unroll
+        for (int i = 0; i < D; ++i) { xp[i] = (float)(x[i] - P.center[i]); xv[i] = (float)x[D + i]; }
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            float t = 0.0f;
+#pragma unroll
+            for (int j = 0; j < D; ++j) t = fmaf(P.R[i * D + j], xv[j], t);
+            Rxv[i] = t;
+            gx = fmaf(xv[i], t, gx);
+        }
     }
     s_cnt[0][threadIdx.x] = 0;
     s_cnt[1][threadIdx.x] = 0;
@@ -230,13 +253,14 @@ lq_inball_kernel(const double *__restrict__ V, int64_t N, int64_t q0, int64_t nq
                 from[i] = dir ? y : xo;
                 to[i] = dir ? xo : y;
             }
-            if (same_state<D>(from, to)) {
-                c = 0.0;                                            // linearquadratic.jl:192 (duplicate states)
-            } else {
-                const Abg k = lq_abg<D>(L, from, to);
-                c = lq_cost(k, lq_topt_newton(k, r));
+            // the EXACT candidate test of the reference (cands = cd .> 0, linearquadratic.jl:213) decides here:
+            // stage 1 only discarded pairs that provably fail it
+            const Abg k = lq_abg<D>(L, from, to);
+            if (lq_dcost(k, r) > 0) {
+                if (same_state<D>(from, to)) c = 0.0;               // :192 (duplicate states)
+                else c = lq_cost(k, lq_topt_newton(k, r));
+                acc = c <= r;                                       // :221
             }
-            acc = c <= r;                                           // :221
         }
         const unsigned peers = __match_any_sync(0xffffffffu, have ? (item >> 26) : (0x80000000u | (unsigned)lane));
         const unsigned accm = __ballot_sync(0xffffffffu, acc);
@@ -264,19 +288,57 @@ lq_inball_kernel(const double *__restrict__ V, int64_t N, int64_t q0, int64_t nq
     for (int64_t t0 = 0; t0 < N; t0 += kLqTile) {
         const int cnt = (int)((N - t0 < kLqTile) ? (N - t0) : kLqTile);
         __syncthreads();
-        for (int i = threadIdx.x; i < cnt * NS; i += blockDim.x) tile[i] = V[t0 * NS + i];
+        for (int jj = threadIdx.x; jj < cnt; jj += blockDim.x) {  // FP32 image of the tile (one sample per thread)
+            float yv[D], g = 0.0f;
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+                tile[jj * TS + i] = (float)(V[(t0 + jj) * NS + i] - P.center[i]);
+                yv[i] = (float)V[(t0 + jj) * NS + D + i];
+                tile[jj * TS + D + i] = yv[i];
+            }
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+                float t = 0.0f;
+#pragma unroll
+                for (int j2 = 0; j2 < D; ++j2) t = fmaf(P.R[i * D + j2], yv[j2], t);
+                g = fmaf(yv[i], t, g);
+            }
+            tile[jj * TS + NS] = g;
+        }
         __syncthreads();
         for (int jj = 0; jj < cnt; ++jj) {
             const int64_t j = t0 + jj;
-            double y[NS];
-#pragma unroll
-            for (int i = 0; i < NS; ++i) y[i] = tile[jj * NS + i];
-            // stage 1: cands = cd .> 0 (linearquadratic.jl:213), both directions; j == q is dropped (nearneighbors.jl:171)
+            // stage 1, FP32 with FMA: dcost(r) = 1 - (36/r^4) dp'R dp - (4/r^2)(vx'Rvx + vx'Rvy + vy'Rvy) +- (24/r^3)(vx+vy)'R dp
+            // (+ forwards x -> y, - backwards y -> x; gamma is symmetric for symmetric R).  A pair is kept when the
+            // FP32 value exceeds -delta, delta bounding the FP32 evaluation error for this sample set (lq_prefilter):
+            // a superset of cands = cd .> 0 (linearquadratic.jl:213); stage 2 applies the exact test.
+            // j == q is dropped (nearneighbors.jl:171).
             const bool live = active && j != q;
-            Abg kF, kB;
-            lq_abg_both<D>(L, x, y, &kF, &kB);
-            const bool pf = live && (lq_dcost(kF, r) > 0);
-            const bool pb = live && (lq_dcost(kB, r) > 0);
+            float row[TS];  // one or two 16-byte broadcast reads
+#pragma unroll
+            for (int v4 = 0; v4 < TS / 4; ++v4) {
+                const float4 t4 = reinterpret_cast<const float4 *>(tile + jj * TS)[v4];
+                row[4 * v4] = t4.x; row[4 * v4 + 1] = t4.y; row[4 * v4 + 2] = t4.z; row[4 * v4 + 3] = t4.w;
+            }
+            float dp[D], sv[D], a = 0.0f, b = 0.0f, g = gx + row[NS];
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+                dp[i] = row[i] - xp[i];
+                const float yvi = row[D + i];
+                sv[i] = xv[i] + yvi;
+                g = fmaf(Rxv[i], yvi, g);
+            }
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+                float t = 0.0f;
+#pragma unroll
+                for (int j2 = 0; j2 < D; ++j2) t = fmaf(P.R[i * D + j2], dp[j2], t);
+                a = fmaf(dp[i], t, a);
+                b = fmaf(sv[i], t, b);
+            }
+            const float base = fmaf(-P.c2, g, fmaf(-P.c4, a, 1.0f));
+            const bool pf = live && (fmaf(P.c3, b, base) > P.neg_delta);
+            const bool pb = live && (fmaf(-P.c3, b, base) > P.neg_delta);
             const unsigned mf = __ballot_sync(0xffffffffu, pf), mb = __ballot_sync(0xffffffffu, pb);
             if (mf | mb) {
                 const unsigned lt = (1u << lane) - 1u;
@@ -450,6 +512,37 @@ static LqDev lq_dev(const mpb200_lq *lq) {
     return L;
 }
 
+// Stage 1 evaluates  dcost(r) = 1 - c4 a - c2 g +- c3 b  in FP32 (a = dp'R dp, b = (vx+vy)'R dp, g = vx'Rvx + vx'Rvy +
+// vy'Rvy) from FP32-rounded inputs.  Standard forward error bound for sums of products: |fl(e) - e| <= gamma_k * (sum of
+// the absolute values of the terms), gamma_k = k u / (1 - k u), u = 2^-24; every term is a product of <= 3 rounded inputs
+// reached through <= 12 roundings, so k = 24 covers it; the term magnitudes are bounded with the sample set's own
+// extents (centred positions |p| <= Mp, velocities |v| <= Mv, rho = max row sum of |R|):
+//   a <= rho D (2Mp)^2,  |b| <= rho D (2Mv)(2Mp),  g <= 3 rho D Mv^2.
+// delta = 2 * gamma_24 * (1 + c4 a_max + c3 b_max + c2 g_max): twice the bound, so no pair with exact dcost(r) > 0 is lost.
+template <int D>
+static LqPre lq_prefilter(const mpb200_samples *s, const mpb200_lq *lq, double r) {
+    LqPre P;
+    memset(&P, 0, sizeof(P));
+    double Mp = 0, Mv = 0, rho = 0;
+    for (int i = 0; i < D; ++i) {
+        P.center[i] = 0.5 * (s->h_bbox[i] + s->h_bbox[2 * D + i]);
+        Mp = fmax(Mp, fmax(fabs(s->h_bbox[i] - P.center[i]), fabs(s->h_bbox[2 * D + i] - P.center[i])));
+        Mv = fmax(Mv, fmax(fabs(s->h_bbox[D + i]), fabs(s->h_bbox[2 * D + D + i])));
+        double row = 0;
+        for (int j = 0; j < D; ++j) { P.R[i * D + j] = (float)lq->R[i * D + j]; row += fabs(lq->R[i * D + j]); }
+        rho = fmax(rho, row);
+    }
+    const double c2 = 4.0 / (r * r), c3 = 24.0 / (r * r * r), c4 = 36.0 / (r * r * r * r);
+    P.c2 = (float)c2; P.c3 = (float)c3; P.c4 = (float)c4;
+    const double u = 5.9604644775390625e-08, gk = 24.0 * u / (1.0 - 24.0 * u);
+    const double S = 1.0 + c4 * rho * D * 4.0 * Mp * Mp + c3 * rho * D * 4.0 * Mv * Mp + c2 * 3.0 * rho * D * Mv * Mv;
+    double delta = 2.0 * gk * S;
+    if (!(delta < 1e30)) delta = 1e30;  // absurd extents: the prefilter keeps everything, stage 2 still decides exactly
+    P.neg_delta = -(float)delta;
+    P.neg_delta = nextafterf(P.neg_delta, -INFINITY);
+    return P;
+}
+
 template <int D>
 static int lq_build(mpb200_samples *s, const mpb200_lq *lq, double r, mpb200_table *tF, mpb200_table *tB) {
     Context &c = ctx();
@@ -457,6 +550,7 @@ static int lq_build(mpb200_samples *s, const mpb200_lq *lq, double r, mpb200_tab
     const int64_t N = s->N, nq = s->q1 - s->q0;
     const double *V = s->V.as<double>();
     const LqDev L = lq_dev(lq);
+    const LqPre P = lq_prefilter<D>(s, lq, r);
     for (mpb200_table *t : {tF, tB}) {
         if (int rc = t->counts.reserve(sizeof(int) * (size_t)(nq + 1))) return rc;
         if (int rc = t->colptr.reserve(sizeof(int64_t) * (size_t)(nq + 1))) return rc;
@@ -471,7 +565,7 @@ static int lq_build(mpb200_samples *s, const mpb200_lq *lq, double r, mpb200_tab
         const int64_t probe = nq < 1024 ? nq : 1024;
         MPB_CUDA(cudaMemsetAsync(d_max, 0, sizeof(int), st));
         lq_inball_kernel<D, 0><<<(unsigned)ceil_div(probe, kLqThreads), kLqThreads, 0, st>>>(
-            V, N, s->q0, probe, L, r, tF->counts.as<int>(), tB->counts.as<int>(), nullptr, nullptr, nullptr, nullptr,
+            V, N, s->q0, probe, L, P, r, tF->counts.as<int>(), tB->counts.as<int>(), nullptr, nullptr, nullptr, nullptr,
             nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr);
         MPB_LAUNCHED();
         lq_max_count<<<8, 256, 0, st>>>(tF->counts.as<int>(), tB->counts.as<int>(), probe, d_max);
@@ -498,14 +592,14 @@ static int lq_build(mpb200_samples *s, const mpb200_lq *lq, double r, mpb200_tab
     }
     if (nq > 0) {
         if (single) {
-            lq_inball_kernel<D, 2><<<nb, kLqThreads, 0, st>>>(V, N, s->q0, nq, L, r, tF->counts.as<int>(),
+            lq_inball_kernel<D, 2><<<nb, kLqThreads, 0, st>>>(V, N, s->q0, nq, L, P, r, tF->counts.as<int>(),
                                                              tB->counts.as<int>(), nullptr, nullptr, nullptr, nullptr,
                                                              nullptr, nullptr, cap, slabF_j, slabF_c, slabB_j, slabB_c);
             MPB_LAUNCHED();
             MPB_CUDA(cudaMemsetAsync(d_max, 0, sizeof(int), st));
             lq_max_count<<<64, 256, 0, st>>>(tF->counts.as<int>(), tB->counts.as<int>(), nq, d_max);
         } else {
-            lq_inball_kernel<D, 0><<<nb, kLqThreads, 0, st>>>(V, N, s->q0, nq, L, r, tF->counts.as<int>(),
+            lq_inball_kernel<D, 0><<<nb, kLqThreads, 0, st>>>(V, N, s->q0, nq, L, P, r, tF->counts.as<int>(),
                                                              tB->counts.as<int>(), nullptr, nullptr, nullptr, nullptr,
                                                              nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr);
         }
@@ -536,7 +630,7 @@ static int lq_build(mpb200_samples *s, const mpb200_lq *lq, double r, mpb200_tab
             lq_slab_to_csc<<<g2, 256, 0, st>>>(slabB_j, slabB_c, cap, nq, tB->colptr.as<int64_t>(), tB->rowval.as<int64_t>(),
                                                tB->nzval.as<double>());
         } else {
-            lq_inball_kernel<D, 1><<<nb, kLqThreads, 0, st>>>(V, N, s->q0, nq, L, r, nullptr, nullptr,
+            lq_inball_kernel<D, 1><<<nb, kLqThreads, 0, st>>>(V, N, s->q0, nq, L, P, r, nullptr, nullptr,
                                                              tF->colptr.as<int64_t>(), tB->colptr.as<int64_t>(),
                                                              tF->rowval.as<int64_t>(), tF->nzval.as<double>(),
                                                              tB->rowval.as<int64_t>(), tB->nzval.as<double>(), 0, nullptr,
