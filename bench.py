@@ -268,6 +268,8 @@ class Job:
             nnz0 = self.NN.build_table(self.r)
             self.exchange = sharding.make_exchange(q1 - q0, (nnz0 * 21 // 20 + 63) // 64 + 2)
             self.exchange_kind = "peer-stores" if isinstance(self.exchange, sharding.PeerExchange) else "nccl-allgather"
+            if self.exchange_kind == "peer-stores":
+                self.exchange.attach(self.NN.table)   # column lengths leave right after the count scan, under the fill
         self.nnz = 0
         self.pushes = 0
         self.exchange_ms = []

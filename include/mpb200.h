@@ -287,6 +287,10 @@ typedef struct mpb200_xchg mpb200_xchg;
 #define MPB200_XCHG_MAX_WORLD 16
 int mpb200_xchg_create(int rank, int world, int64_t max_ncols, int64_t word_cap, mpb200_xchg **out, void *ipc_handle);
 int mpb200_xchg_connect(mpb200_xchg *x, const void *handles /* world x 64 bytes, rank order */);
+/* Optional: tie a table handle to the exchange.  Every later mpb200_inball_build on it starts sending the column
+ * lengths of the coming epoch right after its count scan, on a side stream underneath the fill and validity
+ * kernels; the following mpb200_xchg_push then only sends the validity words.  x = NULL detaches. */
+int mpb200_xchg_attach(mpb200_xchg *x, mpb200_table *t);
 int mpb200_xchg_push(mpb200_xchg *x, const mpb200_table *t);
 int mpb200_xchg_view(const mpb200_xchg *x, void **recv, int64_t *slot_bytes, int64_t *counts_off, int64_t *words_off,
                      int64_t *status);

@@ -91,6 +91,7 @@ SIGNATURES = {
     "mpb200_close_points": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, ctypes.c_int, c_dbl, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "mpb200_xchg_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, c_i64, c_i64, P(c_vp), c_vp]),
     "mpb200_xchg_connect": (ctypes.c_int, [c_vp, c_vp]),
+    "mpb200_xchg_attach": (ctypes.c_int, [c_vp, c_vp]),
     "mpb200_xchg_push": (ctypes.c_int, [c_vp, c_vp]),
     "mpb200_xchg_view": (ctypes.c_int, [c_vp, P(c_vp), P(c_i64), P(c_i64), P(c_i64), P(c_i64)]),
     "mpb200_xchg_destroy": (ctypes.c_int, [c_vp]),

@@ -89,7 +89,14 @@ static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 }  // namespace mpb
 
 // ---- handle layouts (opaque in the C ABI) ---------------------------------------
+struct mpb200_xchg;
+struct mpb200_table;
+namespace mpb {
+// xchg.cu: start sending an attached table's column lengths right after its count scan (side stream)
+int xchg_push_counts_early(mpb200_xchg *x, const mpb200_table *t, const int64_t *colptr, int64_t ncols);
+}
 struct mpb200_table {
+    mpb200_xchg *xchg = nullptr;  // exchange this table's builds feed (mpb200_xchg_attach), or NULL
     int64_t ncols = 0;     // columns in this shard
     int64_t col0 = 0;      // first global column (0-based)
     int64_t nnz = 0;

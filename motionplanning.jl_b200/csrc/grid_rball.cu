@@ -842,6 +842,10 @@ static int build_table(mpb200_samples *s, double r, mpb200_table *t) {
         if (int rc = front()) return rc;
     }
     phase_mark(1);
+    // sharded build attached to an exchange: the column lengths are final now -- they go out to the peers on a
+    // side stream while this stream runs the fill and the validity kernels
+    if (t->xchg && nq > 0)
+        if (int rc = xchg_push_counts_early(t->xchg, t, t->colptr.as<int64_t>(), nq)) return rc;
     phase_mark(2);
     static const int fill_u = [] { const char *e = getenv("MPB200_FILL_U"); return e ? atoi(e) : 2; }();
     auto launch_fill = [&](const int64_t *guard, int64_t capacity) -> int {

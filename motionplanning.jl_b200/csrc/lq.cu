@@ -174,6 +174,7 @@ struct LqPre {
     float R[9];        // D x D row-major
     float c2, c3, c4;  // 4/r^2, 24/r^3, 36/r^4
     float neg_delta;   // keep a pair when the FP32 dcost(r) exceeds this (< 0)
+    float r2, delta2;  // ... and a (16 g - r^2) - 12 b^2 <= delta2 (second necessary condition, see lq_prefilter)
 };
 
 constexpr int kLqThreads = 128;
@@ -195,7 +196,7 @@ constexpr int kLqTile = 128;
 // FIFO order; inside a batch the slot is the owner's running count plus the number of accepted earlier
 // peers (match.any + ballot), so rows still come out ascending without a sort.
 template <int D, int MODE>
-__global__ void __launch_bounds__(kLqThreads)
+__global__ void __launch_bounds__(kLqThreads, 4)  // 100 registers, no spills (the default heuristic spilled the stage-1 state)
 lq_inball_kernel(const double *__restrict__ V, int64_t N, int64_t q0, int64_t nq, LqDev L, LqPre P, double r,
                  int *__restrict__ countsF, int *__restrict__ countsB, const int64_t *__restrict__ colptrF,
                  const int64_t *__restrict__ colptrB, int64_t *__restrict__ rowvalF, double *__restrict__ nzvalF,
@@ -306,6 +307,7 @@ lq_inball_kernel(const double *__restrict__ V, int64_t N, int64_t q0, int64_t nq
             tile[jj * TS + NS] = g;
         }
         __syncthreads();
+        const int q_in_tile = (active && q >= t0 && q < t0 + cnt) ? (int)(q - t0) : -1;  // j == q as a 32-bit compare
         for (int jj = 0; jj < cnt; ++jj) {
             const int64_t j = t0 + jj;
             // stage 1, FP32 with FMA: dcost(r) = 1 - (36/r^4) dp'R dp - (4/r^2)(vx'Rvx + vx'Rvy + vy'Rvy) +- (24/r^3)(vx+vy)'R dp
@@ -313,7 +315,7 @@ lq_inball_kernel(const double *__restrict__ V, int64_t N, int64_t q0, int64_t nq
             // FP32 value exceeds -delta, delta bounding the FP32 evaluation error for this sample set (lq_prefilter):
             // a superset of cands = cd .> 0 (linearquadratic.jl:213); stage 2 applies the exact test.
             // j == q is dropped (nearneighbors.jl:171).
-            const bool live = active && j != q;
+            const bool live = active && jj != q_in_tile;
             float row[TS];  // one or two 16-byte broadcast reads
 #pragma unroll
             for (int v4 = 0; v4 < TS / 4; ++v4) {
@@ -337,8 +339,13 @@ lq_inball_kernel(const double *__restrict__ V, int64_t N, int64_t q0, int64_t nq
                 b = fmaf(sv[i], t, b);
             }
             const float base = fmaf(-P.c2, g, fmaf(-P.c4, a, 1.0f));
-            const bool pf = live && (fmaf(P.c3, b, base) > P.neg_delta);
-            const bool pb = live && (fmaf(-P.c3, b, base) > P.neg_delta);
+            // second necessary condition, the same for both directions: cost(t) = t + (alpha u^2 - beta u + gamma)/t with
+            // u = 1/t >= t + D/t, D = gamma - beta^2/(4 alpha), so cost <= r needs 2 sqrt(D) <= r, i.e.
+            // a (16 g - r^2) - 12 b^2 <= 0 (alpha = 12a, beta = +-12b, gamma = 4g).  98% of the dcost(r) > 0 candidates
+            // fail it -- pairs whose optimum lies before r but costs more than r -- and never reach the Newton stage.
+            const bool near = live && (fmaf(-12.0f * b, b, a * fmaf(16.0f, g, -P.r2)) <= P.delta2);
+            const bool pf = near && (fmaf(P.c3, b, base) > P.neg_delta);
+            const bool pb = near && (fmaf(-P.c3, b, base) > P.neg_delta);
             const unsigned mf = __ballot_sync(0xffffffffu, pf), mb = __ballot_sync(0xffffffffu, pb);
             if (mf | mb) {
                 const unsigned lt = (1u << lane) - 1u;
@@ -540,6 +547,15 @@ static LqPre lq_prefilter(const mpb200_samples *s, const mpb200_lq *lq, double r
     if (!(delta < 1e30)) delta = 1e30;  // absurd extents: the prefilter keeps everything, stage 2 still decides exactly
     P.neg_delta = -(float)delta;
     P.neg_delta = nextafterf(P.neg_delta, -INFINITY);
+    // w = a (16 g - r^2) - 12 b^2: same error model, 16 roundings deep; twice the bound again.  A pair is dropped only
+    // if w > delta2, i.e. exactly 4 D - r^2 = w / a >= delta2 / (2 a_max) > 0: its cost exceeds r by a margin many
+    // orders above the FP64 rounding of the reference's own cost evaluation.
+    const double am = rho * D * 4.0 * Mp * Mp, bm = rho * D * 4.0 * Mv * Mp, gm = 3.0 * rho * D * Mv * Mv;
+    const double g16 = 16.0 * u / (1.0 - 16.0 * u);
+    double d2 = 2.0 * g16 * (am * (16.0 * gm + r * r) + 12.0 * bm * bm);
+    if (!(d2 < 1e30)) d2 = 1e30;
+    P.r2 = (float)(r * r);
+    P.delta2 = nextafterf((float)d2, INFINITY);
     return P;
 }
 

@@ -25,6 +25,12 @@ struct mpb200_xchg {
     char *peer[MPB200_XCHG_MAX_WORLD] = {};  // mapped blocks of every rank (peer[rank] == local)
     bool connected = false;
     unsigned long long epoch = 0;       // epochs pushed so far
+    // early push of the column lengths (mpb200_xchg_attach): they are final after the count scan, so they travel on
+    // a side stream underneath the fill and validity kernels; mpb200_xchg_push then only sends the validity words
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    unsigned long long counts_epoch = 0;  // epoch whose column lengths are already on their way
+    const mpb200_table *counts_table = nullptr;
 };
 
 namespace mpb {
@@ -34,20 +40,21 @@ constexpr int kStatusWord = 64;   // index (in 8-byte words) of the error flag
 
 struct PeerPtrs { char *p[MPB200_XCHG_MAX_WORLD]; };
 
-// header (first 64 bytes of a slot): ncols, nnz, epoch
+// header (first 64 bytes of a slot): ncols, nnz, epoch.  what: bit 0 = column lengths, bit 1 = header + validity words
 __global__ void __launch_bounds__(256)
 xchg_push_kernel(const int64_t *__restrict__ colptr, int64_t ncols, const uint4 *__restrict__ words16, int64_t n_words,
-                 int64_t nnz, unsigned long long epoch, PeerPtrs dst, int world, int64_t counts_off, int64_t words_off) {
+                 int64_t nnz, unsigned long long epoch, PeerPtrs dst, int world, int64_t counts_off, int64_t words_off,
+                 int what) {
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
-    if (tid == 0) {
+    if (tid == 0 && (what & 2)) {
         for (int p = 0; p < world; ++p) {
             long long *h = reinterpret_cast<long long *>(dst.p[p]);
             h[0] = ncols; h[1] = nnz; h[2] = (long long)epoch;
         }
     }
     // column lengths: four int32 per 16-byte store
-    const int64_t n4 = (ncols + 3) >> 2;
+    const int64_t n4 = (what & 1) ? ((ncols + 3) >> 2) : 0;
     for (int64_t i = tid; i < n4; i += nthr) {
         int c[4];
 #pragma unroll
@@ -59,7 +66,7 @@ xchg_push_kernel(const int64_t *__restrict__ colptr, int64_t ncols, const uint4 
         for (int p = 0; p < world; ++p) reinterpret_cast<uint4 *>(dst.p[p] + counts_off)[i] = v;
     }
     // validity words: two uint64 per 16-byte store (the table's buffer is padded to a whole number of them)
-    const int64_t n16 = (n_words + 1) >> 1;
+    const int64_t n16 = (what & 2) ? ((n_words + 1) >> 1) : 0;
     for (int64_t i = tid; i < n16; i += nthr) {
         uint4 v = words16[i];
         if (2 * i + 1 >= n_words) { v.z = 0; v.w = 0; }
@@ -102,6 +109,36 @@ xchg_barrier_kernel(PeerPtrs flags, unsigned long long *__restrict__ own_flags, 
 
 }  // namespace mpb
 
+namespace mpb {
+static void xchg_slots(const mpb200_xchg *x, unsigned long long epoch, PeerPtrs *dst, PeerPtrs *flags) {
+    const int64_t set = x->data_off + (int64_t)(epoch & 1) * x->set_bytes + (int64_t)x->rank * x->slot_bytes;
+    for (int p = 0; p < MPB200_XCHG_MAX_WORLD; ++p) {
+        dst->p[p] = p < x->world ? x->peer[p] + set : nullptr;
+        flags->p[p] = p < x->world ? x->peer[p] : nullptr;
+    }
+}
+
+// Called by the table builds right after the column-pointer scan (the table is attached to an exchange): the
+// column lengths of the UPCOMING epoch go out on the side stream while the main stream runs the fill.
+int xchg_push_counts_early(mpb200_xchg *x, const mpb200_table *t, const int64_t *colptr, int64_t ncols) {
+    if (!x || !(x->connected || x->world == 1) || ncols > x->max_ncols) return 0;  // push() reports misuse
+    Context &c = ctx();
+    const unsigned long long epoch = x->epoch + 1;
+    PeerPtrs dst, flags;
+    xchg_slots(x, epoch, &dst, &flags);
+    MPB_CUDA(cudaEventRecord(x->ev_fork, c.stream));
+    MPB_CUDA(cudaStreamWaitEvent(x->side, x->ev_fork, 0));
+    const unsigned grid = (unsigned)std::min<int64_t>(std::max<int64_t>(ceil_div((ncols + 3) / 4, 256), 1), (int64_t)c.sm_count);
+    xchg_push_kernel<<<grid, 256, 0, x->side>>>(colptr, ncols, nullptr, 0, 0, epoch, dst, x->world, x->counts_off,
+                                                x->words_off, 1);
+    MPB_LAUNCHED();
+    MPB_CUDA(cudaEventRecord(x->ev_join, x->side));
+    x->counts_epoch = epoch;
+    x->counts_table = t;
+    return 0;
+}
+}  // namespace mpb
+
 using namespace mpb;
 
 extern "C" {
@@ -135,7 +172,19 @@ int mpb200_xchg_create(int rank, int world, int64_t max_ncols, int64_t word_cap,
         return fail(MPB200_ECUDA, "cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
     }
     x->peer[rank] = x->local;
+    if (cudaStreamCreateWithFlags(&x->side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&x->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&x->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        mpb200_xchg_destroy(x);
+        return fail(MPB200_ECUDA, "could not create the exchange's side stream");
+    }
     *out = x;
+    return MPB200_OK;
+}
+
+int mpb200_xchg_attach(mpb200_xchg *x, mpb200_table *t) {
+    MPB_CHECK_ARG(t != nullptr, "table handle is NULL");
+    t->xchg = x;  // NULL detaches
     return MPB200_OK;
 }
 
@@ -171,18 +220,17 @@ int mpb200_xchg_push(mpb200_xchg *x, const mpb200_table *t) {
     Context &c = ctx();
     cudaStream_t st = c.stream;
     const unsigned long long epoch = ++x->epoch;
-    const int64_t set = x->data_off + (int64_t)(epoch & 1) * x->set_bytes + (int64_t)x->rank * x->slot_bytes;
     PeerPtrs dst, flags;
-    for (int p = 0; p < MPB200_XCHG_MAX_WORLD; ++p) {
-        dst.p[p] = p < x->world ? x->peer[p] + set : nullptr;
-        flags.p[p] = p < x->world ? x->peer[p] : nullptr;
-    }
+    xchg_slots(x, epoch, &dst, &flags);
     phase_bank(MPB200_OP_OTHER);
     phase_mark(0);
-    const int64_t units = std::max<int64_t>((t->ncols + 3) / 4, (n_words + 1) / 2);
+    // column lengths already under way on the side stream (attached table, pushed right after its count scan)?
+    const bool early = x->counts_epoch == epoch && x->counts_table == t;
+    if (early) MPB_CUDA(cudaStreamWaitEvent(st, x->ev_join, 0));
+    const int64_t units = std::max<int64_t>(early ? 0 : (t->ncols + 3) / 4, (n_words + 1) / 2);
     const unsigned grid = (unsigned)std::min<int64_t>(std::max<int64_t>(ceil_div(units, 256), 1), (int64_t)c.sm_count * 4);
     xchg_push_kernel<<<grid, 256, 0, st>>>(t->colptr.as<int64_t>(), t->ncols, t->edge_bits.as<uint4>(), n_words, t->nnz,
-                                           epoch, dst, x->world, x->counts_off, x->words_off);
+                                           epoch, dst, x->world, x->counts_off, x->words_off, early ? 2 : 3);
     MPB_LAUNCHED();
     xchg_barrier_kernel<<<1, 32, 0, st>>>(flags, reinterpret_cast<unsigned long long *>(x->local), x->rank, x->world,
                                           epoch, 20LL * 1000 * 1000 * 1000);
@@ -216,6 +264,9 @@ int mpb200_xchg_destroy(mpb200_xchg *x) {
     if (ctx().ready) cudaStreamSynchronize(ctx().stream);
     for (int p = 0; p < x->world; ++p)
         if (p != x->rank && x->peer[p]) cudaIpcCloseMemHandle(x->peer[p]);
+    if (x->side) { cudaStreamSynchronize(x->side); cudaStreamDestroy(x->side); }
+    if (x->ev_fork) cudaEventDestroy(x->ev_fork);
+    if (x->ev_join) cudaEventDestroy(x->ev_join);
     if (x->local) cudaFree(x->local);
     delete x;
     return MPB200_OK;

@@ -223,6 +223,14 @@ class PeerExchange:
         _lib.check(lib.mpb200_xchg_connect(self.h, buf))
         dist.barrier(group=group)   # every rank has mapped every buffer before the first push
 
+    def attach(self, table):
+        """later builds of `table` send their column lengths early, underneath the fill (mpb200_xchg_attach);
+        call again after the table handle changes (the first build creates it)"""
+        from . import _lib
+        if table.h:
+            _lib.check(_lib.lib().mpb200_xchg_attach(self.h, table.h))
+            self._attached = table
+
     def run(self, table):
         from . import _lib
         _lib.check(_lib.lib().mpb200_xchg_push(self.h, table.h))
@@ -244,6 +252,9 @@ class PeerExchange:
     def close(self):
         from . import _lib
         if self.h:
+            t = getattr(self, "_attached", None)
+            if t is not None and t.h:
+                _lib.load().mpb200_xchg_attach(None, t.h)   # the table must not keep a pointer to a dead exchange
             torch.cuda.synchronize()
             dist.barrier(group=self.group)   # no peer may still be storing into a buffer that is about to be freed
             _lib.load().mpb200_xchg_destroy(self.h)

@@ -39,6 +39,8 @@ def main():
         nnz = NN.build_table(r)
         NN.edges_free(NN.table, CC, SS, fetch=False)
         ex = sharding.make_exchange(q1 - q0, (nnz + 63) // 64 + 1, kind=kind)
+        if kind == "peer":
+            ex.attach(NN.table)                            # column lengths travel early, under the fill
         for _ in range(3):                                 # several epochs: the alternating buffer sets and the flag barrier
             NN.build_table(r)
             NN.edges_free(NN.table, CC, SS, fetch=False, count=False)
