@@ -510,35 +510,23 @@ rball_fill(const double *__restrict__ sorted_pos, const int *__restrict__ sorted
         for (int v = 0; v < NV; ++v) s_rec[v][threadIdx.x] = make_int4(rec[4 * v], rec[4 * v + 1], rec[4 * v + 2], rec[4 * v + 3]);
     }
     __syncwarp();
-    // The tile's columns are taken U at a time from two lists: first those with at most 32 entries (one key per
-    // lane, the 15-stage network), then the longer ones (two keys per lane, 21 stages on twice the registers) --
-    // with pairs taken in tile order 31% of the groups paid for the long network because ONE of their columns
-    // needed it (17% of the columns do); empty columns are skipped altogether.
-    const unsigned m_small = __ballot_sync(0xffffffffu, k_mine > 0 && k_mine <= 32);
-    const unsigned m_large = __ballot_sync(0xffffffffu, k_mine > 32);
-    unsigned todo = m_small;
-    int rounds = 1;  // warp-uniform
-    while (true) {
-        if (todo == 0) {
-            if (rounds == 2 || m_large == 0) break;
-            todo = m_large;
-            rounds = 2;
-        }
-        int col[U], kc[U];
+    for (int cl0 = 0; cl0 < 32; cl0 += U) {
+        int kc[U];
         unsigned key[U][2];
+        int kmax = 0;
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            col[u] = todo ? (__ffs(todo) - 1) : -1;
-            todo &= todo - 1;  // (0 & anything) stays 0
-            kc[u] = col[u] >= 0 ? __shfl_sync(0xffffffffu, k_mine, col[u]) : 0;
-            col[u] = col[u] >= 0 ? col[u] : 0;
+            kc[u] = __shfl_sync(0xffffffffu, k_mine, cl0 + u);
+            kmax = max(kmax, kc[u]);
         }
+        if (kmax == 0) continue;
+        const int rounds = (kmax > 32) ? 2 : 1;  // warp-uniform
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             int rec[NV * 4];
 #pragma unroll
-            for (int v = 0; v < NV; ++v) {   // broadcast reads of column col[u]'s record
-                const int4 q = s_rec[v][wid * 32 + col[u]];
+            for (int v = 0; v < NV; ++v) {   // broadcast reads of column (cl0 + u)'s record
+                const int4 q = s_rec[v][wid * 32 + cl0 + u];
                 rec[4 * v] = q.x; rec[4 * v + 1] = q.y; rec[4 * v + 2] = q.z; rec[4 * v + 3] = q.w;
             }
             double pc[D];
@@ -550,7 +538,7 @@ rball_fill(const double *__restrict__ sorted_pos, const int *__restrict__ sorted
                 key[u][h] = 0xffffffffu;
                 const int e = lane + 32 * h;
                 if (h < rounds && e < kc[u]) {
-                    int j = tile_list[e * 32 + col[u]];  // candidate number of the e-th hit of this column
+                    int j = tile_list[e * 32 + cl0 + u];  // candidate number of the e-th hit of this column
                     int kp = 0;
 #pragma unroll
                     for (int r = 0; r < kRuns; ++r) {  // run containing candidate j
@@ -593,7 +581,7 @@ rball_fill(const double *__restrict__ sorted_pos, const int *__restrict__ sorted
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const int2 bw = reinterpret_cast<const int2 *>(&s_rec[kWBase / 4][wid * 32 + col[u]])[(kWBase % 4) / 2];
+            const int2 bw = reinterpret_cast<const int2 *>(&s_rec[kWBase / 4][wid * 32 + cl0 + u])[(kWBase % 4) / 2];
             const long long basec = ((long long)bw.y << 32) | (unsigned)bw.x;
             const int ru = (kc[u] > 32) ? 2 : (kc[u] > 0 ? 1 : 0);  // warp-uniform
             for (int h = 0; h < ru; ++h) {
