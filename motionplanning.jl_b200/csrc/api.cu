@@ -7,6 +7,7 @@
 #include <cstring>
 #include <limits>
 #include <algorithm>
+#include <emmintrin.h>
 #include <new>
 #include <thread>
 #include <vector>
@@ -495,7 +496,7 @@ __global__ void __launch_bounds__(256) narrow_rows_kernel(const int64_t *__restr
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         out[i] = (int32_t)in[i];
 }
-constexpr int kFetchChunks = 16;
+constexpr int kFetchChunks = 32;
 void *g_pin = nullptr;  // pinned staging for the narrowed indices (library-owned, grows, reused)
 size_t g_pin_cap = 0;
 cudaEvent_t g_fetch_ev[kFetchChunks] = {};
@@ -530,14 +531,20 @@ static int fetch_rows_narrow(mpb200_table *t, int64_t *rowval, cudaStream_t st, 
     }
     // widening threads: chunk k is converted as soon as its copy has landed (the nzval copy queued behind keeps the bus busy)
     const int device = ctx().device;
-    const int nthreads = (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+    static const int env_threads = [] { const char *e = getenv("MPB200_FETCH_THREADS"); return e ? atoi(e) : 0; }();
+    const int nthreads = env_threads > 0 ? std::min(env_threads, kFetchChunks)
+                                         : (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
     for (int w = 0; w < nthreads; ++w)
         workers->emplace_back([=]() {
             cudaSetDevice(device);
             for (int k = w; k < kFetchChunks; k += nthreads) {
                 cudaEventSynchronize(g_fetch_ev[k]);
                 const int64_t a = std::min<int64_t>(k * per, nnz), b = std::min<int64_t>(a + per, nnz);
-                for (int64_t i = a; i < b; ++i) rowval[i] = (int64_t)h32[i];
+                // streaming stores: the destination is written once and not read here (no read-for-ownership traffic
+                // on a memory bus that is taking the nzval DMA at the same time)
+                long long *dst = reinterpret_cast<long long *>(rowval);
+                for (int64_t i = a; i < b; ++i) _mm_stream_si64(dst + i, (long long)h32[i]);
+                _mm_sfence();
             }
         });
     return 0;

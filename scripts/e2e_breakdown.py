@@ -8,7 +8,7 @@ from bench import fmt_radius, make_samples
 lib = _lib.load()
 N = 1_000_000
 r = fmt_radius(N, 2)
-V_host = torch.from_numpy(np.ascontiguousarray(make_samples(N))).pin_memory()
+V_host = torch.from_numpy(np.ascontiguousarray(make_samples(N, False))).pin_memory()
 V = V_host.numpy()
 CC = mpb200.PointRobot2D(mpb200.obstaclesets.ISRR_2H()); SS = mpb200.UnitHypercube(2); CC.handle()
 pool = _lib.PinnedPool(reuse=True)
