@@ -508,6 +508,14 @@ def main():
     parity_cols = parity_check(job, rank, world)
     (_,), (parity_all,) = allreduce_max_sum([0.0], [float(parity_cols)], world)
 
+    # what the output format alone costs: the table's write pattern without any neighbour work (csrc/peaks.cu)
+    write_floor_ms = None
+    if rank == 0:
+        import ctypes
+        v = ctypes.c_double(0.0)
+        if lib.mpb200_table_write_floor(job.NN.table.h, ctypes.byref(v)) == 0:
+            write_floor_ms = v.value
+
     other = None
     if world > 1:
         # the other scaling mode, same code path, fewer steps
@@ -613,7 +621,11 @@ def main():
                     "ms_per_step": 1e3 * e2e_s, "steps": args.e2e_steps},
             "roofline": {"kernel": "rball_fill<2>", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": fill_traffic(), "peak_kind": peak_kind,
-                         "algorithmic_bytes_per_launch": alg_bytes},
+                         "algorithmic_bytes_per_launch": alg_bytes,
+                         "write_pattern_floor_ms": write_floor_ms, "kernel_ms": fill_ms,
+                         "frac_of_write_pattern_floor": (write_floor_ms / fill_ms) if write_floor_ms else None,
+                         "note": "write_pattern_floor = a kernel that only writes the same column bursts in the same order "
+                                 "(mpb200_table_write_floor): the cost of the reference's CSC format for samples numbered as drawn"},
         }
         if world == 1 and not args.no_cpu_baseline:
             # the oracle port on this box's host cores: full workload, single thread (the reference is

@@ -304,6 +304,11 @@ int mpb200_xchg_destroy(mpb200_xchg *x);
 #define MPB200_PEAK_DFMA 1
 #define MPB200_PEAK_FFMA 2
 int mpb200_pipe_peak(int kind, double *ops_per_s);
+/* Duration (ms, CUDA events, best of 3 after an L2 eviction) of a kernel that does nothing but WRITE a table of
+ * t's shape: every column as one contiguous Int64 + one Float64 burst at colptr[w], columns visited in the order the
+ * fill kernel visits them, constant data.  This is what the reference's CSC output format costs on the device before
+ * any neighbour work: the floor the fill kernel's time is compared with, next to the plain-copy HBM peak. */
+int mpb200_table_write_floor(const mpb200_table *t, double *ms);
 
 #ifdef __cplusplus
 }

@@ -95,6 +95,7 @@ SIGNATURES = {
     "mpb200_xchg_push": (ctypes.c_int, [c_vp, c_vp]),
     "mpb200_xchg_view": (ctypes.c_int, [c_vp, P(c_vp), P(c_i64), P(c_i64), P(c_i64), P(c_i64)]),
     "mpb200_xchg_destroy": (ctypes.c_int, [c_vp]),
+    "mpb200_table_write_floor": (ctypes.c_int, [c_vp, P(c_dbl)]),
     "mpb200_pipe_peak": (ctypes.c_int, [ctypes.c_int, P(c_dbl)]),
     "mpb200_lq_motions_free": (ctypes.c_int, [c_vp, c_dbl, c_vp, c_vp, c_i64, c_vp, P(SpaceDesc), c_vp, P(c_i64)]),
 }

@@ -193,6 +193,7 @@ int lq_motions_free_device(const mpb200_lq *lq, double r, const double *dA, cons
                            unsigned long long *d_checks);
 
 int pipe_peak_device(int kind, double *ops_per_s);
+int table_write_floor_device(const mpb200_table *t, double *ms);
 int close_points_device(const mpb200_obstacles *o, const double *dP, const double *dW, int64_t n, int dw, double r2,
                         int *d_count, double *d_d2, int *d_shape, double *d_x, double *d_all_d2, double *d_all_x);
 int lqg_setup_host(int n, int m, const double *A, const double *B, const double *c, const double *R, LqgHost *S);
@@ -992,6 +993,13 @@ int mpb200_close_points(const mpb200_obstacles *o, const double *p_aos, const do
     if (all_x) MPB_CUDA(cudaMemcpyAsync(all_x, bAX.p, sizeof(double) * nS * dw, cudaMemcpyDeviceToHost, st));
     MPB_CUDA(cudaStreamSynchronize(st));
     return MPB200_OK;
+}
+
+int mpb200_table_write_floor(const mpb200_table *t, double *ms) {
+    MPB_REQUIRE_INIT();
+    MPB_CHECK_ARG(t != nullptr && ms != nullptr, "NULL argument");
+    MPB_CHECK_ARG(t->ncols > 0 && t->nnz > 0, "empty table");
+    return table_write_floor_device(t, ms);
 }
 
 int mpb200_pipe_peak(int kind, double *ops_per_s) {

@@ -10,6 +10,7 @@
 //   MPB200_PEAK_DFMA       __fma_rn double                     (the advertised FP64 figure / 2 per FMA)
 //   MPB200_PEAK_FFMA       __fmaf_rn                           (FP32 CUDA-core peak, for the FP32 prefilter)
 #include "common.cuh"
+#include <algorithm>
 
 namespace mpb {
 
@@ -42,6 +43,60 @@ __global__ void __launch_bounds__(256) pipe_peak_kernel(int iters, double seed, 
 #pragma unroll
     for (int c = 0; c < kPeakChains; ++c) t += a[c] + (double)f[c];
     if (t == 123.456) sink[0] = t;  // never true: keeps the chains alive
+}
+
+// ---- the write pattern of a CSC table, alone -----------------------------------------------------------------
+// rball_fill has to emit every column as one contiguous Int64 burst + one Float64 burst (~220 B each at the FMT*
+// radius) at colptr[w], and it visits the columns in GRID-CELL order while colptr runs in sample-index order: for
+// samples numbered as drawn the bursts land at random offsets of a 440 MB range.  This kernel does ONLY that -- one
+// warp per column, same visiting order, same streaming stores, constant data, no candidate loads, no distance, no
+// sort -- so its duration is what the output format costs on this device before any neighbour work is done: the
+// floor rball_fill can be compared with, next to the plain-copy HBM peak.
+__global__ void __launch_bounds__(256)
+table_write_pattern_kernel(const int64_t *__restrict__ colptr, const int *__restrict__ order, int64_t ncols,
+                           long long *__restrict__ rowval, double *__restrict__ nzval) {
+    const int lane = threadIdx.x & 31;
+    const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t t = gw; t < ncols; t += nw) {
+        const int64_t w = order ? order[t] : t;
+        const int64_t base = colptr[w] - 1;
+        const int k = (int)(colptr[w + 1] - colptr[w]);
+        for (int e = lane; e < k; e += 32) {
+            __stcs(rowval + base + e, (long long)(e + 1));
+            __stcs(nzval + base + e, 1.0);
+        }
+    }
+}
+
+int table_write_floor_device(const mpb200_table *t, double *ms) {
+    Context &c = ctx();
+    cudaStream_t st = c.stream;
+    static DevBuf rv, nz;
+    if (int rc = rv.reserve(sizeof(int64_t) * (size_t)(t->nnz + 1))) return rc;
+    if (int rc = nz.reserve(sizeof(double) * (size_t)(t->nnz + 1))) return rc;
+    cudaEvent_t e0, e1;
+    MPB_CUDA(cudaEventCreate(&e0));
+    MPB_CUDA(cudaEventCreate(&e1));
+    float best = 1e30f;
+    const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(t->ncols > 0 ? t->ncols : 1, 8), (int64_t)c.sm_count * 16);
+    for (int rep = 0; rep < 4; ++rep) {
+        MPB_CUDA(cudaMemsetAsync(rv.p, 0, 512 << 20 < rv.cap ? (size_t)(512 << 20) : rv.cap, st));  // evict the table from L2
+        MPB_CUDA(cudaEventRecord(e0, st));
+        table_write_pattern_kernel<<<grid, 256, 0, st>>>(t->colptr.as<int64_t>(), t->has_order ? t->col_order.as<int>() : nullptr,
+                                                         t->ncols, rv.as<long long>(), nz.as<double>());
+        MPB_LAUNCHED();
+        MPB_CUDA(cudaEventRecord(e1, st));
+        MPB_CUDA(cudaEventSynchronize(e1));
+        float m = 0;
+        MPB_CUDA(cudaEventElapsedTime(&m, e0, e1));
+        if (rep > 0 && m < best) best = m;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    rv.release();
+    nz.release();
+    *ms = best;
+    return 0;
 }
 
 int pipe_peak_device(int kind, double *ops_per_s) {
