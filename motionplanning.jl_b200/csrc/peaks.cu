@@ -11,6 +11,8 @@
 //   MPB200_PEAK_FFMA       __fmaf_rn                           (FP32 CUDA-core peak, for the FP32 prefilter)
 #include "common.cuh"
 #include <algorithm>
+#include <cstdlib>
+#include <vector>
 
 namespace mpb {
 
@@ -57,13 +59,23 @@ table_write_pattern_kernel(const int64_t *__restrict__ colptr, const int *__rest
                            long long *__restrict__ rowval, double *__restrict__ nzval) {
     const int lane = threadIdx.x & 31;
     const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t t = gw; t < ncols; t += nw) {
-        const int64_t w = order ? order[t] : t;
-        const int64_t base = colptr[w] - 1;
-        const int k = (int)(colptr[w + 1] - colptr[w]);
-        for (int e = lane; e < k; e += 32) {
-            __stcs(rowval + base + e, (long long)(e + 1));
-            __stcs(nzval + base + e, 1.0);
+    // a warp takes 32 columns at a time: every lane fetches one column's extent (32 independent gathers in flight,
+    // as in rball_fill, where thread t owns the record of query t), then the warp writes the columns one after the other
+    for (int64_t t0 = gw * 32; t0 < ncols; t0 += nw * 32) {
+        long long my_base = 0;
+        int my_k = 0;
+        if (t0 + lane < ncols) {
+            const int64_t w = order ? order[t0 + lane] : t0 + lane;
+            my_base = colptr[w] - 1;
+            my_k = (int)(colptr[w + 1] - colptr[w]);
+        }
+        for (int c = 0; c < 32; ++c) {
+            const long long base = __shfl_sync(0xffffffffu, my_base, c);
+            const int k = __shfl_sync(0xffffffffu, my_k, c);
+            for (int e = lane; e < k; e += 32) {
+                __stcs(rowval + base + e, (long long)(e + 1));
+                __stcs(nzval + base + e, 1.0);
+            }
         }
     }
 }
@@ -78,11 +90,30 @@ int table_write_floor_device(const mpb200_table *t, double *ms) {
     MPB_CUDA(cudaEventCreate(&e0));
     MPB_CUDA(cudaEventCreate(&e1));
     float best = 1e30f;
-    const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(t->ncols > 0 ? t->ncols : 1, 8), (int64_t)c.sm_count * 16);
+    const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(t->ncols > 0 ? t->ncols : 1, 8 * 32), (int64_t)c.sm_count * 16);
+    const int *order = t->has_order ? t->col_order.as<int>() : nullptr;
+    // experiment (MPB200_FLOOR_BANDS=B): the same columns visited band by band (B index ranges), cell order inside a band
+    static DevBuf banded;
+    const char *eb = getenv("MPB200_FLOOR_BANDS");
+    const int bands = eb ? atoi(eb) : 0;
+    if (bands > 1 && order) {
+        std::vector<int> h((size_t)t->ncols), o;
+        MPB_CUDA(cudaMemcpyAsync(h.data(), order, sizeof(int) * (size_t)t->ncols, cudaMemcpyDeviceToHost, st));
+        MPB_CUDA(cudaStreamSynchronize(st));
+        const int64_t per = ceil_div(t->ncols, bands);
+        o.reserve(h.size());
+        for (int b = 0; b < bands; ++b)
+            for (int w : h)
+                if (w / per == b) o.push_back(w);
+        if (int rc = banded.reserve(sizeof(int) * o.size())) return rc;
+        MPB_CUDA(cudaMemcpyAsync(banded.p, o.data(), sizeof(int) * o.size(), cudaMemcpyHostToDevice, st));
+        MPB_CUDA(cudaStreamSynchronize(st));
+        order = banded.as<int>();
+    }
     for (int rep = 0; rep < 4; ++rep) {
         MPB_CUDA(cudaMemsetAsync(rv.p, 0, 512 << 20 < rv.cap ? (size_t)(512 << 20) : rv.cap, st));  // evict the table from L2
         MPB_CUDA(cudaEventRecord(e0, st));
-        table_write_pattern_kernel<<<grid, 256, 0, st>>>(t->colptr.as<int64_t>(), t->has_order ? t->col_order.as<int>() : nullptr,
+        table_write_pattern_kernel<<<grid, 256, 0, st>>>(t->colptr.as<int64_t>(), order,
                                                          t->ncols, rv.as<long long>(), nz.as<double>());
         MPB_LAUNCHED();
         MPB_CUDA(cudaEventRecord(e1, st));
