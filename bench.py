@@ -503,6 +503,16 @@ def main():
     clocks = sampler.stop()
     nnz = job.nnz
     (total_ms_max,), (edges_all,) = allreduce_max_sum([total_ms], [float(nnz)], world)
+    per_rank = None
+    if world > 1:   # every rank's own view of the step (its event total and kernel phases): shows skew and who waits
+        mine = torch.tensor([total_ms / args.steps, phases["table"][0] / args.steps, float(np.mean(phases["points"])),
+                             float(np.mean(phases["edges"])),
+                             float(np.mean(phases["exchange"])) if phases["exchange"] else 0.0, float(nnz)],
+                            dtype=torch.float64, device="cuda")
+        allr = torch.empty(world * mine.numel(), dtype=torch.float64, device="cuda")
+        dist.all_gather_into_tensor(allr, mine)
+        per_rank = [dict(zip(("ms_per_step", "inball_total", "points", "edges", "exchange_incl_wait", "edges_built"), row))
+                    for row in allr.cpu().numpy().reshape(world, -1).round(4).tolist()]
     ms_per_step = total_ms_max / args.steps
     value = edges_all / (ms_per_step / 1e3)
     parity_cols = parity_check(job, rank, world)
@@ -610,6 +620,7 @@ def main():
                          "inball_total": phases["table"][0] / args.steps,
                          "exchange": float(np.mean(phases["exchange"])) if phases["exchange"] else None},
             "exchange": job.exchange_kind,
+            "per_rank": per_rank,
             "parity_checked": int(parity_all),
             "gpu_launches": launches,
             "renumbered_samples": renumbered,

@@ -54,6 +54,7 @@ __global__ void __launch_bounds__(256) pipe_peak_kernel(int iters, double seed, 
 // warp per column, same visiting order, same streaming stores, constant data, no candidate loads, no distance, no
 // sort -- so its duration is what the output format costs on this device before any neighbour work is done: the
 // floor rball_fill can be compared with, next to the plain-copy HBM peak.
+template <bool I32>
 __global__ void __launch_bounds__(256)
 table_write_pattern_kernel(const int64_t *__restrict__ colptr, const int *__restrict__ order, int64_t ncols,
                            long long *__restrict__ rowval, double *__restrict__ nzval) {
@@ -73,7 +74,8 @@ table_write_pattern_kernel(const int64_t *__restrict__ colptr, const int *__rest
             const long long base = __shfl_sync(0xffffffffu, my_base, c);
             const int k = __shfl_sync(0xffffffffu, my_k, c);
             for (int e = lane; e < k; e += 32) {
-                __stcs(rowval + base + e, (long long)(e + 1));
+                if (I32) __stcs(reinterpret_cast<int *>(rowval) + base + e, e + 1);  // experiment: 4-byte row indices
+                else __stcs(rowval + base + e, (long long)(e + 1));
                 __stcs(nzval + base + e, 1.0);
             }
         }
@@ -113,8 +115,10 @@ int table_write_floor_device(const mpb200_table *t, double *ms) {
     for (int rep = 0; rep < 4; ++rep) {
         MPB_CUDA(cudaMemsetAsync(rv.p, 0, 512 << 20 < rv.cap ? (size_t)(512 << 20) : rv.cap, st));  // evict the table from L2
         MPB_CUDA(cudaEventRecord(e0, st));
-        table_write_pattern_kernel<<<grid, 256, 0, st>>>(t->colptr.as<int64_t>(), order,
-                                                         t->ncols, rv.as<long long>(), nz.as<double>());
+        if (getenv("MPB200_FLOOR_I32"))
+            table_write_pattern_kernel<true><<<grid, 256, 0, st>>>(t->colptr.as<int64_t>(), order, t->ncols, rv.as<long long>(), nz.as<double>());
+        else
+            table_write_pattern_kernel<false><<<grid, 256, 0, st>>>(t->colptr.as<int64_t>(), order, t->ncols, rv.as<long long>(), nz.as<double>());
         MPB_LAUNCHED();
         MPB_CUDA(cudaEventRecord(e1, st));
         MPB_CUDA(cudaEventSynchronize(e1));

@@ -38,4 +38,34 @@ mpb200.MetricNN.sample_free(CC, SS, 5000, seed=1, order="morton").close()
 Bx = mpb200.PointRobotNDBoxes([mpb200.BoxBounds(np.array([0.5, -10.0]), np.array([10.0, 10.0]))])
 P = mpb200.MCProblem(np.eye(2)[None], (np.eye(2) * 0.1)[None], np.eye(2), np.array([[0.2, 0.0]] * 2), [0.3, 0.7], [[3.0, 0.0]])
 mpb200.collision_probability(P, Bx, 20000, seed=3)
+# round 2: general linear-affine LQ (numeric 2BVP), batched closest / closeR, pipe peaks, table write floor,
+# the narrowed table fetch, and the peer exchange in a world of one (pack kernel + flag barrier on the own buffer)
+import ctypes
+from mpb200 import _lib, sharding
+A = np.array([[0.0, 1.0, 0.0], [0.0, 0.0, 1.0], [0.0, 0.0, 0.0]]); Bm = np.array([[0.0], [0.0], [1.0]])
+LQ = mpb200.linearquadratic.LinearQuadraticQuasiMetricSpace(np.array([0, -1.0, -2.0]), np.array([1, 1.0, 2.0]), A, Bm,
+                                                            np.array([0.0, 0.1, 0.2]), np.array([[2.0]]),
+                                                            np.array([[1.0, 0, 0], [0, 1.0, 0]]))
+V = np.array([0, -1.0, -2.0]) + rng.random((400, 3)) * np.array([1, 2.0, 4.0])
+Q = mpb200.QuasiMetricNN(V, LQ.dist); Q.precompute(1.3); Q.lq_edges_free(CC, LQ)
+mpb200.linearquadratic.lq_motions_free(V[:50], V[50:100], CC, LQ, 1.3); Q.close()
+Wm = np.tile(np.array([[2.0, 0.3], [0.3, 1.0]]), (300, 1, 1))
+mpb200.montecarlo.close_points(rng.random((300, 2)), CC, Wm, 0.2, want_all=True)
+B4 = mpb200.PointRobotNDBoxes([mpb200.BoxBounds(np.full(4, 0.2), np.full(4, 0.5)), mpb200.BoxBounds(np.full(4, 0.6), np.full(4, 0.9))])
+mpb200.montecarlo.close_points(rng.random((100, 4)), B4, np.tile(np.eye(4) + 0.1, (100, 1, 1)), 1.0)
+lib = mpb200.load()
+v = ctypes.c_double(0.0)
+for kind in (0, 1, 2):
+    _lib.check(lib.mpb200_pipe_peak(kind, ctypes.byref(v)))
+V = rng.random((60000, 2)); NN = mpb200.MetricNN(V); NN.precompute(0.02)          # > 2^20 entries: narrowed fetch
+_lib.check(lib.mpb200_table_write_floor(NN.table.h, ctypes.byref(v)))
+NN.edges_free(NN.table, CC, SS, fetch=False, count=False)
+x = _lib.c_vp(); h = (ctypes.c_char * 64)()
+_lib.check(lib.mpb200_xchg_create(0, 1, 60000, (NN.table.nnz + 63) // 64 + 1, ctypes.byref(x), h))
+_lib.check(lib.mpb200_xchg_connect(x, h)); _lib.check(lib.mpb200_xchg_attach(x, NN.table.h))
+for _ in range(2):
+    NN.build_table(0.02); NN.edges_free(NN.table, CC, SS, fetch=False, count=False); _lib.check(lib.mpb200_xchg_push(x, NN.table.h))
+st = _lib.c_i64(0)
+_lib.check(lib.mpb200_xchg_view(x, None, None, None, None, ctypes.byref(st))); assert st.value == 0
+_lib.check(lib.mpb200_xchg_attach(None, NN.table.h)); _lib.check(lib.mpb200_xchg_destroy(x)); NN.close()
 print("sanitize run complete")
