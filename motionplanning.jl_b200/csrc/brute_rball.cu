@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "scan.cuh"
 #include "tc_rball.cuh"
+#include <algorithm>
 #include <cstdlib>
 
 namespace mpb {
@@ -116,6 +117,47 @@ slab_to_csc(const int *__restrict__ slab_j, const double *__restrict__ slab_s, i
         }
     }
 }
+// slab -> CSC for UNORDERED slabs (the symmetric tensor-core sweep): one block per column sorts the column's entries
+// by sample index in shared memory (bitonic on index << 32 | slot, the squared distances parked by slot) and writes
+// them out in order.  NP = capacity (power of two >= every column length).
+template <int NP>
+__global__ void __launch_bounds__(128)
+slab_sort_to_csc(const int *__restrict__ slab_j, const double *__restrict__ slab_s, int cap, int64_t nq,
+                 const int64_t *__restrict__ colptr, int64_t *__restrict__ rowval, double *__restrict__ nzval) {
+    __shared__ unsigned long long key[NP];
+    __shared__ double sv[NP];
+    for (int64_t w = blockIdx.x; w < nq; w += gridDim.x) {
+        const int64_t base = colptr[w] - 1;
+        const int k = (int)(colptr[w + 1] - colptr[w]);
+        int n = 32;
+        while (n < k) n <<= 1;  // block-uniform: the network runs on the smallest power of two that holds the column
+        for (int e = threadIdx.x; e < n; e += blockDim.x) {
+            if (e < k) {
+                key[e] = ((unsigned long long)(unsigned)slab_j[w * cap + e] << 32) | (unsigned)e;
+                sv[e] = slab_s[w * cap + e];
+            } else {
+                key[e] = ~0ULL;
+            }
+        }
+        __syncthreads();
+        for (int size = 2; size <= n; size <<= 1)
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                for (int t = threadIdx.x; t < n / 2; t += blockDim.x) {
+                    const int lo = ((t & ~(stride - 1)) << 1) | (t & (stride - 1)), hi = lo | stride;
+                    const bool up = (lo & size) == 0;
+                    const unsigned long long a = key[lo], b = key[hi];
+                    if ((a > b) == up) { key[lo] = b; key[hi] = a; }
+                }
+                __syncthreads();
+            }
+        for (int e = threadIdx.x; e < k; e += blockDim.x) {
+            const unsigned long long ky = key[e];
+            rowval[base + e] = (int64_t)(ky >> 32) + 1;
+            nzval[base + e] = sqrt(sv[(unsigned)ky]);
+        }
+        __syncthreads();
+    }
+}
 __global__ void max_count(const int *__restrict__ counts, int64_t n, int *__restrict__ out) {
     int m = 0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) m = max(m, counts[i]);
@@ -204,13 +246,17 @@ static int brute_build(mpb200_samples *s, double r, mpb200_table *t) {
         if (cap == 0 || need > 0.8 * avail) cap = 0;
     }
     bool single = cap > 0;
+    // full-range tensor-core builds multiply every unordered pair once and append it to both columns (tc_rball.cu,
+    // MODE 3); MPB200_TC_FULL=1 keeps the one-sided sweep.  The sorting conversion holds a column in shared memory.
+    static const bool tc_full = getenv("MPB200_TC_FULL") != nullptr;
+    const bool symmetric = single && use_tc && !tc_full && nq == N && s->q0 == 0 && cap <= 2048;
     if (single) {
         if (int rc = t->scratch.reserve(12 * (size_t)cap * (size_t)nq + 64)) return rc;
         double *slab_s = t->scratch.as<double>();
         int *slab_j = reinterpret_cast<int *>(slab_s + (size_t)cap * (size_t)nq);
         if (use_tc) {
             if constexpr (kTcDim) {
-                if (int rc = tc_sweep<D>(s, plan, r, nq, counts, cap, slab_j, slab_s)) return rc;
+                if (int rc = tc_sweep<D>(s, plan, r, nq, counts, cap, slab_j, slab_s, symmetric)) return rc;
             }
         } else {
             brute_rball_kernel<D, 2><<<nb, kBrThreads, 0, st>>>(V, Vf, N, s->q0, nq, r2, thr32, counts, nullptr, nullptr,
@@ -245,6 +291,15 @@ static int brute_build(mpb200_samples *s, double r, mpb200_table *t) {
         if (single) {
             const double *slab_s = t->scratch.as<double>();
             const int *slab_j = reinterpret_cast<const int *>(slab_s + (size_t)cap * (size_t)nq);
+            if (symmetric) {
+                const unsigned gs = (unsigned)std::min<int64_t>(nq, (int64_t)ctx().sm_count * 32);
+                if (cap <= 1024)
+                    slab_sort_to_csc<1024><<<gs, 128, 0, st>>>(slab_j, slab_s, cap, nq, t->colptr.as<int64_t>(),
+                                                               t->rowval.as<int64_t>(), t->nzval.as<double>());
+                else
+                    slab_sort_to_csc<2048><<<gs, 128, 0, st>>>(slab_j, slab_s, cap, nq, t->colptr.as<int64_t>(),
+                                                               t->rowval.as<int64_t>(), t->nzval.as<double>());
+            } else
             slab_to_csc<<<(unsigned)(ctx().sm_count * 8), 256, 0, st>>>(slab_j, slab_s, cap, nq, t->colptr.as<int64_t>(),
                                                                        t->rowval.as<int64_t>(), t->nzval.as<double>());
         } else {

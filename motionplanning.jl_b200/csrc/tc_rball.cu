@@ -135,7 +135,12 @@ __device__ __forceinline__ double tc_exact_sq(const double *__restrict__ a, cons
     return s;
 }
 
-// MODE 0: count only, MODE 2: count + append (index, exact squared distance) to the column's slab
+// MODE 0: count only, MODE 2: count + append (index, exact squared distance) to the column's slab.
+// MODE 3: the SYMMETRIC sweep (full-range builds): the relation and the stored distance are symmetric -- (a-b)^2 and
+// (b-a)^2 are the same bits -- so a CTA only multiplies its 128 queries against sample tiles at or after its own and
+// every accepted pair (q, j), j > q, is appended to BOTH columns, with an atomic slot counter per column.  Half the
+// MMAs, half the accumulator read-back (the kernel's bound, see the header); the slabs are then unordered and
+// slab_sort_to_csc sorts each column by index.  CTAs are launched longest-first (tile 0 sweeps everything).
 template <int D, int MODE>
 __global__ void __launch_bounds__(kTcM, 4)
 tc_rball_kernel(const double *__restrict__ V, const float *__restrict__ opB, const float *__restrict__ nrm_half,
@@ -193,7 +198,7 @@ tc_rball_kernel(const double *__restrict__ V, const float *__restrict__ opB, con
 
     int cnt = 0;
     uint32_t phase = 0;
-    for (int64_t t0 = 0; t0 < Npad; t0 += kTcN) {
+    for (int64_t t0 = (MODE == 3) ? (int64_t)blockIdx.x * kTcM : 0; t0 < Npad; t0 += kTcN) {
         // stage operand B: the tile is one contiguous 8 KB block already in the smem layout
         {
             const float4 *src = reinterpret_cast<const float4 *>(opB) + (t0 >> 7) * (4 * 128);
@@ -233,7 +238,16 @@ tc_rball_kernel(const double *__restrict__ V, const float *__restrict__ opB, con
                     const int i = __ffs(mask) - 1;
                     mask &= mask - 1;
                     const int64_t j = t0 + c0 + i;
-                    if (j < N && j != q) {
+                    if (MODE == 3) {
+                        if (j < N && j > q) {  // the pair's other half (j < q, diagonal tile only) belongs to row j
+                            const double s64 = tc_exact_sq<D>(V + q * D, V + j * D);
+                            if (s64 <= r2) {
+                                const int sq_ = atomicAdd(&counts[q], 1), sj_ = atomicAdd(&counts[j], 1);
+                                if (sq_ < cap) { slab_j[q * cap + sq_] = (int)j; slab_s[q * cap + sq_] = s64; }
+                                if (sj_ < cap) { slab_j[j * cap + sj_] = (int)q; slab_s[j * cap + sj_] = s64; }
+                            }
+                        }
+                    } else if (j < N && j != q) {
                         const double s64 = tc_exact_sq<D>(V + q * D, V + j * D);
                         if (s64 <= r2) {
                             if (MODE == 2 && cnt < cap) {
@@ -249,7 +263,7 @@ tc_rball_kernel(const double *__restrict__ V, const float *__restrict__ opB, con
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();  // accumulator and sB are free for the next tile
     }
-    if (active) counts[w] = cnt;
+    if (MODE != 3 && active) counts[w] = cnt;
     if (warp == 0)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(kTcN));
 }
@@ -310,10 +324,14 @@ int tc_prepare_operands(mpb200_samples *s, double r, TcPlan *plan) {
 
 template <int D>
 int tc_sweep(mpb200_samples *s, const TcPlan &P, double r, int64_t nq_run, int *counts, int cap, int *slab_j,
-             double *slab_s) {
+             double *slab_s, bool symmetric) {
     cudaStream_t st = ctx().stream;
     const unsigned nb = (unsigned)ceil_div(nq_run > 0 ? nq_run : 1, kTcM);
-    if (cap > 0)
+    if (symmetric) {  // full range, q0 == 0, slabs present: counts are the atomic slot counters
+        MPB_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * (size_t)nq_run, st));
+        tc_rball_kernel<D, 3><<<nb, kTcM, 0, st>>>(s->V.as<double>(), P.opB, P.nrm_half, s->N, P.Npad, 0, nq_run, r * r,
+                                                   P.delta, counts, cap, slab_j, slab_s);
+    } else if (cap > 0)
         tc_rball_kernel<D, 2><<<nb, kTcM, 0, st>>>(s->V.as<double>(), P.opB, P.nrm_half, s->N, P.Npad, s->q0, nq_run, r * r,
                                                    P.delta, counts, cap, slab_j, slab_s);
     else
@@ -325,7 +343,7 @@ int tc_sweep(mpb200_samples *s, const TcPlan &P, double r, int64_t nq_run, int *
 
 #define MPB_TC_INSTANTIATE(D_)                                                                                 \
     template int tc_prepare_operands<D_>(mpb200_samples *, double, TcPlan *);                                   \
-    template int tc_sweep<D_>(mpb200_samples *, const TcPlan &, double, int64_t, int *, int, int *, double *);
+    template int tc_sweep<D_>(mpb200_samples *, const TcPlan &, double, int64_t, int *, int, int *, double *, bool);
 MPB_TC_INSTANTIATE(4) MPB_TC_INSTANTIATE(5) MPB_TC_INSTANTIATE(6) MPB_TC_INSTANTIATE(7) MPB_TC_INSTANTIATE(8)
 MPB_TC_INSTANTIATE(9) MPB_TC_INSTANTIATE(10) MPB_TC_INSTANTIATE(11) MPB_TC_INSTANTIATE(12) MPB_TC_INSTANTIATE(13)
 MPB_TC_INSTANTIATE(14)

@@ -14,7 +14,9 @@ struct TcPlan {
 bool tc_band_is_tight(const mpb200_samples *s, double r);
 template <int D> int tc_prepare_operands(mpb200_samples *s, double r, TcPlan *plan);
 // sweep the first nq_run query columns of the shard; cap > 0: also append hits to the slabs
+// symmetric: full-range build with slabs -- each unordered pair is multiplied once and appended to both columns
+// (atomic slots, unordered slabs: finish with the sorting slab conversion)
 template <int D> int tc_sweep(mpb200_samples *s, const TcPlan &P, double r, int64_t nq_run, int *counts, int cap,
-                              int *slab_j, double *slab_s);
+                              int *slab_j, double *slab_s, bool symmetric = false);
 
 }  // namespace mpb
