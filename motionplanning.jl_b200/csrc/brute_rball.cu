@@ -119,13 +119,13 @@ slab_to_csc(const int *__restrict__ slab_j, const double *__restrict__ slab_s, i
 }
 // slab -> CSC for UNORDERED slabs (the symmetric tensor-core sweep): one block per column sorts the column's entries
 // by sample index in shared memory (bitonic on index << 32 | slot, the squared distances parked by slot) and writes
-// them out in order.  NP = capacity (power of two >= every column length).
-template <int NP>
+// them out in order.  np = capacity (power of two >= every column length), 16 bytes of dynamic shared memory each.
 __global__ void __launch_bounds__(128)
-slab_sort_to_csc(const int *__restrict__ slab_j, const double *__restrict__ slab_s, int cap, int64_t nq,
+slab_sort_to_csc(const int *__restrict__ slab_j, const double *__restrict__ slab_s, int cap, int np, int64_t nq,
                  const int64_t *__restrict__ colptr, int64_t *__restrict__ rowval, double *__restrict__ nzval) {
-    __shared__ unsigned long long key[NP];
-    __shared__ double sv[NP];
+    extern __shared__ unsigned long long s_sort[];  // np keys, then np squared distances
+    unsigned long long *key = s_sort;
+    double *sv = reinterpret_cast<double *>(s_sort + np);
     for (int64_t w = blockIdx.x; w < nq; w += gridDim.x) {
         const int64_t base = colptr[w] - 1;
         const int k = (int)(colptr[w + 1] - colptr[w]);
@@ -249,7 +249,7 @@ static int brute_build(mpb200_samples *s, double r, mpb200_table *t) {
     // full-range tensor-core builds multiply every unordered pair once and append it to both columns (tc_rball.cu,
     // MODE 3); MPB200_TC_FULL=1 keeps the one-sided sweep.  The sorting conversion holds a column in shared memory.
     static const bool tc_full = getenv("MPB200_TC_FULL") != nullptr;
-    const bool symmetric = single && use_tc && !tc_full && nq == N && s->q0 == 0 && cap <= 2048;
+    const bool symmetric = single && use_tc && !tc_full && nq == N && s->q0 == 0 && cap <= 8192;  // 8192 entries = 128 KB of shared memory
     if (single) {
         if (int rc = t->scratch.reserve(12 * (size_t)cap * (size_t)nq + 64)) return rc;
         double *slab_s = t->scratch.as<double>();
@@ -292,13 +292,13 @@ static int brute_build(mpb200_samples *s, double r, mpb200_table *t) {
             const double *slab_s = t->scratch.as<double>();
             const int *slab_j = reinterpret_cast<const int *>(slab_s + (size_t)cap * (size_t)nq);
             if (symmetric) {
+                int np = 32;
+                while (np < cap) np <<= 1;
+                const size_t smem = 16 * (size_t)np;
+                MPB_CUDA(cudaFuncSetAttribute(slab_sort_to_csc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 const unsigned gs = (unsigned)std::min<int64_t>(nq, (int64_t)ctx().sm_count * 32);
-                if (cap <= 1024)
-                    slab_sort_to_csc<1024><<<gs, 128, 0, st>>>(slab_j, slab_s, cap, nq, t->colptr.as<int64_t>(),
-                                                               t->rowval.as<int64_t>(), t->nzval.as<double>());
-                else
-                    slab_sort_to_csc<2048><<<gs, 128, 0, st>>>(slab_j, slab_s, cap, nq, t->colptr.as<int64_t>(),
-                                                               t->rowval.as<int64_t>(), t->nzval.as<double>());
+                slab_sort_to_csc<<<gs, 128, smem, st>>>(slab_j, slab_s, cap, np, nq, t->colptr.as<int64_t>(),
+                                                        t->rowval.as<int64_t>(), t->nzval.as<double>());
             } else
             slab_to_csc<<<(unsigned)(ctx().sm_count * 8), 256, 0, st>>>(slab_j, slab_s, cap, nq, t->colptr.as<int64_t>(),
                                                                        t->rowval.as<int64_t>(), t->nzval.as<double>());
