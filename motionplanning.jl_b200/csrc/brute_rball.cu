@@ -117,24 +117,28 @@ slab_to_csc(const int *__restrict__ slab_j, const double *__restrict__ slab_s, i
         }
     }
 }
-// slab -> CSC for UNORDERED slabs (the symmetric tensor-core sweep): one block per column sorts the column's entries
-// by sample index in shared memory (bitonic on index << 32 | slot, the squared distances parked by slot) and writes
-// them out in order.  np = capacity (power of two >= every column length), 16 bytes of dynamic shared memory each.
+// slab -> CSC after the symmetric tensor-core sweep.  A slab row holds the column's entries with a larger index than
+// the column at the front (appended by the column's own thread: already ascending) and those with a smaller index at
+// the back (appended by their own rows' threads through an atomic slot: unordered).  One block per column sorts the
+// back part by sample index in shared memory (bitonic on index << 32 | slot, squared distances parked by slot) and
+// writes  sorted(back) ++ front.  np = power of two >= every column's back part, 16 bytes of shared memory each.
 __global__ void __launch_bounds__(128)
-slab_sort_to_csc(const int *__restrict__ slab_j, const double *__restrict__ slab_s, int cap, int np, int64_t nq,
-                 const int64_t *__restrict__ colptr, int64_t *__restrict__ rowval, double *__restrict__ nzval) {
+slab_merge_to_csc(const int *__restrict__ slab_j, const double *__restrict__ slab_s, int cap, int np, int64_t nq,
+                  const int *__restrict__ own, const int *__restrict__ remote, const int64_t *__restrict__ colptr,
+                  int64_t *__restrict__ rowval, double *__restrict__ nzval) {
     extern __shared__ unsigned long long s_sort[];  // np keys, then np squared distances
     unsigned long long *key = s_sort;
     double *sv = reinterpret_cast<double *>(s_sort + np);
     for (int64_t w = blockIdx.x; w < nq; w += gridDim.x) {
         const int64_t base = colptr[w] - 1;
-        const int k = (int)(colptr[w + 1] - colptr[w]);
+        const int kr = remote[w], ko = own[w];
         int n = 32;
-        while (n < k) n <<= 1;  // block-uniform: the network runs on the smallest power of two that holds the column
+        while (n < kr) n <<= 1;  // block-uniform: the smallest power of two that holds the unordered part
         for (int e = threadIdx.x; e < n; e += blockDim.x) {
-            if (e < k) {
-                key[e] = ((unsigned long long)(unsigned)slab_j[w * cap + e] << 32) | (unsigned)e;
-                sv[e] = slab_s[w * cap + e];
+            if (e < kr) {
+                const size_t at = (size_t)w * cap + (cap - 1 - e);
+                key[e] = ((unsigned long long)(unsigned)slab_j[at] << 32) | (unsigned)e;
+                sv[e] = slab_s[at];
             } else {
                 key[e] = ~0ULL;
             }
@@ -150,13 +154,20 @@ slab_sort_to_csc(const int *__restrict__ slab_j, const double *__restrict__ slab
                 }
                 __syncthreads();
             }
-        for (int e = threadIdx.x; e < k; e += blockDim.x) {
+        for (int e = threadIdx.x; e < kr; e += blockDim.x) {
             const unsigned long long ky = key[e];
             rowval[base + e] = (int64_t)(ky >> 32) + 1;
             nzval[base + e] = sqrt(sv[(unsigned)ky]);
         }
+        for (int e = threadIdx.x; e < ko; e += blockDim.x) {
+            rowval[base + kr + e] = (int64_t)slab_j[(size_t)w * cap + e] + 1;
+            nzval[base + kr + e] = sqrt(slab_s[(size_t)w * cap + e]);
+        }
         __syncthreads();
     }
+}
+__global__ void add_counts(const int *__restrict__ a, const int *__restrict__ b, int64_t n, int *__restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = a[i] + b[i];
 }
 __global__ void max_count(const int *__restrict__ counts, int64_t n, int *__restrict__ out) {
     int m = 0;
@@ -208,7 +219,7 @@ static int brute_build(mpb200_samples *s, double r, mpb200_table *t) {
         to_float_padded<D><<<(unsigned)ceil_div(N, 256), 256, 0, st>>>(V, N, Vf);
         MPB_LAUNCHED();
     }
-    if (int rc = t->counts.reserve(sizeof(int) * (size_t)(nq + 2))) return rc;
+    if (int rc = t->counts.reserve(sizeof(int) * (size_t)(3 * nq + 4))) return rc;  // totals | own | partner appends
     if (int rc = t->colptr.reserve(sizeof(int64_t) * (size_t)(nq + 1))) return rc;
     const unsigned nb = (unsigned)ceil_div(nq > 0 ? nq : 1, kBrThreads);
     const double r2 = r * r;
@@ -256,7 +267,14 @@ static int brute_build(mpb200_samples *s, double r, mpb200_table *t) {
         int *slab_j = reinterpret_cast<int *>(slab_s + (size_t)cap * (size_t)nq);
         if (use_tc) {
             if constexpr (kTcDim) {
-                if (int rc = tc_sweep<D>(s, plan, r, nq, counts, cap, slab_j, slab_s, symmetric)) return rc;
+                if (symmetric) {
+                    int *own = counts + nq + 2, *remote = own + nq;
+                    if (int rc = tc_sweep<D>(s, plan, r, nq, own, cap, slab_j, slab_s, remote)) return rc;
+                    add_counts<<<(unsigned)(ctx().sm_count * 4), 256, 0, st>>>(own, remote, nq, counts);
+                    MPB_LAUNCHED();
+                } else {
+                    if (int rc = tc_sweep<D>(s, plan, r, nq, counts, cap, slab_j, slab_s)) return rc;
+                }
             }
         } else {
             brute_rball_kernel<D, 2><<<nb, kBrThreads, 0, st>>>(V, Vf, N, s->q0, nq, r2, thr32, counts, nullptr, nullptr,
@@ -295,10 +313,10 @@ static int brute_build(mpb200_samples *s, double r, mpb200_table *t) {
                 int np = 32;
                 while (np < cap) np <<= 1;
                 const size_t smem = 16 * (size_t)np;
-                MPB_CUDA(cudaFuncSetAttribute(slab_sort_to_csc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                MPB_CUDA(cudaFuncSetAttribute(slab_merge_to_csc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 const unsigned gs = (unsigned)std::min<int64_t>(nq, (int64_t)ctx().sm_count * 32);
-                slab_sort_to_csc<<<gs, 128, smem, st>>>(slab_j, slab_s, cap, np, nq, t->colptr.as<int64_t>(),
-                                                        t->rowval.as<int64_t>(), t->nzval.as<double>());
+                slab_merge_to_csc<<<gs, 128, smem, st>>>(slab_j, slab_s, cap, np, nq, counts + nq + 2, counts + 2 * nq + 2,
+                                                         t->colptr.as<int64_t>(), t->rowval.as<int64_t>(), t->nzval.as<double>());
             } else
             slab_to_csc<<<(unsigned)(ctx().sm_count * 8), 256, 0, st>>>(slab_j, slab_s, cap, nq, t->colptr.as<int64_t>(),
                                                                        t->rowval.as<int64_t>(), t->nzval.as<double>());

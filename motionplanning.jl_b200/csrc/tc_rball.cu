@@ -145,7 +145,7 @@ template <int D, int MODE>
 __global__ void __launch_bounds__(kTcM, 4)
 tc_rball_kernel(const double *__restrict__ V, const float *__restrict__ opB, const float *__restrict__ nrm_half,
                 int64_t N, int64_t Npad, int64_t q0, int64_t nq, double r2, float delta, int *__restrict__ counts,
-                int cap, int *__restrict__ slab_j, double *__restrict__ slab_s) {
+                int cap, int *__restrict__ slab_j, double *__restrict__ slab_s, int *__restrict__ rcounts) {
     __shared__ __align__(128) float4 sA[4 * kTcM];   // 8 KB
     __shared__ __align__(128) float4 sB[4 * kTcN];   // 8 KB
     __shared__ __align__(8) uint64_t s_bar;
@@ -197,6 +197,9 @@ tc_rball_kernel(const double *__restrict__ V, const float *__restrict__ opB, con
     const uint32_t my_tmem = tmem + ((uint32_t)(warp * 32) << 16);
 
     int cnt = 0;
+    int64_t pend_j = -1;  // MODE 3: a partner append whose slot (an atomic's return value) has not been used yet
+    int pend_slot = 0;
+    double pend_s = 0.0;
     uint32_t phase = 0;
     for (int64_t t0 = (MODE == 3) ? (int64_t)blockIdx.x * kTcM : 0; t0 < Npad; t0 += kTcN) {
         // stage operand B: the tile is one contiguous 8 KB block already in the smem layout
@@ -242,9 +245,19 @@ tc_rball_kernel(const double *__restrict__ V, const float *__restrict__ opB, con
                         if (j < N && j > q) {  // the pair's other half (j < q, diagonal tile only) belongs to row j
                             const double s64 = tc_exact_sq<D>(V + q * D, V + j * D);
                             if (s64 <= r2) {
-                                const int sq_ = atomicAdd(&counts[q], 1), sj_ = atomicAdd(&counts[j], 1);
-                                if (sq_ < cap) { slab_j[q * cap + sq_] = (int)j; slab_s[q * cap + sq_] = s64; }
-                                if (sj_ < cap) { slab_j[j * cap + sj_] = (int)q; slab_s[j * cap + sj_] = s64; }
+                                // own column: entries fill the slab row from the front with a private counter (no atomic)
+                                if (cnt < cap) { slab_j[q * cap + cnt] = (int)j; slab_s[q * cap + cnt] = s64; }
+                                ++cnt;
+                                // partner's column: entries fill its slab row from the BACK, slot from an atomic counter.
+                                // The store that needs the returned slot is deferred to the next hit, so the atomic's
+                                // round trip overlaps the sweep instead of stalling the warp at every accepted pair.
+                                if (pend_j >= 0 && pend_slot < cap) {
+                                    slab_j[pend_j * cap + (cap - 1 - pend_slot)] = (int)q;
+                                    slab_s[pend_j * cap + (cap - 1 - pend_slot)] = pend_s;
+                                }
+                                pend_slot = atomicAdd(&rcounts[j], 1);
+                                pend_j = j;
+                                pend_s = s64;
                             }
                         }
                     } else if (j < N && j != q) {
@@ -263,7 +276,15 @@ tc_rball_kernel(const double *__restrict__ V, const float *__restrict__ opB, con
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();  // accumulator and sB are free for the next tile
     }
-    if (MODE != 3 && active) counts[w] = cnt;
+    if (MODE == 3) {
+        if (pend_j >= 0 && pend_slot < cap) {
+            slab_j[pend_j * cap + (cap - 1 - pend_slot)] = (int)q;
+            slab_s[pend_j * cap + (cap - 1 - pend_slot)] = pend_s;
+        }
+        if (active) counts[w] = cnt;  // own entries; the entries appended by partners are counted in rcounts
+    } else if (active) {
+        counts[w] = cnt;
+    }
     if (warp == 0)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(kTcN));
 }
@@ -324,26 +345,26 @@ int tc_prepare_operands(mpb200_samples *s, double r, TcPlan *plan) {
 
 template <int D>
 int tc_sweep(mpb200_samples *s, const TcPlan &P, double r, int64_t nq_run, int *counts, int cap, int *slab_j,
-             double *slab_s, bool symmetric) {
+             double *slab_s, int *rcounts) {
     cudaStream_t st = ctx().stream;
     const unsigned nb = (unsigned)ceil_div(nq_run > 0 ? nq_run : 1, kTcM);
-    if (symmetric) {  // full range, q0 == 0, slabs present: counts are the atomic slot counters
-        MPB_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * (size_t)nq_run, st));
+    if (rcounts) {  // symmetric: full range, q0 == 0, slabs present; rcounts = atomic counters of the partner appends
+        MPB_CUDA(cudaMemsetAsync(rcounts, 0, sizeof(int) * (size_t)nq_run, st));
         tc_rball_kernel<D, 3><<<nb, kTcM, 0, st>>>(s->V.as<double>(), P.opB, P.nrm_half, s->N, P.Npad, 0, nq_run, r * r,
-                                                   P.delta, counts, cap, slab_j, slab_s);
+                                                   P.delta, counts, cap, slab_j, slab_s, rcounts);
     } else if (cap > 0)
         tc_rball_kernel<D, 2><<<nb, kTcM, 0, st>>>(s->V.as<double>(), P.opB, P.nrm_half, s->N, P.Npad, s->q0, nq_run, r * r,
-                                                   P.delta, counts, cap, slab_j, slab_s);
+                                                   P.delta, counts, cap, slab_j, slab_s, nullptr);
     else
         tc_rball_kernel<D, 0><<<nb, kTcM, 0, st>>>(s->V.as<double>(), P.opB, P.nrm_half, s->N, P.Npad, s->q0, nq_run, r * r,
-                                                   P.delta, counts, 0, nullptr, nullptr);
+                                                   P.delta, counts, 0, nullptr, nullptr, nullptr);
     MPB_LAUNCHED();
     return 0;
 }
 
 #define MPB_TC_INSTANTIATE(D_)                                                                                 \
     template int tc_prepare_operands<D_>(mpb200_samples *, double, TcPlan *);                                   \
-    template int tc_sweep<D_>(mpb200_samples *, const TcPlan &, double, int64_t, int *, int, int *, double *, bool);
+    template int tc_sweep<D_>(mpb200_samples *, const TcPlan &, double, int64_t, int *, int, int *, double *, int *);
 MPB_TC_INSTANTIATE(4) MPB_TC_INSTANTIATE(5) MPB_TC_INSTANTIATE(6) MPB_TC_INSTANTIATE(7) MPB_TC_INSTANTIATE(8)
 MPB_TC_INSTANTIATE(9) MPB_TC_INSTANTIATE(10) MPB_TC_INSTANTIATE(11) MPB_TC_INSTANTIATE(12) MPB_TC_INSTANTIATE(13)
 MPB_TC_INSTANTIATE(14)

@@ -14,9 +14,10 @@ struct TcPlan {
 bool tc_band_is_tight(const mpb200_samples *s, double r);
 template <int D> int tc_prepare_operands(mpb200_samples *s, double r, TcPlan *plan);
 // sweep the first nq_run query columns of the shard; cap > 0: also append hits to the slabs
-// symmetric: full-range build with slabs -- each unordered pair is multiplied once and appended to both columns
-// (atomic slots, unordered slabs: finish with the sorting slab conversion)
+// rcounts != NULL: the symmetric sweep of a full-range build with slabs -- each unordered pair (q, j), j > q, is
+// multiplied once; row q's thread appends it to the FRONT of its own slab row (counts[q] entries) and to the BACK of
+// row j's (rcounts[j] entries, atomic slots).  Finish with the merging / sorting slab conversion.
 template <int D> int tc_sweep(mpb200_samples *s, const TcPlan &P, double r, int64_t nq_run, int *counts, int cap,
-                              int *slab_j, double *slab_s, bool symmetric = false);
+                              int *slab_j, double *slab_s, int *rcounts = nullptr);
 
 }  // namespace mpb
