@@ -256,6 +256,21 @@ int mpb200_mc_collision_probability(const mpb200_mc_problem *p, const mpb200_obs
                                     int64_t first, int64_t n, mpb200_mc_result *out, uint8_t *hit_out,
                                     double *w_out);
 
+/* ---- k-nearest connections ---------------------------------------------------------------------
+ * The reference exports knn / knnF / knnB / mutualknn* (nearneighbors.jl:9-11) and FMT*'s connections = :K branch
+ * calls mutualknnF! / knnB! (fmt.jl:6,17-19,70,72), but defines none of them (`:K` throws there).  Specification
+ * implemented here (parity unpinned; restated in oracle/oracle.py):
+ *   knn(v, k): the k samples j != v with the smallest stored value, ties towards the smaller index, returned like
+ *   every neighbourhood (ascending indices + values);  mutualknnF(v, k) = knnF(v, k) U { w : v in knnB(w, k) }.
+ * Both are table operations on top of ANY neighbour table (Euclidean or steering cost):
+ *   mpb200_table_knn keeps the k best entries of every column of t; columns of t with fewer than k entries are kept
+ *   whole and counted in *short_cols -- rebuild t with a larger radius until it is 0 and the result is the k-NN table;
+ *   mpb200_table_union_transpose forms out[:, v] = a[:, v] U { w : v in b[:, w] } (values from a, else from b;
+ *   full-range tables over the same sample set).  Columns are limited to 8192 entries.
+ * Non-NULL *out handles are reused.  Edge validity works on the results like on any table. */
+int mpb200_table_knn(const mpb200_table *t, int k, mpb200_table **out, int64_t *nnz, int64_t *short_cols);
+int mpb200_table_union_transpose(const mpb200_table *a, const mpb200_table *b, mpb200_table **out, int64_t *nnz);
+
 /* ---- closest obstacle points under a weight matrix (Monte-Carlo proposal geometry) ----------
  * Replaces closest(p, shape, W) / closeR(p, CC, W, r2) (SAT2D.jl:208-285; boxesND.jl:61-86; robots2D.jl:25-26)
  * for n query points at once, each with its own SPD weight matrix W_i (dw x dw row-major; dw = 2 for 2-D

@@ -15,7 +15,7 @@ from .statespaces import (BoundedEuclideanStateSpace, BoundedStateSpace, Euclide
 from .nearneighbors import (ImmutableNNC, MetricNN, QuasiMetricNN, SampleSet, SparseMatrixCSC, SparseVectorView,  # noqa: F401
                             loadNN, saveNN,
                             addpoints, filter_neighborhood, inball, inballB, inballF, nonzeroinds,
-                            nonzeros, viewcol)
+                            nonzeros, viewcol, knn, knnB, knnF, mutualknn, mutualknnF)
 from .linearquadratic import (DoubleIntegrator, LinearQuadratic, LinearQuadraticQuasiMetricSpace,  # noqa: F401
                               lq_motions_free, setup_steering, steer, steer_batch)
 from .problems import (BallGoal, MPProblem, MPSolution, PointGoal, RectangleGoal, StateGoal, is_goal_pt,  # noqa: F401

@@ -193,6 +193,8 @@ int lq_motions_free_device(const mpb200_lq *lq, double r, const double *dA, cons
                            unsigned long long *d_checks);
 
 int pipe_peak_device(int kind, double *ops_per_s);
+int table_knn_device(const mpb200_table *t, int k, mpb200_table *out, int64_t *short_cols, DevBuf &scan_tmp);
+int table_union_transpose_device(const mpb200_table *a, const mpb200_table *b, mpb200_table *out, DevBuf &scan_tmp);
 int table_write_floor_device(const mpb200_table *t, double *ms);
 int close_points_device(const mpb200_obstacles *o, const double *dP, const double *dW, int64_t n, int dw, double r2,
                         int *d_count, double *d_d2, int *d_shape, double *d_x, double *d_all_d2, double *d_all_x);
@@ -992,6 +994,52 @@ int mpb200_close_points(const mpb200_obstacles *o, const double *p_aos, const do
     if (all_d2) MPB_CUDA(cudaMemcpyAsync(all_d2, bAD.p, sizeof(double) * nS, cudaMemcpyDeviceToHost, st));
     if (all_x) MPB_CUDA(cudaMemcpyAsync(all_x, bAX.p, sizeof(double) * nS * dw, cudaMemcpyDeviceToHost, st));
     MPB_CUDA(cudaStreamSynchronize(st));
+    return MPB200_OK;
+}
+
+// ---- k-nearest connections (table operations) ----------------------------------------------------------------
+static int out_table(mpb200_table **out, mpb200_table **t, bool *fresh) {
+    *t = *out;
+    *fresh = false;
+    if (!*t) {
+        *t = new (std::nothrow) mpb200_table();
+        if (!*t) return fail(MPB200_ENOMEM, "out of host memory");
+        *fresh = true;
+    }
+    return 0;
+}
+int mpb200_table_knn(const mpb200_table *t, int k, mpb200_table **out, int64_t *nnz, int64_t *short_cols) {
+    MPB_REQUIRE_INIT();
+    MPB_CHECK_ARG(t != nullptr && out != nullptr, "NULL handle");
+    MPB_CHECK_ARG(k >= 1, "k must be at least 1");
+    MPB_CHECK_ARG(*out != t, "the output table must be a different handle");
+    mpb200_table *o;
+    bool fresh;
+    if (int rc = out_table(out, &o, &fresh)) return rc;
+    static DevBuf scan_tmp;
+    int64_t n_short = 0;
+    int rc = table_knn_device(t, k, o, &n_short, scan_tmp);
+    if (rc) { if (fresh) mpb200_table_destroy(o); return rc; }
+    *out = o;
+    if (nnz) *nnz = o->nnz;
+    if (short_cols) *short_cols = n_short;
+    return MPB200_OK;
+}
+int mpb200_table_union_transpose(const mpb200_table *a, const mpb200_table *b, mpb200_table **out, int64_t *nnz) {
+    MPB_REQUIRE_INIT();
+    MPB_CHECK_ARG(a != nullptr && b != nullptr && out != nullptr, "NULL handle");
+    MPB_CHECK_ARG(*out != a && *out != b, "the output table must be a different handle");
+    MPB_CHECK_ARG(a->src_N == b->src_N && a->src_N >= 0, "the two tables were built from different sample sets");
+    MPB_CHECK_ARG(a->col0 == 0 && b->col0 == 0 && a->ncols == a->src_N && b->ncols == b->src_N,
+                  "mutual neighbourhoods need full-range tables (every column of the sample set)");
+    mpb200_table *o;
+    bool fresh;
+    if (int rc = out_table(out, &o, &fresh)) return rc;
+    static DevBuf scan_tmp;
+    int rc = table_union_transpose_device(a, b, o, scan_tmp);
+    if (rc) { if (fresh) mpb200_table_destroy(o); return rc; }
+    *out = o;
+    if (nnz) *nnz = o->nnz;
     return MPB200_OK;
 }
 

@@ -230,6 +230,29 @@ class SampleSet:
         return SparseMatrixCSC(len(self), table.ncols, colptr, rowval, nzval)
 
 
+def _knn_radius_guess(V, k):
+    """radius of the ball expected to hold ~1.6 k samples of a uniform cloud filling the samples' bounding box"""
+    import math
+    N, d = V.shape
+    ext = np.maximum(V.max(axis=0) - V.min(axis=0), 1e-300)
+    zeta = math.pi ** (d / 2) / math.gamma(d / 2 + 1)
+    return float((1.6 * k / max(N, 1) * float(np.prod(ext)) / zeta) ** (1.0 / d))
+
+
+def _table_knn(src, k, dst):
+    """mpb200_table_knn: dst = the k best entries of every column of src; returns the number of short columns"""
+    nnz, short = _lib.c_i64(0), _lib.c_i64(0)
+    _lib.check(_lib.lib().mpb200_table_knn(src.h, int(k), ctypes.byref(dst.h), ctypes.byref(nnz), ctypes.byref(short)))
+    dst.nnz, dst.ncols = nnz.value, src.ncols
+    return short.value
+
+
+def _table_union_transpose(a, b, dst):
+    nnz = _lib.c_i64(0)
+    _lib.check(_lib.lib().mpb200_table_union_transpose(a.h, b.h, ctypes.byref(dst.h), ctypes.byref(nnz)))
+    dst.nnz, dst.ncols = nnz.value, a.ncols
+
+
 class MetricNN(SampleSet):
     """nearneighbors.jl:62-74 for symmetric distances (Euclidean).
 
@@ -278,6 +301,34 @@ class MetricNN(SampleSet):
         self.cache = ImmutableNNC(D, float(r))
         return self.cache
 
+    def precompute_knn(self, k, r0=None, grow=1.3, max_rounds=40):
+        """k-nearest connections (nearneighbors.jl:9-11 exports the names, fmt.jl:17-19 uses them, nothing defines
+        them: specification in csrc/knn.cu).  Builds r-ball tables with a growing radius until every column holds at
+        least k entries, keeps the k nearest of each (mpb200_table_knn) and forms the mutual neighbourhoods
+        (mpb200_table_union_transpose).  Afterwards knn / knnF / knnB / mutualknn* are column views.
+        Returns (knn cache, mutual cache); self.r is the radius of the last build (every stored neighbour is within it)."""
+        N = len(self)
+        k = min(int(k), N - 1)
+        if k < 1:
+            raise ValueError("k-nearest connections need at least two samples")
+        if (self.q0, self.q1) != (0, N):
+            raise ValueError("k-nearest tables need the full column range (mutual neighbourhoods are a transpose)")
+        r = float(r0) if r0 else _knn_radius_guess(self.V, k)
+        if not hasattr(self, "table_knn"):
+            self.table_knn, self.table_mknn = DeviceTable("knn"), DeviceTable("mknn")
+        for _ in range(max_rounds):
+            self.build_table(r)
+            if _table_knn(self.table, k, self.table_knn) == 0:
+                break
+            r *= grow
+        else:
+            raise RuntimeError("k-nearest search did not reach k = %d neighbours per sample" % k)
+        _table_union_transpose(self.table_knn, self.table_knn, self.table_mknn)
+        self.k = k
+        self.cache_knn = ImmutableNNC(self.fetch_table(self.table_knn, "knn"), float(r))
+        self.cache_mknn = ImmutableNNC(self.fetch_table(self.table_mknn, "mknn"), float(r))
+        return self.cache_knn, self.cache_mknn
+
     def precompute_checked(self, r, CC, SS):
         """precompute + edge validity through the fused pass -> (ImmutableNNC, edge chunks, checks)"""
         _, checks = self.build_table_checked(r, CC, SS)
@@ -287,6 +338,9 @@ class MetricNN(SampleSet):
 
     def close(self):
         self.table.close()
+        for name in ("table_knn", "table_mknn"):
+            if hasattr(self, name):
+                getattr(self, name).close()
         super().close()
 
 
@@ -317,12 +371,37 @@ class QuasiMetricNN(SampleSet):
         self.cacheB = ImmutableNNC(self.fetch_table(self.tableB, "nnB"), float(r))
         return self.cacheF, self.cacheB
 
-    def lq_edges_free(self, CC, SS, fetch=True):
-        """validity per stored entry (row y -> column x) of the BACKWARD table: the motion
-        V[y] -> V[x] that fmt.jl:75 asks about; returns (chunks, checks)"""
+    def precompute_knn(self, k, r0, grow=1.3, max_rounds=30):
+        """k-nearest connections under the steering cost: forward / backward cost-ball tables with a growing cost
+        radius (from r0) until every column holds k entries, then the k cheapest of each and the mutual forward
+        neighbourhoods  knnF(v) U { w : v in knnB(w) }.  Returns (knnF, knnB, mutualF) caches."""
+        N = len(self)
+        k = min(int(k), N - 1)
+        r = float(r0)
+        if not hasattr(self, "table_knnF"):
+            self.table_knnF, self.table_knnB, self.table_mknnF = DeviceTable("knnF"), DeviceTable("knnB"), DeviceTable("mknnF")
+        for _ in range(max_rounds):
+            self.build_tables(r)
+            shortF = _table_knn(self.tableF, k, self.table_knnF)
+            shortB = _table_knn(self.tableB, k, self.table_knnB)
+            if shortF == 0 and shortB == 0:
+                break
+            r *= grow
+        else:
+            raise RuntimeError("k-nearest search did not reach k = %d neighbours per sample" % k)
+        _table_union_transpose(self.table_knnF, self.table_knnB, self.table_mknnF)
+        self.k = k
+        self.cache_knnF = ImmutableNNC(self.fetch_table(self.table_knnF, "knnF"), float(r))
+        self.cache_knnB = ImmutableNNC(self.fetch_table(self.table_knnB, "knnB"), float(r))
+        self.cache_mknnF = ImmutableNNC(self.fetch_table(self.table_mknnF, "mknnF"), float(r))
+        return self.cache_knnF, self.cache_knnB, self.cache_mknnF
+
+    def lq_edges_free(self, CC, SS, fetch=True, table=None):
+        """validity per stored entry (row y -> column x) of the BACKWARD table (or `table`, e.g. the backward k-nearest
+        table): the motion V[y] -> V[x] that fmt.jl:75 asks about; returns (chunks, checks)"""
         d = SS.desc()
-        t = self.tableB
-        bits = self.pool.array(("lq_edge_bits",), (t.nnz + 63) // 64, np.uint64) if fetch else None
+        t = table if table is not None else self.tableB
+        bits = self.pool.array(("lq_edge_bits", t.name), (t.nnz + 63) // 64, np.uint64) if fetch else None
         checks = _lib.c_i64(0)
         _lib.check(_lib.lib().mpb200_lq_edges_free(self.handle(), t.h, self.dist.handle(), self.r, CC.handle(),
                                                    ctypes.byref(d), _lib.ptr(bits), ctypes.byref(checks)))
@@ -332,6 +411,9 @@ class QuasiMetricNN(SampleSet):
     def close(self):
         self.tableF.close()
         self.tableB.close()
+        for name in ("table_knnF", "table_knnB", "table_mknnF"):
+            if hasattr(self, name):
+                getattr(self, name).close()
         super().close()
 
 
@@ -367,3 +449,39 @@ def inballB(NN, v, r, f=None):
         NN.precompute(r)
     col = viewcol(NN.cacheB.D, v - NN.q0)
     return filter_neighborhood(col, f) if f is not None else col
+
+
+# ---- k-nearest neighbourhoods (names exported at nearneighbors.jl:9-11; used at fmt.jl:17-19) -----------------
+def _need(NN, attr):
+    c = getattr(NN, attr, None)
+    if c is None:
+        raise RuntimeError("call precompute_knn(k) first (k-nearest tables are built for one k)")
+    return c
+
+
+def _served(NN, cache, v, k, f):
+    if k != NN.k:
+        raise ValueError("the k-nearest tables were built for k = %d" % NN.k)
+    col = viewcol(cache.D, v)
+    return filter_neighborhood(col, f) if f is not None else col
+
+
+def knn(NN, v, k, f=None):
+    """knn!(NN, v, k[, f]) for a symmetric metric"""
+    return _served(NN, _need(NN, "cache_knn"), v, k, f)
+
+
+def mutualknn(NN, v, k, f=None):
+    return _served(NN, _need(NN, "cache_mknn"), v, k, f)
+
+
+def knnF(NN, v, k, f=None):
+    return knn(NN, v, k, f) if isinstance(NN, MetricNN) else _served(NN, _need(NN, "cache_knnF"), v, k, f)
+
+
+def knnB(NN, v, k, f=None):
+    return knn(NN, v, k, f) if isinstance(NN, MetricNN) else _served(NN, _need(NN, "cache_knnB"), v, k, f)
+
+
+def mutualknnF(NN, v, k, f=None):
+    return mutualknn(NN, v, k, f) if isinstance(NN, MetricNN) else _served(NN, _need(NN, "cache_mknnF"), v, k, f)

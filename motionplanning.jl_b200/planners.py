@@ -33,7 +33,7 @@ def _bits_to_bool(chunks, n):
 
 
 def fmtstar(P, N=None, rm=1.0, connections="R", r=0.0, ensure_goal_ct=1, init_idx=1, checkpts=True, seed=0,
-            edge_checks="table"):
+            edge_checks="table", k=None):
     """fmtstar!(P, N; rm, connections, r, ensure_goal_ct, init_idx, checkpts) -> (status, cost, elapsed)
 
     edge_checks = "table": the validity of EVERY stored edge is precomputed in one pass (K7/K8/K9) and fmt.jl:75
@@ -45,12 +45,12 @@ def fmtstar(P, N=None, rm=1.0, connections="R", r=0.0, ensure_goal_ct=1, init_id
     t_start = time.perf_counter()
     N = len(P.V) if N is None else N
     P.CC.count = 0
-    if connections == "K":
-        # knn*/mutualknn* are exported but never defined in the reference (nearneighbors.jl:9-11,
-        # fmt.jl:17-19): connections = :K throws there as well
-        raise NotImplementedError("k-nearest connections are undefined in the reference (mutualknnF!, knnB!)")
-    if connections != "R":
+    if connections not in ("R", "K"):
         raise ValueError("Connection type must be radial (:R) or k-nearest (:K)")
+    # connections = :K: nearF = mutualknnF!, nearB = knnB! (fmt.jl:17-19).  The reference exports those names
+    # (nearneighbors.jl:9-11) but never defines them, so :K throws there; here they follow the specification of
+    # csrc/knn.cu (k nearest by stored value, ties to the smaller index; mutual = knnF U transpose(knnB)).
+    knn_mode = connections == "K"
     SS, CC = P.SS, P.CC
     if r > 0:
         setup_steering(SS, r)
@@ -64,6 +64,8 @@ def fmtstar(P, N=None, rm=1.0, connections="R", r=0.0, ensure_goal_ct=1, init_id
     if r == 0:
         r = fmt_radius(N, SS.dim, rm, free_volume_ub)
         setup_steering(SS, r)
+    if k is None:                                          # fmt.jl:6
+        k = min(int(math.ceil((2 * rm) ** SS.dim * (math.e / SS.dim) * math.log(N))), N - 1)
 
     # ---- the batched precompute that replaces the lazy per-call hot path -----------------------
     if edge_checks not in ("table", "lazy"):
@@ -71,7 +73,20 @@ def fmtstar(P, N=None, rm=1.0, connections="R", r=0.0, ensure_goal_ct=1, init_id
     lazy = edge_checks == "lazy"
     lq = isinstance(SS.dist, LinearQuadratic)
     ebits = None
-    if lq:
+    if knn_mode and lq:
+        cF, cB, cM = NN.precompute_knn(k, r)               # cost radius grows from r until every column holds k
+        r = cB.r
+        setup_steering(SS, r)                              # the steering horizon of the waypoint checks = the last radius
+        NN.r = r
+        DF, DB = cM.D, cB.D
+        if not lazy:
+            ebits, _ = NN.lq_edges_free(CC, SS, table=NN.table_knnB)
+    elif knn_mode:
+        cK, cM = NN.precompute_knn(k)
+        DF, DB = cM.D, cK.D
+        if not lazy:
+            ebits, _ = NN.edges_free(NN.table_knn, CC, SS)
+    elif lq:
         cF, cB = NN.precompute(r)
         DF, DB = cF.D, cB.D
         if not lazy:
@@ -136,8 +151,8 @@ def fmtstar(P, N=None, rm=1.0, connections="R", r=0.0, ensure_goal_ct=1, init_id
             xs_ = np.fromiter((t[0] for t in todo), dtype=np.int64) - 1
             ok = (lq_motions_free if lq else segments_free)(V[ys_], V[xs_], CC, SS)
             device_batches += 1
-        for k, (x, y_min, c_min, e) in enumerate(todo):
-            if (ok[k] if lazy else evalid[e]):             # is_free_motion(V[y_min], V[x], CC, SS)
+        for t_i, (x, y_min, c_min, e) in enumerate(todo):
+            if (ok[t_i] if lazy else evalid[e]):             # is_free_motion(V[y_min], V[x], CC, SS)
                 A[x - 1] = y_min
                 C[x - 1] = c_min
                 heapq.heappush(heap, (c_min, x))
@@ -166,6 +181,7 @@ def fmtstar(P, N=None, rm=1.0, connections="R", r=0.0, ensure_goal_ct=1, init_id
         "radius_multiplier": rm, "collision_checks": checks, "num_samples": N, "cost": float(C[z - 1]),
         "cumcost": costs, "planner": "FMTstar", "solved": solved, "tree": A, "path": sol, "r": r,
         "precomputed_edge_checks": int(lookups_before), "edge_checks": edge_checks,
+        "connections": connections, "k": (k if knn_mode else None),
         "device_edge_batches": device_batches,
     }
     P.solution = MPSolution(P.status, float(C[z - 1]), time.perf_counter() - t_start, meta)

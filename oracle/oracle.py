@@ -465,6 +465,71 @@ class LinearQuadraticGeneral:
         return out, cnt.value
 
 
+# ---- k-nearest connections: specification of csrc/knn.cu (the reference defines nothing; parity unpinned) ---------
+def knn_from_values(vals, k, skip):
+    """indices (ascending) of the k smallest entries of vals, ties towards the smaller index, `skip` excluded"""
+    idx = np.arange(len(vals))
+    keep = idx != skip
+    order = np.lexsort((idx[keep], vals[keep]))[:k]
+    return np.sort(idx[keep][order])
+
+
+def knn_brute(V, k):
+    """k-NN table of a Euclidean sample set as (colptr, rowval, nzval), 1-based: distances in the reference's order
+    (sum over coordinates left to right, one rounding per operation, then sqrt), k nearest by (distance, index)"""
+    V = _f64(V)
+    N, d = V.shape
+    k = min(k, N - 1)
+    colptr = 1 + k * np.arange(N + 1, dtype=np.int64)
+    rowval = np.zeros(N * k, dtype=np.int64)
+    nzval = np.zeros(N * k)
+    for q in range(N):
+        t = V[q, 0] - V[:, 0]
+        s = t * t
+        for i in range(1, d):
+            t = V[q, i] - V[:, i]
+            s = s + t * t
+        dist = np.sqrt(s)
+        sel = knn_from_values(dist, k, q)
+        rowval[q * k:(q + 1) * k] = sel + 1
+        nzval[q * k:(q + 1) * k] = dist[sel]
+    return colptr, rowval, nzval
+
+
+def knn_of_table(colptr, rowval, nzval, k):
+    """the same selection applied to the columns of any table (what mpb200_table_knn does)"""
+    cp = [1]
+    rv, nz = [], []
+    for w in range(len(colptr) - 1):
+        a, b = colptr[w] - 1, colptr[w + 1] - 1
+        rows, vals = rowval[a:b], nzval[a:b]
+        if len(rows) > k:
+            order = np.lexsort((np.arange(len(rows)), vals))[:k]
+            order = np.sort(order)
+            rows, vals = rows[order], vals[order]
+        rv.append(rows); nz.append(vals); cp.append(cp[-1] + len(rows))
+    return np.asarray(cp, dtype=np.int64), np.concatenate(rv).astype(np.int64), np.concatenate(nz)
+
+
+def union_transpose(A, B, N):
+    """out[:, v] = A[:, v] U { w : v in B[:, w] }, values from A else from B (what mpb200_table_union_transpose does)"""
+    cols = [dict() for _ in range(N)]
+    bcp, brv, bnz = B
+    for w in range(N):
+        for e in range(bcp[w] - 1, bcp[w + 1] - 1):
+            cols[brv[e] - 1][w + 1] = bnz[e]
+    acp, arv, anz = A
+    for v in range(N):
+        for e in range(acp[v] - 1, acp[v + 1] - 1):
+            cols[v][int(arv[e])] = anz[e]
+    cp = [1]
+    rv, nz = [], []
+    for v in range(N):
+        rows = sorted(cols[v])
+        rv.extend(rows); nz.extend(cols[v][r_] for r_ in rows); cp.append(cp[-1] + len(rows))
+    return np.asarray(cp, dtype=np.int64), np.asarray(rv, dtype=np.int64), np.asarray(nz)
+
+
 def close_points(obs, P, Ws, r2, want_all=False):
     """closeR(p, CC, W, r2) for every row of P with its own W (oracle/closest.c) ->
     (count[n], d2[n,S], shape[n,S], x[n,S,dw]) [+ (all_d2[n,S], all_x[n,S,dw])]"""
