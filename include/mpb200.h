@@ -222,6 +222,37 @@ int mpb200_lq_edges_free(const mpb200_samples *s, const mpb200_table *t, const m
 int mpb200_lq_motions_free(const mpb200_lq *lq, double r, const double *v_aos, const double *w_aos, int64_t n,
                            const mpb200_obstacles *o, const mpb200_space_desc *ss, uint8_t *out, int64_t *checks);
 
+/* ---- chopped-metric car spaces (Dubins / Reeds-Shepp) --------------------------------------------
+ * Replaces, for SE2 states (x, y, theta; AoS 3 x N):
+ *   ReedsSheppExact / DubinsExact and their evaluate = reedsshepp / dubins (simplecars.jl:5-27, 196-213, 266-364),
+ *   ChoppedMetric / ChoppedQuasiMetric evaluation (primitivetypes.jl:79-100),
+ *   helper_data_structures(V, ::Chopped...{ReedsSheppExact|DubinsExact}) = KD-tree over (x, y) (simplecars.jl:42-52)
+ *   + inball(V, ::ChoppedPreMetric, ::TreeDistanceDS, v, r, forwards) (nearneighbors.jl:185-198),
+ *   steering_control / propagate / collision_waypoints (simplecars.jl:55-82) behind is_free_motion
+ *   (statespaces.jl:134-142, 153-158).
+ * sin / cos / atan2 / acos are fixed polynomial routines (specified in oracle/cars.c; the reference calls openlibm:
+ * parity unpinned there); everything else follows the reference's operation order. */
+#define MPB200_CAR_REEDS_SHEPP 0
+#define MPB200_CAR_DUBINS 1
+/* tableF column v: { i != v : (x,y) within r, chopped d(V[v] -> V[i]) <= r }, stored value = the path length;
+ * tableB column v: the same with d(V[i] -> V[v]) (Dubins; pass tableB = NULL for the symmetric Reeds-Shepp
+ * metric, whose MetricNN serves inballF! and inballB! from the forward table).  chopval = the metric's chop value
+ * (setup_steering sets it to r).  s must hold d = 3 states; the query range of s is honoured. */
+int mpb200_car_inball_build(mpb200_samples *s, int32_t kind, double turning_radius, double r, double chopval,
+                            mpb200_table **tableF, mpb200_table **tableB, int64_t *nnzF, int64_t *nnzB);
+/* (cost, steering_control) for n explicit pairs: segments = n x 5 x (duration, signed speed, signed curvature),
+ * nseg[i] of them valid (3 for Dubins, 3..5 for Reeds-Shepp) */
+int mpb200_car_steer(int32_t kind, double turning_radius, double speed, const double *v_aos, const double *w_aos,
+                     int64_t n, double *cost, int32_t *nseg, double *segments);
+/* is_free_motion(V[y], V[x], CC, SS) for every stored entry (row y, column x) of a table: arc waypoints every pi/12
+ * of positive heading change (simplecars.jl:71-82), each but the last bounds-checked, consecutive ones swept. */
+int mpb200_car_edges_free(const mpb200_samples *s, const mpb200_table *t, int32_t kind, double turning_radius,
+                          double speed, const mpb200_obstacles *o, const mpb200_space_desc *ss, uint64_t *bitchunks,
+                          int64_t *checks);
+int mpb200_car_motions_free(int32_t kind, double turning_radius, double speed, const double *v_aos,
+                            const double *w_aos, int64_t n, const mpb200_obstacles *o, const mpb200_space_desc *ss,
+                            uint8_t *out, int64_t *checks);
+
 /* ---- Monte-Carlo trajectory collision probability -----------------------------------
  * NOT in the reference (only paper links, README.md:9-10, and the helper geometry
  * closest/closeR, SAT2D.jl:208-285, boxesND.jl:61-86): specified in SURVEY.md section 11 /

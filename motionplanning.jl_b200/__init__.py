@@ -18,6 +18,8 @@ from .nearneighbors import (ImmutableNNC, MetricNN, QuasiMetricNN, SampleSet, Sp
                             nonzeros, viewcol, knn, knnB, knnF, mutualknn, mutualknnF)
 from .linearquadratic import (DoubleIntegrator, LinearQuadratic, LinearQuadraticQuasiMetricSpace,  # noqa: F401
                               lq_motions_free, setup_steering, steer, steer_batch)
+from .simplecars import (ChoppedMetric, ChoppedQuasiMetric, DubinsExact, DubinsQuasiMetricSpace, ReedsSheppExact,  # noqa: F401
+                         ReedsSheppMetricSpace, car_motions_free, car_steer_batch, steering_control)
 from .problems import (BallGoal, MPProblem, MPSolution, PointGoal, RectangleGoal, StateGoal, is_goal_pt,  # noqa: F401
                        sample_free, sample_free_goal, sample_goal)
 from .planners import fmtstar  # noqa: F401

@@ -192,6 +192,16 @@ int lq_motions_free_device(const mpb200_lq *lq, double r, const double *dA, cons
                            const mpb200_obstacles *o, const mpb200_space_desc *ss, uint8_t *d_out,
                            unsigned long long *d_checks);
 
+int car_extract_xy_device(const double *dV3, int64_t N, double *dV2);
+int car_inball_device(const mpb200_samples *s, const mpb200_table *cand, int kind, double rturn, double r, double chopval,
+                      mpb200_table *tF, mpb200_table *tB, DevBuf &work, DevBuf &scan_tmp);
+int car_edges_free_device(const mpb200_samples *s, const mpb200_table *t, int kind, double rturn, double speed,
+                          const mpb200_obstacles *o, const mpb200_space_desc *ss, uint32_t *d_bits32,
+                          unsigned long long *d_checks);
+int car_motions_free_device(int kind, double rturn, double speed, const double *dA, const double *dB, int64_t n,
+                            const mpb200_obstacles *o, const mpb200_space_desc *ss, uint8_t *d_out, unsigned long long *d_checks);
+int car_steer_device(int kind, double rturn, double speed, const double *dA, const double *dB, int64_t n, double *d_cost,
+                     int *d_nseg, double *d_segs);
 int pipe_peak_device(int kind, double *ops_per_s);
 int table_knn_device(const mpb200_table *t, int k, mpb200_table *out, int64_t *short_cols, DevBuf &scan_tmp);
 int table_union_transpose_device(const mpb200_table *a, const mpb200_table *b, mpb200_table *out, DevBuf &scan_tmp);
@@ -397,6 +407,9 @@ int mpb200_samples_destroy(mpb200_samples *s) {
     if (!s) return MPB200_OK;
     if (ctx().ready) cudaStreamSynchronize(ctx().stream);
     if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
+    if (s->shadow_xy) mpb200_samples_destroy(s->shadow_xy);
+    if (s->shadow_cand) mpb200_table_destroy(s->shadow_cand);
+    s->car_work.release();
     s->V.release(); s->cell_start.release(); s->cell_fill.release(); s->sorted_idx.release();
     s->sorted_pos.release(); s->pt_order.release(); s->minmax.release(); s->scan_tmp.release(); s->point_bits.release(); s->q_order.release(); s->aux.release();
     delete s;
@@ -994,6 +1007,144 @@ int mpb200_close_points(const mpb200_obstacles *o, const double *p_aos, const do
     if (all_d2) MPB_CUDA(cudaMemcpyAsync(all_d2, bAD.p, sizeof(double) * nS, cudaMemcpyDeviceToHost, st));
     if (all_x) MPB_CUDA(cudaMemcpyAsync(all_x, bAX.p, sizeof(double) * nS * dw, cudaMemcpyDeviceToHost, st));
     MPB_CUDA(cudaStreamSynchronize(st));
+    return MPB200_OK;
+}
+
+// ---- chopped-metric car spaces --------------------------------------------------------------------------------
+static int car_args(int32_t kind, double rturn, double speed) {
+    MPB_CHECK_ARG(kind == MPB200_CAR_REEDS_SHEPP || kind == MPB200_CAR_DUBINS, "kind must be MPB200_CAR_REEDS_SHEPP or MPB200_CAR_DUBINS");
+    MPB_CHECK_ARG(rturn > 0 && rturn < std::numeric_limits<double>::infinity(), "turning radius must be positive");
+    MPB_CHECK_ARG(speed > 0 && speed < std::numeric_limits<double>::infinity(), "speed must be positive");
+    return MPB200_OK;
+}
+int mpb200_car_inball_build(mpb200_samples *s, int32_t kind, double turning_radius, double r, double chopval,
+                            mpb200_table **tableF, mpb200_table **tableB, int64_t *nnzF, int64_t *nnzB) {
+    MPB_REQUIRE_INIT();
+    MPB_CHECK_ARG(s != nullptr && tableF != nullptr, "NULL handle");
+    MPB_CHECK_ARG(s->d == 3, "car spaces need SE2 states (d = 3: x, y, theta)");
+    MPB_CHECK_ARG(r >= 0 && r == r && chopval == chopval, "r must be a non-negative number");
+    if (int rc = car_args(kind, turning_radius, 1.0)) return rc;
+    MPB_CHECK_ARG(tableB == nullptr || tableB != tableF, "tableF and tableB must be different handles");
+    // the (x, y) columns as a 2-D sample set (the reference's KD-tree lower-bound structure), made once
+    if (!s->shadow_xy) {
+        mpb200_samples *xy = new (std::nothrow) mpb200_samples();
+        if (!xy) return fail(MPB200_ENOMEM, "out of host memory");
+        xy->N = s->N; xy->d = 2; xy->q0 = 0; xy->q1 = s->N;
+        int rc = xy->V.reserve(sizeof(double) * (size_t)(2 * s->N + 1));
+        if (!rc) rc = car_extract_xy_device(s->V.as<double>(), s->N, xy->V.as<double>());
+        if (!rc) rc = finish_samples(xy);
+        if (rc) { mpb200_samples_destroy(xy); return rc; }
+        s->shadow_xy = xy;
+    }
+    mpb200_samples *xy = s->shadow_xy;
+    if (xy->q0 != s->q0 || xy->q1 != s->q1)
+        if (int rc = mpb200_samples_set_query_range(xy, s->q0, s->q1)) return rc;
+    if (int rc = mpb200_inball_build(xy, r, &s->shadow_cand, nullptr)) return rc;
+    mpb200_table *tF = *tableF, *tB = tableB ? *tableB : nullptr;
+    bool freshF = false, freshB = false;
+    if (!tF) { tF = new (std::nothrow) mpb200_table(); freshF = true; }
+    if (tableB && !tB) { tB = new (std::nothrow) mpb200_table(); freshB = true; }
+    if (!tF || (tableB && !tB)) {
+        if (freshF && tF) mpb200_table_destroy(tF);
+        if (freshB && tB) mpb200_table_destroy(tB);
+        return fail(MPB200_ENOMEM, "out of host memory");
+    }
+    int rc = car_inball_device(s, s->shadow_cand, kind, turning_radius, r, chopval, tF, tB, s->car_work, s->scan_tmp);
+    if (rc) {
+        if (freshF) mpb200_table_destroy(tF);
+        if (freshB) mpb200_table_destroy(tB);
+        return rc;
+    }
+    *tableF = tF;
+    if (tableB) *tableB = tB;
+    if (nnzF) *nnzF = tF->nnz;
+    if (nnzB) *nnzB = tB ? tB->nnz : 0;
+    return MPB200_OK;
+}
+int mpb200_car_steer(int32_t kind, double turning_radius, double speed, const double *v, const double *w, int64_t n,
+                     double *cost, int32_t *nseg, double *segments) {
+    MPB_REQUIRE_INIT();
+    MPB_CHECK_ARG(n >= 0 && (n == 0 || (v && w && cost && nseg && segments)), "NULL argument");
+    if (int rc = car_args(kind, turning_radius, speed)) return rc;
+    if (n == 0) return MPB200_OK;
+    cudaStream_t st = ctx().stream;
+    static DevBuf bufA, bufB, bufC, bufN, bufS;
+    const size_t bytes = sizeof(double) * (size_t)(3 * n);
+    if (int rc = bufA.reserve(bytes)) return rc;
+    if (int rc = bufB.reserve(bytes)) return rc;
+    if (int rc = bufC.reserve(sizeof(double) * (size_t)n)) return rc;
+    if (int rc = bufN.reserve(sizeof(int) * (size_t)n)) return rc;
+    if (int rc = bufS.reserve(sizeof(double) * (size_t)(15 * n))) return rc;
+    MPB_CUDA(cudaMemcpyAsync(bufA.p, v, bytes, cudaMemcpyHostToDevice, st));
+    MPB_CUDA(cudaMemcpyAsync(bufB.p, w, bytes, cudaMemcpyHostToDevice, st));
+    if (int rc = car_steer_device(kind, turning_radius, speed, bufA.as<double>(), bufB.as<double>(), n, bufC.as<double>(),
+                                  bufN.as<int>(), bufS.as<double>()))
+        return rc;
+    MPB_CUDA(cudaMemcpyAsync(cost, bufC.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    MPB_CUDA(cudaMemcpyAsync(nseg, bufN.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    MPB_CUDA(cudaMemcpyAsync(segments, bufS.p, sizeof(double) * (size_t)(15 * n), cudaMemcpyDeviceToHost, st));
+    MPB_CUDA(cudaStreamSynchronize(st));
+    return MPB200_OK;
+}
+int mpb200_car_edges_free(const mpb200_samples *s, const mpb200_table *t_, int32_t kind, double turning_radius,
+                          double speed, const mpb200_obstacles *o, const mpb200_space_desc *ss, uint64_t *bitchunks,
+                          int64_t *checks) {
+    MPB_REQUIRE_INIT();
+    MPB_CHECK_ARG(s && t_ && o && ss, "NULL handle");
+    MPB_CHECK_ARG(s->d == 3, "car spaces need SE2 states (d = 3: x, y, theta)");
+    if (int rc = car_args(kind, turning_radius, speed)) return rc;
+    mpb200_table *t = const_cast<mpb200_table *>(t_);
+    MPB_CHECK_ARG(t->src_N == s->N && t->src_d == s->d, "the table was not built from this sample set");
+    Context &c = ctx();
+    cudaStream_t st = c.stream;
+    const size_t words = (size_t)ceil_div(t->nnz, 64);
+    if (int rc = t->edge_bits.reserve(sizeof(uint64_t) * (words + 1))) return rc;
+    t->edge_bits_valid = false;
+    phase_bank(MPB200_OP_EDGES);
+    phase_mark(0);
+    MPB_CUDA(cudaMemsetAsync(t->edge_bits.p, 0, sizeof(uint64_t) * (words + 1), st));
+    MPB_CUDA(cudaMemsetAsync(c.d_scalar + 4, 0, sizeof(int64_t), st));
+    if (int rc = car_edges_free_device(s, t, kind, turning_radius, speed, o, ss, t->edge_bits.as<uint32_t>(),
+                                       reinterpret_cast<unsigned long long *>(c.d_scalar + 4)))
+        return rc;
+    t->edge_bits_valid = true;
+    t->edge_bits_nnz = t->nnz;
+    phase_mark(1);
+    phases_collect(1);
+    if (bitchunks || checks) {
+        if (bitchunks && words)
+            MPB_CUDA(cudaMemcpyAsync(bitchunks, t->edge_bits.p, sizeof(uint64_t) * words, cudaMemcpyDeviceToHost, st));
+        MPB_CUDA(cudaMemcpyAsync(c.h_scalar + 4, c.d_scalar + 4, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        MPB_CUDA(cudaStreamSynchronize(st));
+        if (checks) *checks = c.h_scalar[4];
+    }
+    return MPB200_OK;
+}
+int mpb200_car_motions_free(int32_t kind, double turning_radius, double speed, const double *v, const double *w,
+                            int64_t n, const mpb200_obstacles *o, const mpb200_space_desc *ss, uint8_t *out,
+                            int64_t *checks) {
+    MPB_REQUIRE_INIT();
+    MPB_CHECK_ARG(o && ss && n >= 0 && (n == 0 || (v && w && out)), "NULL argument");
+    if (int rc = car_args(kind, turning_radius, speed)) return rc;
+    if (checks) *checks = 0;
+    if (n == 0) return MPB200_OK;
+    Context &c = ctx();
+    cudaStream_t st = c.stream;
+    static DevBuf bufA, bufB, bufO;
+    const size_t bytes = sizeof(double) * (size_t)(3 * n);
+    if (int rc = bufA.reserve(bytes)) return rc;
+    if (int rc = bufB.reserve(bytes)) return rc;
+    if (int rc = bufO.reserve((size_t)n + 64)) return rc;
+    MPB_CUDA(cudaMemcpyAsync(bufA.p, v, bytes, cudaMemcpyHostToDevice, st));
+    MPB_CUDA(cudaMemcpyAsync(bufB.p, w, bytes, cudaMemcpyHostToDevice, st));
+    MPB_CUDA(cudaMemsetAsync(c.d_scalar + 5, 0, sizeof(int64_t), st));
+    if (int rc = car_motions_free_device(kind, turning_radius, speed, bufA.as<double>(), bufB.as<double>(), n, o, ss,
+                                         bufO.as<uint8_t>(), reinterpret_cast<unsigned long long *>(c.d_scalar + 5)))
+        return rc;
+    MPB_CUDA(cudaMemcpyAsync(out, bufO.p, (size_t)n, cudaMemcpyDeviceToHost, st));
+    MPB_CUDA(cudaMemcpyAsync(c.h_scalar + 5, c.d_scalar + 5, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    MPB_CUDA(cudaStreamSynchronize(st));
+    if (checks) *checks = c.h_scalar[5];
     return MPB200_OK;
 }
 

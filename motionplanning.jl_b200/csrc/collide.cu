@@ -425,6 +425,7 @@ int make_space(const mpb200_space_desc *ss, int d_state, SpaceDev *out, int *dw)
             else if (N_ == 8 && DW_ == 8) { CALL(8, 8, 1); done__ = true; }                \
             else if (N_ == 9 && DW_ == 9) { CALL(9, 9, 1); done__ = true; }                \
             else if (N_ == 10 && DW_ == 10) { CALL(10, 10, 1); done__ = true; }            \
+            else if (N_ == 3 && DW_ == 2) { CALL(3, 2, 1); done__ = true; }                \
             else if (N_ == 4 && DW_ == 2) { CALL(4, 2, 1); done__ = true; }                \
             else if (N_ == 6 && DW_ == 3) { CALL(6, 3, 1); done__ = true; }                \
         }                                                                                  \

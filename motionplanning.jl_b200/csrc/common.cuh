@@ -143,6 +143,10 @@ struct mpb200_samples {
     cudaGraphExec_t graph_exec = nullptr;
     uint64_t graph_key[32] = {};
     int graph_launches = 0;  // kernels inside the graph (launch accounting)
+    // car spaces (cars.cu): the (x, y) columns as a sample set of their own + the Euclidean candidate table over them
+    mpb200_samples *shadow_xy = nullptr;
+    mpb200_table *shadow_cand = nullptr;
+    mpb::DevBuf car_work;
 };
 
 struct mpb200_obstacles {

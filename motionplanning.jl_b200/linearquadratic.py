@@ -59,6 +59,8 @@ def setup_steering(d, r):
         d = d.dist
     if isinstance(d, LinearQuadratic):
         d.cmax = float(r)
+    elif hasattr(d, "chopval"):                            # setup_steering(d::ChoppedPreMetric, r), statespaces.jl:75
+        d.chopval = float(r)
 
 
 def LinearQuadraticQuasiMetricSpace(lo, hi, A, B, c, R, C):

@@ -230,6 +230,23 @@ class SampleSet:
         return SparseMatrixCSC(len(self), table.ncols, colptr, rowval, nzval)
 
 
+def _is_car(dist):
+    from .simplecars import is_car_metric
+    return is_car_metric(dist)
+
+
+def _car_edges_free(NN, table, CC, SS, fetch=True):
+    """validity per stored entry (row y -> column x) of a car-space table: the motion V[y] -> V[x] (fmt.jl:75)"""
+    m = NN.dist.m
+    d = SS.desc()
+    bits = NN.pool.array(("car_edge_bits", table.name), (table.nnz + 63) // 64, np.uint64) if fetch else None
+    checks = _lib.c_i64(0)
+    _lib.check(_lib.lib().mpb200_car_edges_free(NN.handle(), table.h, m.kind, m.r, m.s, CC.handle(), ctypes.byref(d),
+                                                _lib.ptr(bits), ctypes.byref(checks)))
+    CC.count += checks.value
+    return bits, checks.value
+
+
 def _knn_radius_guess(V, k):
     """radius of the ball expected to hold ~1.6 k samples of a uniform cloud filling the samples' bounding box"""
     import math
@@ -268,8 +285,17 @@ class MetricNN(SampleSet):
     def build_table(self, r):
         """Device-only: grid build + count + fill; the table stays in HBM. Returns nnz."""
         nnz = _lib.c_i64(0)
-        _lib.check(_lib.lib().mpb200_inball_build(self.handle(), float(r), ctypes.byref(self.table.h),
-                                                  ctypes.byref(nnz)))
+        if _is_car(self.dist):
+            # ChoppedMetric{ReedsSheppExact}: helper_data_structures = KD-tree over (x, y) (simplecars.jl:42-44),
+            # inball = lower-bound candidates + exact metric (nearneighbors.jl:185-198); forward costs only
+            # (inballF! and inballB! of a MetricNN are both inball!, nearneighbors.jl:200-203)
+            m = self.dist.m
+            chop = self.dist.chopval if self.dist.chopval < float("inf") else float(r)
+            _lib.check(_lib.lib().mpb200_car_inball_build(self.handle(), m.kind, m.r, float(r), chop,
+                                                          ctypes.byref(self.table.h), None, ctypes.byref(nnz), None))
+        else:
+            _lib.check(_lib.lib().mpb200_inball_build(self.handle(), float(r), ctypes.byref(self.table.h),
+                                                      ctypes.byref(nnz)))
         self.table.nnz = nnz.value
         self.table.ncols = self.q1 - self.q0
         self.r = float(r)
@@ -329,6 +355,9 @@ class MetricNN(SampleSet):
         self.cache_mknn = ImmutableNNC(self.fetch_table(self.table_mknn, "mknn"), float(r))
         return self.cache_knn, self.cache_mknn
 
+    def car_edges_free(self, CC, SS, fetch=True):
+        return _car_edges_free(self, self.table, CC, SS, fetch)
+
     def precompute_checked(self, r, CC, SS):
         """precompute + edge validity through the fused pass -> (ImmutableNNC, edge chunks, checks)"""
         _, checks = self.build_table_checked(r, CC, SS)
@@ -357,6 +386,16 @@ class QuasiMetricNN(SampleSet):
 
     def build_tables(self, r):
         nF, nB = _lib.c_i64(0), _lib.c_i64(0)
+        if _is_car(self.dist):                             # ChoppedQuasiMetric{DubinsExact} (simplecars.jl:45-49)
+            m = self.dist.m
+            chop = self.dist.chopval if self.dist.chopval < float("inf") else float(r)
+            _lib.check(_lib.lib().mpb200_car_inball_build(self.handle(), m.kind, m.r, float(r), chop,
+                                                          ctypes.byref(self.tableF.h), ctypes.byref(self.tableB.h),
+                                                          ctypes.byref(nF), ctypes.byref(nB)))
+            for t, n in ((self.tableF, nF), (self.tableB, nB)):
+                t.nnz, t.ncols = n.value, self.q1 - self.q0
+            self.r = float(r)
+            return nF.value, nB.value
         _lib.check(_lib.lib().mpb200_lq_inball_build(self.handle(), self.dist.handle(), float(r),
                                                      ctypes.byref(self.tableF.h), ctypes.byref(self.tableB.h),
                                                      ctypes.byref(nF), ctypes.byref(nB)))
@@ -395,6 +434,9 @@ class QuasiMetricNN(SampleSet):
         self.cache_knnB = ImmutableNNC(self.fetch_table(self.table_knnB, "knnB"), float(r))
         self.cache_mknnF = ImmutableNNC(self.fetch_table(self.table_mknnF, "mknnF"), float(r))
         return self.cache_knnF, self.cache_knnB, self.cache_mknnF
+
+    def car_edges_free(self, CC, SS, fetch=True, table=None):
+        return _car_edges_free(self, table if table is not None else self.tableB, CC, SS, fetch)
 
     def lq_edges_free(self, CC, SS, fetch=True, table=None):
         """validity per stored entry (row y -> column x) of the BACKWARD table (or `table`, e.g. the backward k-nearest

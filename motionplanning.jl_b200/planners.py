@@ -18,6 +18,7 @@ import time
 import numpy as np
 
 from .linearquadratic import LinearQuadratic, setup_steering
+from .simplecars import is_car_metric
 from .nearneighbors import MetricNN
 from .problems import MPSolution, goal_mask, sample_free
 from .statespaces import Euclidean, states_free, volume
@@ -72,6 +73,9 @@ def fmtstar(P, N=None, rm=1.0, connections="R", r=0.0, ensure_goal_ct=1, init_id
         raise ValueError("edge_checks must be 'table' or 'lazy'")
     lazy = edge_checks == "lazy"
     lq = isinstance(SS.dist, LinearQuadratic)
+    car = is_car_metric(SS.dist)
+    if car and knn_mode:
+        raise NotImplementedError("k-nearest connections are not wired for the car spaces")
     ebits = None
     if knn_mode and lq:
         cF, cB, cM = NN.precompute_knn(k, r)               # cost radius grows from r until every column holds k
@@ -86,6 +90,14 @@ def fmtstar(P, N=None, rm=1.0, connections="R", r=0.0, ensure_goal_ct=1, init_id
         DF, DB = cM.D, cK.D
         if not lazy:
             ebits, _ = NN.edges_free(NN.table_knn, CC, SS)
+    elif car:
+        if SS.dist.symmetric:                              # MetricNN: inballF! = inballB! = inball! (forward costs)
+            DF = DB = NN.precompute(r).D
+        else:
+            cF, cB = NN.precompute(r)
+            DF, DB = cF.D, cB.D
+        if not lazy:
+            ebits, _ = NN.car_edges_free(CC, SS)
     elif lq:
         cF, cB = NN.precompute(r)
         DF, DB = cF.D, cB.D
@@ -101,6 +113,7 @@ def fmtstar(P, N=None, rm=1.0, connections="R", r=0.0, ensure_goal_ct=1, init_id
     evalid = _bits_to_bool(ebits, DB.nnz) if not lazy else None
     if lazy:
         from .linearquadratic import lq_motions_free
+        from .simplecars import car_motions_free
         from .statespaces import segments_free
     F = _bits_to_bool(NN.points_free(CC, SS), N) if checkpts else np.ones(N, dtype=bool)
     is_goal = goal_mask(V, P.goal, SS)
@@ -141,7 +154,7 @@ def fmtstar(P, N=None, rm=1.0, connections="R", r=0.0, ensure_goal_ct=1, init_id
             j = int(np.argmin(costs))                      # findmin: first minimum
             c_min, y_min = float(costs[j]), int(cand[j])
             e = lo + int(np.flatnonzero(keep)[j])          # stored entry (row y_min, column x)
-            if lq:
+            if lq or car:
                 checks += 1                                # counted per motion; segments in metadata below
             else:
                 checks += int(inb[y_min - 1])
@@ -149,7 +162,7 @@ def fmtstar(P, N=None, rm=1.0, connections="R", r=0.0, ensure_goal_ct=1, init_id
         if lazy and todo:                                  # ONE batched device call for the whole expansion
             ys_ = np.fromiter((t[1] for t in todo), dtype=np.int64) - 1
             xs_ = np.fromiter((t[0] for t in todo), dtype=np.int64) - 1
-            ok = (lq_motions_free if lq else segments_free)(V[ys_], V[xs_], CC, SS)
+            ok = (car_motions_free if car else lq_motions_free if lq else segments_free)(V[ys_], V[xs_], CC, SS)
             device_batches += 1
         for t_i, (x, y_min, c_min, e) in enumerate(todo):
             if (ok[t_i] if lazy else evalid[e]):             # is_free_motion(V[y_min], V[x], CC, SS)

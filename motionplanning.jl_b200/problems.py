@@ -122,7 +122,7 @@ class MPProblem:
 def defaultNN(SS, init):
     """statespaces.jl:163-170"""
     init = np.asarray(init, dtype=np.float64)
-    if isinstance(SS.dist, Euclidean):
+    if isinstance(SS.dist, Euclidean) or getattr(SS.dist, "symmetric", False):   # Metric / ChoppedMetric{<:Metric}
         return MetricNN(init.reshape(1, -1), SS.dist, init)
     return QuasiMetricNN(init.reshape(1, -1), SS.dist, init)
 

@@ -148,6 +148,9 @@ def is_free_state(v, CC, SS=None):
 def is_free_motion(v, w, CC, SS=None):
     """statespaces.jl:153-158 for straight-line (Euclidean) waypoints / robots2D.jl:13 / boxesND.jl:26"""
     if SS is not None and not isinstance(SS.dist, Euclidean):
+        from .simplecars import car_motions_free, is_car_metric
+        if is_car_metric(SS.dist):
+            return bool(car_motions_free(v, w, CC, SS)[0])
         from .linearquadratic import lq_is_free_motion
         return lq_is_free_motion(v, w, CC, SS)
     return bool(segments_free(v, w, CC, SS)[0])
@@ -160,6 +163,9 @@ def is_free_path(path, CC, SS=None):
         return True
     if SS is not None and not isinstance(SS.dist, Euclidean):
         # is_free_motion(p[i], p[i+1], CC, SS) per pair: the waypoints of the optimal trajectory, not a chord
+        from .simplecars import car_motions_free, is_car_metric
+        if is_car_metric(SS.dist):
+            return bool(np.all(car_motions_free(P[:-1], P[1:], CC, SS)))
         from .linearquadratic import lq_motions_free
         return bool(np.all(lq_motions_free(P[:-1], P[1:], CC, SS)))
     return bool(np.all(segments_free(P[:-1], P[1:], CC, SS)))

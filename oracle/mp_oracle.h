@@ -140,6 +140,25 @@ void orc_lqg_edges_free_csc(const orc_checker *CC, const orc_space *Sp, const or
                             const int64_t *colptr, const int64_t *rowval, int64_t c0, int64_t c1, uint8_t *out,
                             int64_t *count);
 
+/* cars.c : chopped-metric car spaces (simplecars.jl; primitivetypes.jl:79-100; nearneighbors.jl:185-198).
+ * kind 0 = ReedsSheppExact, 1 = DubinsExact; states (x, y, theta); segs = 5 x (duration, speed, curvature). */
+double orc_mod2pi(double x);
+void orc_det_sincos(double x, double *sn, double *cs);
+double orc_det_sin(double x);
+double orc_det_cos(double x);
+double orc_det_atan2(double y, double x);
+double orc_det_acos(double x);
+double orc_car_steer(int kind, double rturn, double speed, const double *v, const double *w, int *nseg, double *segs);
+void orc_car_propagate(const double *v, const double *u3, double *out);
+double orc_car_chopped(int kind, double rturn, double chopval, const double *v, const double *w);
+void orc_car_inball(const double *V, int64_t N, int kind, double rturn, double r, double chopval, int forwards,
+                    int64_t q0, int64_t q1, int64_t *colptr, int64_t *rowval, double *nzval);
+int orc_car_is_free_motion(const orc_checker *CC, const orc_space *S, int kind, double rturn, double speed,
+                           const double *v, const double *w, int64_t *count);
+void orc_car_edges_free_csc(const orc_checker *CC, const orc_space *S, int kind, double rturn, double speed,
+                            const double *V, const int64_t *colptr, const int64_t *rowval, int64_t c0, int64_t c1,
+                            uint8_t *out, int64_t *count);
+
 /* closest.c : closest / closeR under a weight matrix (SAT2D.jl:208-285, boxesND.jl:61-86); W row-major */
 #define ORC_CP_MAXD 4
 void orc_closest_circle(const double *p, const double *rec, const double *W, double *d2, double *x);

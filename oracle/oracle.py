@@ -90,6 +90,21 @@ def lib():
                                              P(c_i64)]
         L.orc_close_points.argtypes = [P(Checker), c_vp, c_vp, c_i64, ctypes.c_int, c_dbl, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]
         L.orc_close_points.restype = ctypes.c_int
+        for f in ("orc_mod2pi", "orc_det_sin", "orc_det_cos", "orc_det_acos"):
+            getattr(L, f).restype = c_dbl
+            getattr(L, f).argtypes = [c_dbl]
+        L.orc_det_atan2.restype = c_dbl
+        L.orc_det_atan2.argtypes = [c_dbl, c_dbl]
+        L.orc_car_steer.restype = c_dbl
+        L.orc_car_steer.argtypes = [ctypes.c_int, c_dbl, c_dbl, c_vp, c_vp, P(ctypes.c_int), c_vp]
+        L.orc_car_propagate.argtypes = [c_vp, c_vp, c_vp]
+        L.orc_car_chopped.restype = c_dbl
+        L.orc_car_chopped.argtypes = [ctypes.c_int, c_dbl, c_dbl, c_vp, c_vp]
+        L.orc_car_inball.argtypes = [c_vp, c_i64, ctypes.c_int, c_dbl, c_dbl, c_dbl, ctypes.c_int, c_i64, c_i64, c_vp,
+                                     c_vp, c_vp]
+        L.orc_car_is_free_motion.argtypes = [P(Checker), P(Space), ctypes.c_int, c_dbl, c_dbl, c_vp, c_vp, P(c_i64)]
+        L.orc_car_edges_free_csc.argtypes = [P(Checker), P(Space), ctypes.c_int, c_dbl, c_dbl, c_vp, c_vp, c_vp, c_i64,
+                                             c_i64, c_vp, P(c_i64)]
         L.orc_lq_steer.argtypes = [ctypes.c_int, c_vp, c_vp, c_vp, c_dbl, P(c_dbl), P(c_dbl)]
         L.orc_lq_cost_terms.argtypes = [ctypes.c_int, c_vp, c_vp, c_vp, c_dbl, c_vp]
         L.orc_lq_state.argtypes = [ctypes.c_int, c_vp, c_vp, c_dbl, c_dbl, c_vp]
@@ -462,6 +477,64 @@ class LinearQuadraticGeneral:
         cnt = c_i64(0)
         lib().orc_lqg_edges_free_csc(ctypes.byref(cc), ctypes.byref(space.c), ctypes.byref(self.S), float(r), _p(V),
                                      _p(colptr), _p(rowval), c0, c0 + len(colptr) - 1, _p(out), ctypes.byref(cnt))
+        return out, cnt.value
+
+
+class SimpleCar:
+    """ReedsSheppExact (kind 0) / DubinsExact (kind 1) with turning radius r and speed s (oracle/cars.c)"""
+
+    def __init__(self, kind, r=1.0, s=1.0):
+        self.kind = {"reedsshepp": 0, "dubins": 1}.get(kind, kind)
+        self.r, self.s = float(r), float(s)
+
+    def steer(self, v, w):
+        """-> (cost, segments[l, 3]) = (path length, steering_control as (duration, speed, curvature) rows)"""
+        v, w = _f64(v), _f64(w)
+        n = ctypes.c_int(0)
+        segs = np.zeros(15)
+        c = lib().orc_car_steer(self.kind, self.r, self.s, _p(v), _p(w), ctypes.byref(n), _p(segs))
+        return c, segs.reshape(5, 3)[:n.value].copy()
+
+    def propagate(self, v, u):
+        v, u = _f64(v), _f64(u)
+        out = np.zeros(3)
+        lib().orc_car_propagate(_p(v), _p(u), _p(out))
+        return out
+
+    def chopped(self, v, w, chopval):
+        v, w = _f64(v), _f64(w)
+        return lib().orc_car_chopped(self.kind, self.r, float(chopval), _p(v), _p(w))
+
+    def inball(self, V, r, forwards=True, chopval=None, q0=0, q1=None):
+        V = _f64(V)
+        N = V.shape[0]
+        q1 = N if q1 is None else q1
+        chop = float(r if chopval is None else chopval)
+        colptr = np.zeros(q1 - q0 + 1, dtype=np.int64)
+        lib().orc_car_inball(_p(V), N, self.kind, self.r, float(r), chop, int(forwards), q0, q1, _p(colptr), None, None)
+        nnz = int(colptr[-1] - 1)
+        rowval, nzval = np.zeros(nnz, dtype=np.int64), np.zeros(nnz)
+        lib().orc_car_inball(_p(V), N, self.kind, self.r, float(r), chop, int(forwards), q0, q1, _p(colptr), _p(rowval),
+                             _p(nzval))
+        return colptr, rowval, nzval
+
+    def is_free_motion(self, obs, space, v, w):
+        v, w = _f64(v), _f64(w)
+        cc = obs.checker()
+        cnt = c_i64(0)
+        ok = lib().orc_car_is_free_motion(ctypes.byref(cc), ctypes.byref(space.c), self.kind, self.r, self.s, _p(v), _p(w),
+                                          ctypes.byref(cnt))
+        return bool(ok), cnt.value
+
+    def edges_free_csc(self, obs, space, V, colptr, rowval, c0=0):
+        V = _f64(V)
+        colptr = np.ascontiguousarray(colptr, dtype=np.int64)
+        rowval = np.ascontiguousarray(rowval, dtype=np.int64)
+        out = np.zeros(len(rowval), dtype=np.uint8)
+        cc = obs.checker()
+        cnt = c_i64(0)
+        lib().orc_car_edges_free_csc(ctypes.byref(cc), ctypes.byref(space.c), self.kind, self.r, self.s, _p(V), _p(colptr),
+                                     _p(rowval), c0, c0 + len(colptr) - 1, _p(out), ctypes.byref(cnt))
         return out, cnt.value
 
 

@@ -29,6 +29,8 @@ def fmt_oracle(V, is_goal, neighborsF, neighborsB, point_free, edge_free, checkp
             bi, bd = neighborsB(x)
             keep = [k for k in range(len(bi)) if H[bi[k] - 1]]
             costs = [C[bi[k] - 1] + bd[k] for k in keep]
+            if not costs:      # only possible with k-nearest connections (x in knnF(z) but no open node in knnB(x)):
+                continue       # findmin of an empty set would throw in the reference; specified here as 'skip x'
             j = min(range(len(costs)), key=lambda t: (costs[t], t))      # findmin: first minimum
             c_min, y_min = costs[j], int(bi[keep[j]])
             ok, n = edge_free(y_min - 1, x - 1)
