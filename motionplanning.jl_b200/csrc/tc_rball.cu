@@ -29,7 +29,11 @@
 namespace mpb {
 
 constexpr int kTcM = 128;      // query rows per CTA (= threads: one TMEM lane per thread)
-constexpr int kTcN = 128;      // samples per MMA tile (= TMEM columns per CTA)
+#ifndef MPB_TC_N
+#define MPB_TC_N 64
+#endif
+constexpr int kTcN = MPB_TC_N;  // samples per MMA tile (= TMEM columns per CTA): 64 -> eight CTAs share an SM's 512 columns
+constexpr int kTcCtas = 512 / kTcN;
 constexpr int kTcK = 16;       // contraction length: d coordinates + 2 threshold slots, zero padded
 
 __device__ __forceinline__ float to_tf32(float x) {
@@ -142,7 +146,7 @@ __device__ __forceinline__ double tc_exact_sq(const double *__restrict__ a, cons
 // MMAs, half the accumulator read-back (the kernel's bound, see the header); the slabs are then unordered and
 // slab_sort_to_csc sorts each column by index.  CTAs are launched longest-first (tile 0 sweeps everything).
 template <int D, int MODE>
-__global__ void __launch_bounds__(kTcM, 4)
+__global__ void __launch_bounds__(kTcM, kTcCtas)
 tc_rball_kernel(const double *__restrict__ V, const float *__restrict__ opB, const float *__restrict__ nrm_half,
                 int64_t N, int64_t Npad, int64_t q0, int64_t nq, double r2, float delta, int *__restrict__ counts,
                 int cap, int *__restrict__ slab_j, double *__restrict__ slab_s, int *__restrict__ rcounts) {
@@ -201,12 +205,24 @@ tc_rball_kernel(const double *__restrict__ V, const float *__restrict__ opB, con
     int pend_slot = 0;
     double pend_s = 0.0;
     uint32_t phase = 0;
-    for (int64_t t0 = (MODE == 3) ? (int64_t)blockIdx.x * kTcM : 0; t0 < Npad; t0 += kTcN) {
-        // stage operand B: the tile is one contiguous 8 KB block already in the smem layout
-        {
-            const float4 *src = reinterpret_cast<const float4 *>(opB) + (t0 >> 7) * (4 * 128);
+    // operand image: [tile of 128 samples][chunk 0..3][row 0..127]; an MMA tile = rows (t0 & 127) .. + kTcN of it
+    constexpr int kStage = 4 * kTcN / kTcM;  // float4 per thread per tile
+    float4 nextB[kStage];
+    auto load_tile = [&](int64_t t0) {
+        const float4 *src = reinterpret_cast<const float4 *>(opB) + (t0 >> 7) * (4 * 128) + (t0 & 127);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) sB[i * kTcN + tid] = src[i * 128 + tid];
+        for (int u = 0; u < kStage; ++u) {
+            const int i = tid + u * kTcM;
+            nextB[u] = src[(i / kTcN) * 128 + (i % kTcN)];
+        }
+    };
+    const int64_t t_first = (MODE == 3) ? (int64_t)blockIdx.x * kTcM : 0;
+    if (t_first < Npad) load_tile(t_first);
+    for (int64_t t0 = t_first; t0 < Npad; t0 += kTcN) {
+        // stage operand B (loaded one tile ahead into registers, so its global-load latency is behind the epilogue)
+        {
+#pragma unroll
+            for (int u = 0; u < kStage; ++u) sB[tid + u * kTcM] = nextB[u];
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> tensor core
         __syncthreads();
@@ -216,6 +232,7 @@ tc_rball_kernel(const double *__restrict__ V, const float *__restrict__ opB, con
             umma_tf32(tmem, a_desc1, b_desc1, idesc, 1u);
             umma_commit(bar);
         }
+        if (t0 + kTcN < Npad) load_tile(t0 + kTcN);
         mbar_wait(bar, phase);
         phase ^= 1u;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
