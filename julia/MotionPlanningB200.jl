@@ -279,4 +279,75 @@ function helper_data_structures{S}(V::Vector{S}, M::LinearQuadratic, backend::Ty
     BruteDistanceDS(fetch(tF[], nF[])), US, BruteDistanceDS(fetch(tB[], nB[])), US   # DSF, USF, DSB, USB (:73-76)
 end
 
+# ---- chopped-metric car spaces (simplecars.jl) ------------------------------------------------------------
+# helper_data_structures(V, ::ChoppedMetric{ReedsSheppExact}) / (V, ::ChoppedQuasiMetric{DubinsExact}) build a KD-tree
+# over (x, y) and every inball evaluates the exact metric on its candidates (simplecars.jl:42-52,
+# nearneighbors.jl:185-198); here the whole forward (and, for Dubins, backward) table is built at once and served as
+# ImmutableNNC caches.  kind: 0 = Reeds-Shepp, 1 = Dubins (MPB200_CAR_*).
+car_kind(::ReedsSheppExact) = Int32(0)
+car_kind(::DubinsExact) = Int32(1)
+function fetch_table(t::Ptr{Void}, N::Int, nnz::Int64)
+    cp = Array(Int64, N + 1); rv = Array(Int64, nnz); nz = Array(Float64, nnz)
+    check(ccall((:mpb200_table_fetch, LIB), Cint, (Ptr{Void}, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}), t, cp, rv, nz))
+    SparseMatrixCSC(N, N, cp, rv, nz)
+end
+function precompute_inball!{R<:ReedsSheppExact}(NN::MetricNN, M::ChoppedMetric{R}, r::Float64)
+    s = B200Samples(NN.V)                                   # SE2State is a FieldVector: 3 x N Float64
+    tF = Ref{Ptr{Void}}(C_NULL); nF = Ref{Int64}(0)
+    check(ccall((:mpb200_car_inball_build, LIB), Cint,
+                (Ptr{Void}, Int32, Float64, Float64, Float64, Ref{Ptr{Void}}, Ptr{Void}, Ref{Int64}, Ptr{Void}),
+                s.h, car_kind(M.m), M.m.r, r, M.chopval, tF, C_NULL, nF, C_NULL))
+    N = length(NN.V)
+    MetricNN(NN.V, NN.dist, NN.init, ImmutableNNC(fetch_table(tF[], N, nF[]), fill(r, N)), NN.DS, NN.US), s, tF[]
+end
+function precompute_inball!{D<:DubinsExact}(NN::QuasiMetricNN, M::ChoppedQuasiMetric{D}, r::Float64)
+    s = B200Samples(NN.V)
+    tF = Ref{Ptr{Void}}(C_NULL); tB = Ref{Ptr{Void}}(C_NULL); nF = Ref{Int64}(0); nB = Ref{Int64}(0)
+    check(ccall((:mpb200_car_inball_build, LIB), Cint,
+                (Ptr{Void}, Int32, Float64, Float64, Float64, Ref{Ptr{Void}}, Ref{Ptr{Void}}, Ref{Int64}, Ref{Int64}),
+                s.h, car_kind(M.m), M.m.r, r, M.chopval, tF, tB, nF, nB))
+    N = length(NN.V)
+    QuasiMetricNN(NN.V, NN.dist, NN.init, ImmutableNNC(fetch_table(tF[], N, nF[]), fill(r, N)),
+                  ImmutableNNC(fetch_table(tB[], N, nB[]), fill(r, N)), NN.DSF, NN.USF, NN.DSB, NN.USB), s, tF[], tB[]
+end
+# is_free_motion(v, w, CC, SS) over the arc waypoints (statespaces.jl:153-158, simplecars.jl:71-82)
+function is_free_motion{S,M<:ChoppedPreMetric}(v::SE2State, w::SE2State, CC::B200Checker, SS::BoundedStateSpace{S,M})
+    sd = space_desc(SS); out = Array(UInt8, 1); checks = Ref{Int64}(0); m = SS.dist.m
+    check(ccall((:mpb200_car_motions_free, LIB), Cint,
+                (Int32, Float64, Float64, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Void}, Ref{SpaceDescC}, Ptr{UInt8}, Ref{Int64}),
+                car_kind(m), m.r, m.s, Float64[v...], Float64[w...], 1, CC.h, sd.c, out, checks))
+    CC.count += checks[]
+    out[1] != 0
+end
+# steering_control(d, v, w) (simplecars.jl:69-70) as the reference's ZeroOrderHoldControl
+function steering_control_b200(m::SimpleCarMetric, v::SE2State, w::SE2State)
+    cost = Array(Float64, 1); nseg = Array(Int32, 1); segs = Array(Float64, 3, 5)
+    check(ccall((:mpb200_car_steer, LIB), Cint,
+                (Int32, Float64, Float64, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Int32}, Ptr{Float64}),
+                car_kind(m), m.r, m.s, Float64[v...], Float64[w...], 1, cost, nseg, segs))
+    cost[1], [StepControl(segs[1, i], SVector(segs[2, i], segs[3, i])) for i in 1:nseg[1]]
+end
+# validity of every stored edge (row y -> column x  <=>  is_free_motion(V[y], V[x], CC, SS)) as a BitVector
+function car_edges_free(s::B200Samples, t::Ptr{Void}, nnz::Int64, CC::B200Checker, SS::BoundedStateSpace)
+    sd = space_desc(SS); bits = BitVector(nnz); checks = Ref{Int64}(0); m = SS.dist.m
+    check(ccall((:mpb200_car_edges_free, LIB), Cint,
+                (Ptr{Void}, Ptr{Void}, Int32, Float64, Float64, Ptr{Void}, Ref{SpaceDescC}, Ptr{UInt64}, Ref{Int64}),
+                s.h, t, car_kind(m), m.r, m.s, CC.h, sd.c, bits.chunks, checks))
+    bits, checks[]
+end
+
+# ---- k-nearest connections (names exported at nearneighbors.jl:9-11, used at fmt.jl:17-19, defined nowhere) ------
+# table operations on any neighbour table: the k best entries of every column, and the mutual neighbourhoods
+# knnF(v) U { w : v in knnB(w) }; `short` = columns of t that held fewer than k entries (grow r and rebuild until 0)
+function table_knn(t::Ptr{Void}, k::Int)
+    out = Ref{Ptr{Void}}(C_NULL); nnz = Ref{Int64}(0); short = Ref{Int64}(0)
+    check(ccall((:mpb200_table_knn, LIB), Cint, (Ptr{Void}, Cint, Ref{Ptr{Void}}, Ref{Int64}, Ref{Int64}), t, k, out, nnz, short))
+    out[], nnz[], short[]
+end
+function table_union_transpose(a::Ptr{Void}, b::Ptr{Void})
+    out = Ref{Ptr{Void}}(C_NULL); nnz = Ref{Int64}(0)
+    check(ccall((:mpb200_table_union_transpose, LIB), Cint, (Ptr{Void}, Ptr{Void}, Ref{Ptr{Void}}, Ref{Int64}), a, b, out, nnz))
+    out[], nnz[]
+end
+
 end # module
