@@ -667,7 +667,7 @@ def secondary_block(mp, lib):
     _lib.check(lib.mpb200_release_cached())
     out = {}
     args = types.SimpleNamespace(scale=1.0)
-    for name, fn in (("C3", bc.c3), ("C4", bc.c4), ("C5", bc.c5)):
+    for name, fn in (("C3", bc.c3), ("C4", bc.c4), ("C5", bc.c5), ("F4", bc.f4), ("KNN", bc.kn)):
         try:
             out[name] = fn(mp, orc, fx, args)
         except Exception as e:   # noqa: BLE001 -- report and go on: the headline line must still print

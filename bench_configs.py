@@ -271,16 +271,122 @@ def f1(mp, orc, fx, args):
                 cpu_port=dict(sample=nq, samples_per_s=nq / t_cpu, cores=1))
 
 
+def f4(mp, orc, fx, args):
+    """chopped-metric car spaces.  N = 200k SE2 states in the unit square past ISRR_2H, turning radius
+    0.01, r = 0.025 (~390 (x, y) candidates per column): Reeds-Shepp table (one direction, 48 path evaluations per
+    candidate), Dubins tables (both directions, 6 words each) and the arc-waypoint edge checks of the Dubins table."""
+    N = int(200_000 * args.scale)
+    rturn, r = 0.01, 0.025
+    rng = np.random.Generator(np.random.PCG64(20240605))
+    V = np.column_stack([rng.random(N), rng.random(N), rng.uniform(0, 2 * np.pi, N)])
+    CC = mp.PointRobot2D(mp.obstaclesets.ISRR_2H())
+    lib = mp.load()
+    global SYNC
+    SYNC = lib.mpb200_synchronize
+    from mpb200 import _lib
+    out = dict(config="F4", workload="car spaces: N=%d SE2 states, ISRR_2H, turning radius %.3g, r=%.3g" % (N, rturn, r), N=N)
+    q = 32
+    So = orc.StateSpace([0, 0, 0], [1, 1, 2 * np.pi], ("view", [1, 2]))
+    for kind in ("reedsshepp", "dubins"):
+        SS = (mp.ReedsSheppMetricSpace if kind == "reedsshepp" else mp.DubinsQuasiMetricSpace)(rturn)
+        mp.setup_steering(SS, r)
+        car = orc.SimpleCar(kind, rturn)
+        if kind == "reedsshepp":
+            NN = mp.MetricNN(V, SS.dist, V[0])
+            NN.handle()
+            t_nn, nnz = timed(lambda: NN.build_table(r), reps=2)
+            table, evals = NN.table, 1
+        else:
+            NN = mp.QuasiMetricNN(V, SS.dist, V[0])
+            NN.handle()
+            t_nn, (nF, nnz) = timed(lambda: NN.build_tables(r), reps=2)
+            table, evals = NN.tableB, 2
+        ph = [lib.mpb200_last_ms_of(_lib.OP_TABLE, k) for k in range(3)]
+        cand = int(NN_candidates(lib, NN))
+        t_e, (_, checks) = timed(lambda: NN.car_edges_free(CC, SS, fetch=False), reps=2)
+        t_cpu, ref = timed(lambda: car.inball(V, r, kind == "reedsshepp", q0=0, q1=q))
+        t_cpu_e, _ = timed(lambda: car.edges_free_csc(orc.Obstacles2D(fx.ISRR_2H), So, V, ref[0], ref[1], 0))
+        parity = table_parity(mp, NN, table, ref, 0, q)
+        out[kind] = dict(nnz=int(nnz), mean_degree=nnz / N, candidate_pairs=cand, table_gpu_s=t_nn, cost_kernel_ms=ph[1],
+                         steer_evaluations_per_s=evals * cand / (ph[1] / 1e3) if ph[1] > 0 else None,
+                         nn_queries_per_s=evals * N / t_nn, edges_gpu_s=t_e, edges_per_s=nnz / t_e, segment_checks=int(checks),
+                         parity_checked=parity,
+                         cpu_baseline=dict(value=q / t_cpu, unit="queries/s", cores=1, kind="port",
+                                           sample="oracle/cars.c inball on %d of %d columns (one direction); edges %.3g/s"
+                                                  % (q, N, len(ref[1]) / max(t_cpu_e, 1e-9))))
+        NN.close()
+    out.update(metric="nn_queries_per_sec", value=out["reedsshepp"]["nn_queries_per_s"], unit="queries/s")
+    return out
+
+
+def NN_candidates(lib, NN):
+    """entries of the (x, y) candidate table behind the last car build = pairs the cost kernel evaluated"""
+    import ctypes
+    n = ctypes.c_int64(0)
+    lib.mpb200_car_last_candidates(NN.handle(), ctypes.byref(n))
+    return n.value
+
+
+def kn(mp, orc, fx, args):
+    """k-nearest connections on C2's sample set: k from fmt.jl:6, r-ball table grown until every column
+    holds k entries, k-selection, mutual neighbourhoods (device-resident; the host fetch is not timed)."""
+    import math
+    from mpb200 import nearneighbors as nnm
+    N = int(1_000_000 * args.scale)
+    V = fx.uniform_samples(N, 2, 20240602)
+    k = min(int(math.ceil(4 * (math.e / 2) * math.log(N))), N - 1)
+    NN = mp.MetricNN(V)
+    NN.handle()
+    lib = mp.load()
+    global SYNC
+    SYNC = lib.mpb200_synchronize
+    NN.table_knn, NN.table_mknn = nnm.DeviceTable("knn"), nnm.DeviceTable("mknn")
+    state = {}
+
+    def run():
+        r = nnm._knn_radius_guess(V, k)
+        rounds = 0
+        while True:
+            rounds += 1
+            NN.build_table(r)
+            if nnm._table_knn(NN.table, k, NN.table_knn) == 0:
+                break
+            r *= 1.3
+        nnm._table_union_transpose(NN.table_knn, NN.table_knn, NN.table_mknn)
+        state.update(r=r, rounds=rounds, nnz_ball=NN.table.nnz, nnz_mutual=NN.table_mknn.nnz)
+    t_gpu, _ = timed(run, reps=2)
+    q = 64
+    # oracle: brute force k-selection for q columns over all N samples
+    import time as _t
+    t0 = _t.perf_counter()
+    cols = []
+    for c in range(q):
+        d = np.sqrt((V[c, 0] - V[:, 0]) ** 2 + (V[c, 1] - V[:, 1]) ** 2)
+        cols.append(orc.knn_from_values(d, k, c))
+    t_cpu = _t.perf_counter() - t0
+    D = NN.fetch_table(NN.table_knn, "knn")
+    for c in range(q):
+        got = D.rowval[D.colptr[c] - 1:D.colptr[c + 1] - 1] - 1
+        if not np.array_equal(got, cols[c]):
+            raise RuntimeError("PARITY FAILURE: k-nearest column %d differs from the brute-force selection" % c)
+    out = dict(config="KNN", workload="k-nearest connections: C2's %d samples, k=%d (fmt.jl:6)" % (N, k), N=N, k=k,
+               gpu_s=t_gpu, nn_queries_per_s=N / t_gpu, metric="nn_queries_per_sec", value=N / t_gpu, unit="queries/s",
+               parity_checked=q, cpu_baseline=dict(value=q / t_cpu, unit="queries/s", cores=1, kind="port",
+                                                   sample="numpy brute-force selection on %d of %d columns" % (q, N)), **state)
+    NN.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--configs", default="C1,C3,C4,C5,F1")
+    ap.add_argument("--configs", default="C1,C3,C4,C5,F1,F4,KNN")
     ap.add_argument("--scale", type=float, default=1.0)
     args = ap.parse_args()
     import mpb200
     from oracle import oracle as orc
     import fixtures as fx
     mpb200.init(int(os.environ.get("LOCAL_RANK", "0")))
-    table = dict(C1=c1, C3=c3, C4=c4, C5=c5, F1=f1)
+    table = dict(C1=c1, C3=c3, C4=c4, C5=c5, F1=f1, F4=f4, KNN=kn)
     for name in args.configs.split(","):
         out = table[name](mpb200, orc, fx, args)
         print(json.dumps(out), flush=True)

@@ -240,6 +240,9 @@ int mpb200_lq_motions_free(const mpb200_lq *lq, double r, const double *v_aos, c
  * (setup_steering sets it to r).  s must hold d = 3 states; the query range of s is honoured. */
 int mpb200_car_inball_build(mpb200_samples *s, int32_t kind, double turning_radius, double r, double chopval,
                             mpb200_table **tableF, mpb200_table **tableB, int64_t *nnzF, int64_t *nnzB);
+/* entries of the (x, y) candidate table behind the last mpb200_car_inball_build on s = pairs whose exact metric was
+ * evaluated (per direction); measurement aid */
+int mpb200_car_last_candidates(const mpb200_samples *s, int64_t *pairs);
 /* (cost, steering_control) for n explicit pairs: segments = n x 5 x (duration, signed speed, signed curvature),
  * nseg[i] of them valid (3 for Dubins, 3..5 for Reeds-Shepp) */
 int mpb200_car_steer(int32_t kind, double turning_radius, double speed, const double *v_aos, const double *w_aos,

@@ -100,6 +100,7 @@ SIGNATURES = {
     "mpb200_table_write_floor": (ctypes.c_int, [c_vp, P(c_dbl)]),
     "mpb200_pipe_peak": (ctypes.c_int, [ctypes.c_int, P(c_dbl)]),
     "mpb200_car_inball_build": (ctypes.c_int, [c_vp, ctypes.c_int32, c_dbl, c_dbl, c_dbl, P(c_vp), P(c_vp), P(c_i64), P(c_i64)]),
+    "mpb200_car_last_candidates": (ctypes.c_int, [c_vp, P(c_i64)]),
     "mpb200_car_steer": (ctypes.c_int, [ctypes.c_int32, c_dbl, c_dbl, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "mpb200_car_edges_free": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int32, c_dbl, c_dbl, c_vp, P(SpaceDesc), c_vp, P(c_i64)]),
     "mpb200_car_motions_free": (ctypes.c_int, [ctypes.c_int32, c_dbl, c_dbl, c_vp, c_vp, c_i64, c_vp, P(SpaceDesc), c_vp, P(c_i64)]),

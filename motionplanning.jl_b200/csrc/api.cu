@@ -1061,6 +1061,11 @@ int mpb200_car_inball_build(mpb200_samples *s, int32_t kind, double turning_radi
     if (nnzB) *nnzB = tB ? tB->nnz : 0;
     return MPB200_OK;
 }
+int mpb200_car_last_candidates(const mpb200_samples *s, int64_t *pairs) {
+    MPB_CHECK_ARG(s != nullptr && pairs != nullptr, "NULL argument");
+    *pairs = s->shadow_cand ? s->shadow_cand->nnz : 0;
+    return MPB200_OK;
+}
 int mpb200_car_steer(int32_t kind, double turning_radius, double speed, const double *v, const double *w, int64_t n,
                      double *cost, int32_t *nseg, double *segments) {
     MPB_REQUIRE_INIT();

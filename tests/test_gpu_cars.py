@@ -157,3 +157,23 @@ def test_fmt_over_a_car_space_matches_the_oracle(gpu, orc, kind, edge_checks):
     assert cost >= math.hypot(0.8, 0.8)
     assert mp.is_free_path(V[np.asarray(ref["path"]) - 1], CC, SS)
     P.V.close()
+
+
+def test_degenerate_sample_sets_and_argument_errors(gpu, orc):
+    mp = gpu
+    SS = _space(mp, "dubins", 0.1)
+    car = orc.SimpleCar("dubins", 0.1)
+    for V in (np.zeros((1, 3)), np.array([[0.2, 0.2, 0.0], [0.25, 0.2, 0.0]]), np.array([[0.5, 0.5, 1.0]] * 3)):
+        NN = mp.QuasiMetricNN(V, SS.dist, V[0])
+        cF, cB = NN.precompute(0.3)
+        assert _same(cF.D, car.inball(V, 0.3, True)) and _same(cB.D, car.inball(V, 0.3, False))
+        NN.close()
+    bad = mp.DubinsQuasiMetricSpace(-1.0)
+    NN = mp.QuasiMetricNN(np.zeros((4, 3)), bad.dist)
+    with pytest.raises(mp.MPB200Error, match="turning radius"):
+        NN.precompute(0.1)
+    NN.close()
+    NN2 = mp.QuasiMetricNN(np.zeros((4, 2)), SS.dist)
+    with pytest.raises(mp.MPB200Error, match="SE2"):
+        NN2.precompute(0.1)
+    NN2.close()
