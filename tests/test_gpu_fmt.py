@@ -78,8 +78,12 @@ def test_fmt_sample_free_and_failure_modes(gpu, orc):
     # infeasible start -> :failed, cost Inf (fmt.jl:24-29)
     P2 = mp.MPProblem(SS, [0.08, 0.43], mp.PointGoal([0.9, 0.9]), CC)
     assert mp.fmtstar(P2, 100) == float("inf") and P2.status == "failed"
-    with pytest.raises(NotImplementedError):                                     # :K is undefined in the reference too
-        mp.fmtstar(P, connections="K")
+    with pytest.raises(ValueError, match="radial"):                              # fmt.jl:20
+        mp.fmtstar(P, connections="X")
+    # :K (undefined in the reference) follows the specification of csrc/knn.cu: it solves the same problem
+    P3 = mp.MPProblem(SS, [0.1, 0.1], mp.BallGoal([0.9, 0.9], 0.05), CC)
+    status3, cost3, _ = mp.fmtstar(P3, 2000, rm=1.2, ensure_goal_ct=3, seed=5, connections="K")
+    assert status3 == "solved" and 1.0 < cost3 < 2.2 and P3.solution.metadata["k"] >= 1
 
 
 def test_fmt_double_integrator_matches_oracle(gpu, orc):
