@@ -26,19 +26,29 @@ constexpr double kPi = 3.141592653589793;
 constexpr double kTwoPi = 6.283185307179586;
 constexpr double kInf = __builtin_huge_val();
 
-// Julia's mod(x, 2pi): exact remainder with the sign of the divisor
+// Julia's mod(x, 2pi): exact remainder with the sign of the divisor.  The quotient comes from a multiplication by
+// 1/2pi (it can be off by one next to an integer); x - q*2pi is then exact in one fma (a multiple of ulp(2pi) below 8
+// whenever q is within one of the true quotient), and a wrong q is corrected and the remainder recomputed, so the
+// result equals fmod(x, 2pi) bit for bit (the oracle calls libm's fmod).
 __device__ __forceinline__ double mod2pi(double x) {
-    const double q = trunc(x / kTwoPi);
-    double r = __fma_rn(-q, kTwoPi, x);  // exact: x - q*2pi is a multiple of ulp(2pi) below 8
-    if (x >= 0.0) { if (r < 0.0) r += kTwoPi; }   // the rounded quotient can only be one too large
-    else { if (r > 0.0) r -= kTwoPi; }
+    double q = trunc(x * 0.15915494309189535);
+    double r = __fma_rn(-q, kTwoPi, x);
+    if (x >= 0.0) {
+        if (r < 0.0) { q -= 1.0; r = __fma_rn(-q, kTwoPi, x); }
+        else if (r >= kTwoPi) { q += 1.0; r = __fma_rn(-q, kTwoPi, x); }
+    } else {
+        if (r > 0.0) { q += 1.0; r = __fma_rn(-q, kTwoPi, x); }
+        else if (r <= -kTwoPi) { q -= 1.0; r = __fma_rn(-q, kTwoPi, x); }
+    }
     if (r == 0.0) return 0.0;
     return r < 0.0 ? r + kTwoPi : r;
 }
 
 __device__ __noinline__ void sincos_(double x, double *sn, double *cs) {
-    const double kf = floor(x * 0.6366197723675814 + 0.5);
-    const double th = ((x - kf * 1.5707963267341256) - kf * 6.077100506303966e-11) - kf * 2.0222662487111665e-21;
+    // on |x|, reflected: sin is exactly odd and cos exactly even (evaluations at -t are shared with those at t)
+    const double ax = fabs(x);
+    const double kf = floor(ax * 0.6366197723675814 + 0.5);
+    const double th = ((ax - kf * 1.5707963267341256) - kf * 6.077100506303966e-11) - kf * 2.0222662487111665e-21;
     const double t2 = th * th;
     double ps = -1.0 / 355687428096000.0;
     ps = ps * t2 + 1.0 / 1307674368000.0;
@@ -64,6 +74,7 @@ __device__ __noinline__ void sincos_(double x, double *sn, double *cs) {
     else if (q == 1) { *sn = c; *cs = -s; }
     else if (q == 2) { *sn = -s; *cs = -c; }
     else { *sn = -c; *cs = s; }
+    if (x < 0.0) *sn = -*sn;
 }
 __device__ __forceinline__ double sin_(double x) { double s, c; sincos_(x, &s, &c); return s; }
 __device__ __forceinline__ double cos_(double x) { double s, c; sincos_(x, &s, &c); return c; }
@@ -191,21 +202,20 @@ __device__ double dubins(const double *s1, const double *s2, double r, double s,
 // ---- Reeds-Shepp (simplecars.jl:215-523) -------------------------------------------------------------------------
 __device__ __forceinline__ void Rpolar(double x, double y, double *r, double *th) { *r = sqrt(x * x + y * y); *th = atan2_(y, x); }
 __device__ __forceinline__ double Mwrap(double t) { const double m = mod2pi(t); return m > kPi ? m - kTwoPi : m; }
-__device__ double Tau(double u, double v, double E, double N) {
+// Tau(u, v, E, N) for v = +-u, given (su, cu) = sincos(u): cos(v) == cos(u) exactly, sin / cos of delta in one call
+__device__ double Tau(double u, double v, double E, double N, double su, double cu) {
     const double delta = Mwrap(u - v);
-    const double A = sin_(u) - sin_(delta);
-    const double Bc = cos_(u) - cos_(delta) - 1.0;
-    double r, th;
-    Rpolar(E * A + N * Bc, N * A - E * Bc, &r, &th);
-    const double t = 2.0 * cos_(delta) - 2.0 * cos_(v) - 2.0 * cos_(u) + 3.0;
+    double sd, cd;
+    sincos_(delta, &sd, &cd);
+    const double A = su - sd;
+    const double Bc = cu - cd - 1.0;
+    const double th = atan2_(N * A - E * Bc, E * A + N * Bc);
+    const double t = 2.0 * cd - 2.0 * cu - 2.0 * cu + 3.0;
     return t < 0.0 ? Mwrap(th + kPi) : Mwrap(th);
 }
-__device__ __forceinline__ double Omega(double u, double v, double E, double N, double t) { return Mwrap(Tau(u, v, E, N) - u + v - t); }
 
 // family: 0 LpSpLp 1 LpSpRp 2 LpRmLp 3 LpRmLm 4 LpRpuLmuRm 5 LpRmuLmuRp 6 LpRmSmLm 7 LpRmSmRm 8 LpRmSmLmRp
-__device__ bool rs_family(int fam, double tx, double ty, double tt, Best &B) {
-    double stt, ctt;
-    sincos_(tt, &stt, &ctt);
+__device__ bool rs_family(int fam, double tx, double ty, double tt, double stt, double ctt, Best &B) {
     double cnew;
     Seg p0, p1, p2, p3 = mkseg(0, 0.0), p4 = mkseg(0, 0.0);
     int l;
@@ -241,8 +251,11 @@ __device__ bool rs_family(int fam, double tx, double ty, double tt, Best &B) {
         const double p = (2.0 + sqrt(E * E + N * N)) / 4.0;
         if (p < 0.0 || p > 1.0) return false;
         const double u = acos_(p);
-        const double t = mod2pi(Tau(u, -u, E, N));
-        const double v = mod2pi(Omega(u, -u, E, N, tt)) - kTwoPi;
+        double su, cu;
+        sincos_(u, &su, &cu);
+        const double tau = Tau(u, -u, E, N, su, cu);   // Omega(u, v, E, N, t) = M(Tau(u, v, E, N) - u + v - t)
+        const double t = mod2pi(tau);
+        const double v = mod2pi(Mwrap(tau - u + (-u) - tt)) - kTwoPi;
         cnew = t + 2.0 * u - v;
         p0 = mkseg(1, t); p1 = mkseg(-1, u); p2 = mkseg(1, -u); p3 = mkseg(-1, v); l = 4;
     } else if (fam == 5) {
@@ -250,8 +263,11 @@ __device__ bool rs_family(int fam, double tx, double ty, double tt, Best &B) {
         const double p = (20.0 - E * E - N * N) / 16.0;
         if (p < 0.0 || p > 1.0) return false;
         const double u = -acos_(p);
-        const double t = mod2pi(Tau(u, u, E, N));
-        const double v = mod2pi(Omega(u, u, E, N, tt));
+        double su, cu;
+        sincos_(u, &su, &cu);
+        const double tau = Tau(u, u, E, N, su, cu);
+        const double t = mod2pi(tau);
+        const double v = mod2pi(Mwrap(tau - u + u - tt));
         cnew = t - 2.0 * u + v;
         p0 = mkseg(1, t); p1 = mkseg(-1, u); p2 = mkseg(1, u); p3 = mkseg(-1, v); l = 4;
     } else if (fam == 6) {
@@ -302,6 +318,7 @@ __device__ bool rs_family(int fam, double tx, double ty, double tt, Best &B) {
 
 // the sweep of simplecars.jl:283-339: per family the transformed targets tried, as a bit mask over
 // (0 target, 1 t, 2 r, 3 tr, 4 b, 5 bt, 6 br, 7 btr), in ascending order = the reference's order
+__device__ double rs_cost_raw(const double *s1, const double *s2, double r, int *key);
 __device__ double reedsshepp(const double *s1, const double *s2, double r, double s, Best &B) {
     const double dx = (s2[0] - s1[0]) / r, dy = (s2[1] - s1[1]) / r;
     double ct, st;
@@ -312,18 +329,19 @@ __device__ double reedsshepp(const double *s1, const double *s2, double r, doubl
     const double xb = x0 * cb + y0 * sb, yb = x0 * sb - y0 * cb;
     B.c = kInf; B.l = 0;
     for (int i = 0; i < 5; ++i) B.p[i] = mkseg(0, 0.0);
-    int post = 0;
-    for (int fam = 0; fam < 9; ++fam) {
-        const unsigned mask = (fam == 2) ? 0x05u : (fam == 3 || fam == 6 || fam == 7) ? 0xffu : 0x0fu;
-        for (int tr = 0; tr < 8; ++tr) {
-            if (!((mask >> tr) & 1u)) continue;
-            const double bx = (tr & 4) ? xb : x0, by = (tr & 4) ? yb : y0;
-            // timeflip: (-x, y, -th); reflect: (x, -y, -th)
-            const double tx = (tr & 1) ? -bx : bx;
-            const double ty = (tr & 2) ? -by : by;
-            const double tt = ((tr & 1) != 0) != ((tr & 2) != 0) ? -t0 : t0;
-            if (rs_family(fam, tx, ty, tt, B)) post = tr;
-        }
+    // the sweep of simplecars.jl:283-339 keeps the first evaluation that attains the minimum; rs_cost_raw finds it
+    // (cost + position in the sweep) with the shared-subexpression pass, and only that one is rebuilt with its control
+    int key;
+    rs_cost_raw(s1, s2, r, &key);
+    const int fam = key >> 3, post = key & 7;
+    {
+        const int tr = post;
+        const double bx = (tr & 4) ? xb : x0, by = (tr & 4) ? yb : y0;
+        // timeflip: (-x, y, -th); reflect: (x, -y, -th)
+        const double tx = (tr & 1) ? -bx : bx;
+        const double ty = (tr & 2) ? -by : by;
+        const bool neg = ((tr & 1) != 0) != ((tr & 2) != 0);
+        rs_family(fam, tx, ty, neg ? -t0 : t0, neg ? -sb : sb, cb, B);
     }
     scale_segments(B, r, s);
     const int l = B.l;
@@ -334,6 +352,136 @@ __device__ double reedsshepp(const double *s1, const double *s2, double r, doubl
     return B.c * r;
 }
 
+// ---- cost only (the table build needs no control): the same candidate lengths, evaluated target by target so that
+// everything the families of one transformed target have in common -- sincos(tt), the polar form of (E, N), the
+// acos of the C|C|C families -- is computed once.  The minimum of a set does not depend on the order it is taken in,
+// so the result is the cost of reedsshepp() bit for bit.
+// *key = 8 * family + target of the FIRST evaluation (in the reference's family-major order) that attains the
+// minimum: the one whose control reedsshepp() returns
+__device__ double rs_cost_raw(const double *s1, const double *s2, double r, int *key) {
+    const double dx = (s2[0] - s1[0]) / r, dy = (s2[1] - s1[1]) / r;
+    double ct, st;
+    sincos_(s1[2], &st, &ct);
+    const double x0 = dx * ct + dy * st, y0 = -dx * st + dy * ct, t0 = mod2pi(s2[2] - s1[2]);
+    double sb, cb;
+    sincos_(t0, &sb, &cb);
+    const double xb = x0 * cb + y0 * sb, yb = x0 * sb - y0 * cb;
+    double best = kInf;
+    int best_key = 1 << 30;
+#define MPB_TAKE(fam_, c_) do { const double c__ = (c_); const int k__ = 8 * (fam_) + tr;                \
+        if (!(best <= c__) || (c__ == best && k__ < best_key)) { best = c__; best_key = k__; } } while (0)
+#pragma unroll 1
+    for (int tr = 0; tr < 8; ++tr) {
+        const double bx = (tr & 4) ? xb : x0, by = (tr & 4) ? yb : y0;
+        const double tx = (tr & 1) ? -bx : bx;
+        const double ty = (tr & 2) ? -by : by;
+        const bool neg = ((tr & 1) != 0) != ((tr & 2) != 0);
+        const double tt = neg ? -t0 : t0, stt = neg ? -sb : sb, ctt = cb;
+        const bool four = tr < 4;  // families tried on the first four targets only
+        if (four) {
+            {   // LpSpLp
+                double rr, th;
+                Rpolar(tx - stt, ty - 1.0 + ctt, &rr, &th);
+                const double t = mod2pi(th), v = mod2pi(tt - t);
+                MPB_TAKE(0, t + rr + v);
+            }
+            {   // LpSpRp
+                double rr, th;
+                Rpolar(tx + stt, ty - 1.0 - ctt, &rr, &th);
+                if (!(rr * rr < 4.0)) {
+                    const double u = sqrt(rr * rr - 4.0);
+                    const double th1 = atan2_(2.0, u);
+                    const double t = mod2pi(th + th1), v = mod2pi(t - tt);
+                    MPB_TAKE(1, t + u + v);
+                }
+            }
+        }
+        {   // E = tx - sin, N = ty + cos - 1: LpRmLp (targets 0, 2), LpRmLm, LpRmSmLm
+            const double E = tx - stt, N = ty + ctt - 1.0;
+            const double EN = E * E + N * N;
+            const double D = sqrt(EN), th = atan2_(N, E);
+            if (!(EN > 16.0)) {
+                double u = acos_(1.0 - D * D / 8.0);
+                const double t = mod2pi(th - u / 2.0 + kPi);
+                const double vv = mod2pi(kPi - u / 2.0 - th + tt);
+                u = -u;
+                if (tr == 0 || tr == 2) MPB_TAKE(2, t - u + vv);
+                const double v3 = vv - kTwoPi;
+                MPB_TAKE(3, t - u - v3);
+            }
+            if (!(D < 2.0)) {
+                const double gamma = acos_(2.0 / D);
+                const double F = sqrt(D * D / 4.0 - 1.0);
+                const double t = mod2pi(kPi + th - gamma);
+                const double u = 2.0 - 2.0 * F;
+                if (!(u > 0.0)) {
+                    const double v = mod2pi(-3.0 * kPi / 2.0 + gamma + tt - th) - kTwoPi;
+                    MPB_TAKE(6, t + kPi / 2.0 - u - v);
+                }
+            }
+        }
+        {   // E = tx + sin, N = ty - cos - 1: LpRpuLmuRm, LpRmuLmuRp, LpRmSmLmRp (first four targets), LpRmSmRm (all)
+            const double E = tx + stt, N = ty - ctt - 1.0;
+            const double D = sqrt(E * E + N * N);
+            if (four) {
+                const double p = (2.0 + D) / 4.0;
+                if (!(p < 0.0 || p > 1.0)) {
+                    const double u = acos_(p);
+                    double su, cu;
+                    sincos_(u, &su, &cu);
+                    const double tau = Tau(u, -u, E, N, su, cu);
+                    const double t = mod2pi(tau);
+                    const double v = mod2pi(Mwrap(tau - u + (-u) - tt)) - kTwoPi;
+                    MPB_TAKE(4, t + 2.0 * u - v);
+                }
+                const double p2 = (20.0 - E * E - N * N) / 16.0;
+                if (!(p2 < 0.0 || p2 > 1.0)) {
+                    const double u = -acos_(p2);
+                    double su, cu;
+                    sincos_(u, &su, &cu);
+                    const double tau = Tau(u, u, E, N, su, cu);
+                    const double t = mod2pi(tau);
+                    const double v = mod2pi(Mwrap(tau - u + u - tt));
+                    MPB_TAKE(5, t - 2.0 * u + v);
+                }
+            }
+            if (!(D < 2.0)) {
+                const double beta = atan2_(N, E);
+                {
+                    const double t = mod2pi(beta + kPi / 2.0);
+                    const double u = 2.0 - D;
+                    if (!(u > 0.0)) {
+                        const double v = mod2pi(-kPi - tt + beta) - kTwoPi;
+                        MPB_TAKE(7, t + kPi / 2.0 - u - v);
+                    }
+                }
+                if (four) {
+                    const double gamma = acos_(2.0 / D);
+                    const double F = sqrt(D * D / 4.0 - 1.0);
+                    const double t = mod2pi(kPi + beta - gamma);
+                    const double u = 4.0 - 2.0 * F;
+                    if (!(u > 0.0)) {
+                        const double v = mod2pi(kPi + beta - tt - gamma);
+                        MPB_TAKE(8, t + kPi - u + v);
+                    }
+                }
+            }
+        }
+    }
+#undef MPB_TAKE
+    *key = best_key;
+    return best;
+}
+__device__ __forceinline__ double rs_cost(const double *s1, const double *s2, double r) {
+    int key;
+    return rs_cost_raw(s1, s2, r, &key) * r;
+}
+
+__device__ double dubins_cost(const double *s1, const double *s2, double r) {
+    Best B;
+    return dubins(s1, s2, r, 1.0, B);
+}
+
 __device__ __forceinline__ double steer(int kind, const double *v, const double *w, double rturn, double speed, Best &B) {
     return kind == MPB200_CAR_DUBINS ? dubins(v, w, rturn, speed, B) : reedsshepp(v, w, rturn, speed, B);
 }
@@ -341,19 +489,21 @@ __device__ __forceinline__ double steer(int kind, const double *v, const double 
 // evaluate(::ChoppedPreMetric, v, w) given the lower bound already computed (primitivetypes.jl:95-100)
 __device__ __forceinline__ double chopped(int kind, double lb, const double *v, const double *w, double rturn, double chopval) {
     if (lb > chopval) return kInf;
-    Best B;
-    const double d = steer(kind, v, w, rturn, 1.0, B);
+    const double d = kind == MPB200_CAR_DUBINS ? dubins_cost(v, w, rturn) : rs_cost(v, w, rturn);
     return d <= chopval ? d : kInf;
 }
 
-__device__ __forceinline__ void propagate(const double *v, const Seg &u, double *out) {
+// (s0, c0) = sincos(v[2])
+__device__ __forceinline__ void propagate(const double *v, const Seg &u, double s0, double c0, double *out) {
     const double dth = u.t * u.u1 * u.u2;
     if (fabs(dth) > 10.0 * 2.220446049250313e-16) {
-        out[0] = v[0] + (sin_(v[2] + dth) - sin_(v[2])) / u.u2;
-        out[1] = v[1] + (cos_(v[2]) - cos_(v[2] + dth)) / u.u2;
+        double s1, c1;
+        sincos_(v[2] + dth, &s1, &c1);
+        out[0] = v[0] + (s1 - s0) / u.u2;
+        out[1] = v[1] + (c0 - c1) / u.u2;
     } else {
-        out[0] = v[0] + u.t * u.u1 * cos_(v[2]);
-        out[1] = v[1] + u.t * u.u1 * sin_(v[2]);
+        out[0] = v[0] + u.t * u.u1 * c0;
+        out[1] = v[1] + u.t * u.u1 * s0;
     }
     out[2] = mod2pi(v[2] + dth);
 }
@@ -387,11 +537,14 @@ __device__ bool motion_free(int kind, double rturn, double speed, const SpaceDev
         prev[0] = cur[0]; prev[1] = cur[1]; prev[2] = cur[2];
         have_prev = true;
         const long long m = (long long)floor(u.t * u.u1 * u.u2 / thres);
+        double s0, c0;
+        sincos_(cur[2], &s0, &c0);
         for (long long i = 1; i <= m && i < 32; ++i) {
             const double ang = (double)i * thres;
-            double pt[3];
-            pt[0] = cur[0] + (sin_(cur[2] + ang) - sin_(cur[2])) / u.u2;
-            pt[1] = cur[1] + (cos_(cur[2]) - cos_(cur[2] + ang)) / u.u2;
+            double pt[3], sa, ca;
+            sincos_(cur[2] + ang, &sa, &ca);
+            pt[0] = cur[0] + (sa - s0) / u.u2;
+            pt[1] = cur[1] + (c0 - ca) / u.u2;
             pt[2] = mod2pi(cur[2] + ang);
             if (!in_state_space<3>(S, prev)) return false;
             *checks += 1;
@@ -399,7 +552,7 @@ __device__ bool motion_free(int kind, double rturn, double speed, const SpaceDev
             prev[0] = pt[0]; prev[1] = pt[1]; prev[2] = pt[2];
         }
         double nxt[3];
-        propagate(cur, u, nxt);
+        propagate(cur, u, s0, c0, nxt);
         cur[0] = nxt[0]; cur[1] = nxt[1]; cur[2] = nxt[2];
     }
     if (have_prev) {  // push!(wps, w)

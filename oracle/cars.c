@@ -36,11 +36,14 @@ double orc_mod2pi(double x)
     return r;
 }
 
-/* sin and cos: Cody-Waite reduction by pi/2 in three parts (|x| < 2^20), Taylor polynomials on [-pi/4, pi/4] */
+/* sin and cos: Cody-Waite reduction by pi/2 in three parts (|x| < 2^20), Taylor polynomials on [-pi/4, pi/4];
+ * sin(-x) == -sin(x) and cos(-x) == cos(x) bit for bit (the device code relies on it to share evaluations) */
 void orc_det_sincos(double x, double *sn, double *cs)
 {
-    double kf = floor(x * 0.6366197723675814 + 0.5);
-    double th = ((x - kf * 1.5707963267341256) - kf * 6.077100506303966e-11) - kf * 2.0222662487111665e-21;
+    /* computed on |x| and reflected, so that sin is exactly odd and cos exactly even */
+    double ax = fabs(x);
+    double kf = floor(ax * 0.6366197723675814 + 0.5);
+    double th = ((ax - kf * 1.5707963267341256) - kf * 6.077100506303966e-11) - kf * 2.0222662487111665e-21;
     double t2 = th * th;
     double ps = -1.0 / 355687428096000.0; /* -1/17! */
     ps = ps * t2 + 1.0 / 1307674368000.0;
@@ -66,6 +69,7 @@ void orc_det_sincos(double x, double *sn, double *cs)
     else if (q == 1) { *sn = c; *cs = -s; }
     else if (q == 2) { *sn = -s; *cs = -c; }
     else { *sn = -c; *cs = s; }
+    if (x < 0.0) *sn = -*sn;
 }
 double orc_det_sin(double x) { double s, c; orc_det_sincos(x, &s, &c); return s; }
 double orc_det_cos(double x) { double s, c; orc_det_sincos(x, &s, &c); return c; }

@@ -68,4 +68,16 @@ for _ in range(2):
 st = _lib.c_i64(0)
 _lib.check(lib.mpb200_xchg_view(x, None, None, None, None, ctypes.byref(st))); assert st.value == 0
 _lib.check(lib.mpb200_xchg_attach(None, NN.table.h)); _lib.check(lib.mpb200_xchg_destroy(x)); NN.close()
+# later in round 2: car spaces (steer, chopped tables both kinds, sharded range, edge + motion checks, both obstacle
+# kinds) and k-nearest connections (k-selection, mutual neighbourhoods)
+Vc = np.column_stack([rng.random(700), rng.random(700), rng.uniform(0, 2 * np.pi, 700)])
+Bc = mpb200.PointRobotNDBoxes([mpb200.BoxBounds(np.array([0.3, 0.3]), np.array([0.5, 0.6]))])
+for mk, cls in ((mpb200.ReedsSheppMetricSpace, mpb200.MetricNN), (mpb200.DubinsQuasiMetricSpace, mpb200.QuasiMetricNN)):
+    S3 = mk(0.05, 0.9)
+    mpb200.setup_steering(S3, 0.2)
+    Nc = cls(Vc, S3.dist, Vc[0]); Nc.precompute(0.2); Nc.car_edges_free(CC, S3); Nc.car_edges_free(Bc, S3)
+    Nc.set_query_range(100, 500); Nc.precompute(0.2); Nc.car_edges_free(CC, S3)
+    mpb200.car_steer_batch(S3, Vc[:64], Vc[64:128]); mpb200.car_motions_free(Vc[:64], Vc[64:128], CC, S3); Nc.close()
+Vk = rng.random((3000, 2)); Nk = mpb200.MetricNN(Vk); Nk.precompute_knn(12); Nk.edges_free(Nk.table_knn, CC, SS); Nk.close()
+Vk = rng.random((900, 6)); Nk = mpb200.MetricNN(Vk); Nk.precompute_knn(9); Nk.close()
 print("sanitize run complete")
