@@ -629,7 +629,10 @@ def main():
             "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": 1e3 * e2e_s, "steps": args.e2e_steps},
+                    "ms_per_step": 1e3 * e2e_s, "steps": args.e2e_steps,
+                    "note": "d2h_bytes_per_step = bytes delivered into the caller's Int64 / Float64 / BitVector arrays (the "
+                            "reference's formats); the Int64 row indices cross PCIe bit-packed (20 bits each at N = 1M) and "
+                            "are unpacked into the caller's array by host threads during the nzval transfer"},
             "roofline": {"kernel": "rball_fill<2>", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": fill_traffic(), "peak_kind": peak_kind,
                          "algorithmic_bytes_per_launch": alg_bytes,

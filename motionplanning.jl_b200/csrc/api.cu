@@ -504,28 +504,84 @@ int mpb200_table_device_view(const mpb200_table *t, void **colptr, void **rowval
 // ---- table fetch -----------------------------------------------------------------------------------------
 // The reference's table format (Int64 rowval + Float64 nzval, 16 bytes per stored neighbour) makes the fetch
 // PCIe-bound: 27.5M entries = 441 MB = 7.9 ms at 57 GB/s against 0.56 ms of kernels.  The row indices are sample
-// numbers < 2^31, so they cross the bus as int32 (narrowed on the device, into pinned staging, in chunks) and are
-// widened back to the caller's Int64 array by a few host threads WHILE the nzval transfer is still running:
-// 25% fewer bytes on the wire, the same bytes in the caller's arrays.
+// numbers <= N, so they cross the bus bit-packed -- B = the smallest multiple of 4 bits that holds N (20 bits for
+// N = 1M; eight indices fill exactly B/4 32-bit words) -- packed on the device into pinned staging in chunks, and are
+// unpacked into the caller's Int64 array by a few host threads WHILE the nzval transfer is still running:
+// fewer bytes on the wire (8 -> 2.5 bytes per index at N = 1M), the same bytes in the caller's arrays.
+}  // extern "C"
 namespace fetchd {
-__global__ void __launch_bounds__(256) narrow_rows_kernel(const int64_t *__restrict__ in, int64_t n, int32_t *__restrict__ out) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        out[i] = (int32_t)in[i];
+template <int BITS>
+__global__ void __launch_bounds__(256) pack_rows_kernel(const int64_t *__restrict__ in, int64_t n, int64_t groups,
+                                                        uint32_t *__restrict__ out) {
+    constexpr int W = BITS / 4;  // words per group of eight indices
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (int64_t)gridDim.x * blockDim.x) {
+        unsigned long long acc = 0;
+        int nb = 0, w = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int64_t e = 8 * g + i;
+            const unsigned long long v = e < n ? (unsigned long long)in[e] : 0ULL;
+            acc |= v << nb;
+            nb += BITS;
+            if (nb >= 32) {
+                out[g * W + w++] = (uint32_t)acc;
+                acc >>= 32;
+                nb -= 32;
+            }
+        }
+    }
+}
+// host side of the same format: groups [g0, g1) of `in` -> dst[8 g0 .. min(8 g1, n)), streaming stores
+template <int BITS>
+static void unpack_rows(const uint32_t *in, int64_t g0, int64_t g1, int64_t n, long long *dst) {
+    constexpr int W = BITS / 4;
+    constexpr unsigned long long mask = BITS == 32 ? 0xffffffffULL : ((1ULL << BITS) - 1ULL);
+    for (int64_t g = g0; g < g1; ++g) {
+        const uint32_t *p = in + g * W;
+        unsigned long long acc = 0;
+        int nb = 0, w = 0;
+        const int64_t base = 8 * g;
+        const int lim = (int)std::min<int64_t>(8, n - base);
+        for (int i = 0; i < lim; ++i) {
+            if (nb < BITS) {
+                acc |= (unsigned long long)p[w++] << nb;
+                nb += 32;
+            }
+            _mm_stream_si64(dst + base + i, (long long)(acc & mask));
+            acc >>= BITS;
+            nb -= BITS;
+        }
+    }
+    _mm_sfence();
 }
 constexpr int kFetchChunks = 32;
-void *g_pin = nullptr;  // pinned staging for the narrowed indices (library-owned, grows, reused)
+void *g_pin = nullptr;  // pinned staging for the packed indices (library-owned, grows, reused)
 size_t g_pin_cap = 0;
 cudaEvent_t g_fetch_ev[kFetchChunks] = {};
 }  // namespace fetchd
 using namespace fetchd;
 
+static int index_bits(int64_t max_value) {
+    int b = 1;
+    while (b < 32 && (int64_t(1) << b) <= max_value) ++b;
+    b = (b + 3) & ~3;
+    return b < 12 ? 12 : b;
+}
+
 static int fetch_rows_narrow(mpb200_table *t, int64_t *rowval, cudaStream_t st, std::vector<std::thread> *workers) {
     const int64_t nnz = t->nnz;
-    if (int rc = t->scratch.reserve(sizeof(int32_t) * (size_t)nnz)) return rc;
-    if (g_pin_cap < sizeof(int32_t) * (size_t)nnz) {
+    static const int env_bits = [] { const char *e = getenv("MPB200_FETCH_BITS"); return e ? atoi(e) : 0; }();
+    const int bits = (env_bits >= 12 && env_bits <= 32 && env_bits % 4 == 0) ? env_bits
+                     : (t->src_N > 0 ? index_bits(t->src_N) : 32);
+    if (t->src_N > 0 && bits < 32 && (int64_t(1) << bits) <= t->src_N) return 1;  // a forced width that cannot hold N
+    const int W = bits / 4;
+    const int64_t groups = ceil_div(nnz, 8);
+    const size_t bytes = sizeof(uint32_t) * (size_t)groups * (size_t)W;
+    if (int rc = t->scratch.reserve(bytes)) return rc;
+    if (g_pin_cap < bytes) {
         if (g_pin) cudaFreeHost(g_pin);
         g_pin = nullptr;
-        g_pin_cap = sizeof(int32_t) * (size_t)nnz + (sizeof(int32_t) * (size_t)nnz) / 8;
+        g_pin_cap = bytes + bytes / 8;
         if (cudaMallocHost(&g_pin, g_pin_cap) != cudaSuccess) {
             cudaGetLastError();
             g_pin = nullptr;
@@ -535,17 +591,29 @@ static int fetch_rows_narrow(mpb200_table *t, int64_t *rowval, cudaStream_t st, 
     }
     for (int k = 0; k < kFetchChunks; ++k)
         if (!g_fetch_ev[k]) MPB_CUDA(cudaEventCreateWithFlags(&g_fetch_ev[k], cudaEventDisableTiming));
-    int32_t *d32 = t->scratch.as<int32_t>();
-    int32_t *h32 = static_cast<int32_t *>(g_pin);
-    narrow_rows_kernel<<<ctx().sm_count * 8, 256, 0, st>>>(t->rowval.as<int64_t>(), nnz, d32);
+    uint32_t *d32 = t->scratch.as<uint32_t>();
+    uint32_t *h32 = static_cast<uint32_t *>(g_pin);
+    const unsigned grid = (unsigned)(ctx().sm_count * 8);
+    const int64_t *src = t->rowval.as<int64_t>();
+    switch (bits) {
+        case 12: pack_rows_kernel<12><<<grid, 256, 0, st>>>(src, nnz, groups, d32); break;
+        case 16: pack_rows_kernel<16><<<grid, 256, 0, st>>>(src, nnz, groups, d32); break;
+        case 20: pack_rows_kernel<20><<<grid, 256, 0, st>>>(src, nnz, groups, d32); break;
+        case 24: pack_rows_kernel<24><<<grid, 256, 0, st>>>(src, nnz, groups, d32); break;
+        case 28: pack_rows_kernel<28><<<grid, 256, 0, st>>>(src, nnz, groups, d32); break;
+        default: pack_rows_kernel<32><<<grid, 256, 0, st>>>(src, nnz, groups, d32); break;
+    }
     MPB_LAUNCHED();
-    const int64_t per = ceil_div(nnz, kFetchChunks);
+    const int64_t per = ceil_div(groups, kFetchChunks);  // groups per chunk
     for (int k = 0; k < kFetchChunks; ++k) {
-        const int64_t a = std::min<int64_t>(k * per, nnz), b = std::min<int64_t>(a + per, nnz);
-        if (b > a) MPB_CUDA(cudaMemcpyAsync(h32 + a, d32 + a, sizeof(int32_t) * (size_t)(b - a), cudaMemcpyDeviceToHost, st));
+        const int64_t a = std::min<int64_t>(k * per, groups), b = std::min<int64_t>(a + per, groups);
+        if (b > a)
+            MPB_CUDA(cudaMemcpyAsync(h32 + a * W, d32 + a * W, sizeof(uint32_t) * (size_t)((b - a) * W), cudaMemcpyDeviceToHost, st));
         MPB_CUDA(cudaEventRecord(g_fetch_ev[k], st));
     }
-    // widening threads: chunk k is converted as soon as its copy has landed (the nzval copy queued behind keeps the bus busy)
+    // unpacking threads: chunk k is converted as soon as its copy has landed (the nzval copy queued behind keeps the
+    // bus busy); streaming stores: the destination is written once and not read here (no read-for-ownership traffic
+    // on a memory bus that is taking the nzval DMA at the same time)
     const int device = ctx().device;
     static const int env_threads = [] { const char *e = getenv("MPB200_FETCH_THREADS"); return e ? atoi(e) : 0; }();
     const int nthreads = env_threads > 0 ? std::min(env_threads, kFetchChunks)
@@ -553,19 +621,24 @@ static int fetch_rows_narrow(mpb200_table *t, int64_t *rowval, cudaStream_t st, 
     for (int w = 0; w < nthreads; ++w)
         workers->emplace_back([=]() {
             cudaSetDevice(device);
+            long long *dst = reinterpret_cast<long long *>(rowval);
             for (int k = w; k < kFetchChunks; k += nthreads) {
                 cudaEventSynchronize(g_fetch_ev[k]);
-                const int64_t a = std::min<int64_t>(k * per, nnz), b = std::min<int64_t>(a + per, nnz);
-                // streaming stores: the destination is written once and not read here (no read-for-ownership traffic
-                // on a memory bus that is taking the nzval DMA at the same time)
-                long long *dst = reinterpret_cast<long long *>(rowval);
-                for (int64_t i = a; i < b; ++i) _mm_stream_si64(dst + i, (long long)h32[i]);
-                _mm_sfence();
+                const int64_t a = std::min<int64_t>(k * per, groups), b = std::min<int64_t>(a + per, groups);
+                switch (bits) {
+                    case 12: unpack_rows<12>(h32, a, b, nnz, dst); break;
+                    case 16: unpack_rows<16>(h32, a, b, nnz, dst); break;
+                    case 20: unpack_rows<20>(h32, a, b, nnz, dst); break;
+                    case 24: unpack_rows<24>(h32, a, b, nnz, dst); break;
+                    case 28: unpack_rows<28>(h32, a, b, nnz, dst); break;
+                    default: unpack_rows<32>(h32, a, b, nnz, dst); break;
+                }
             }
         });
     return 0;
 }
 
+extern "C" {
 int mpb200_table_fetch(const mpb200_table *t_, int64_t *colptr, int64_t *rowval, double *nzval) {
     MPB_REQUIRE_INIT();
     MPB_CHECK_ARG(t_ != nullptr, "table handle is NULL");

@@ -241,3 +241,22 @@ def test_box_edge_validity_shortcuts_next_to_faces(gpu, orc, d, boxes):
     exp, cnt = orc.edges_free_csc(R, SSo, V, D.colptr, D.rowval)
     assert np.array_equal(unpack_bits(bits, D.nnz), exp.astype(bool)) and checks == cnt and D.nnz > 1000
     NN.close()
+
+
+@pytest.mark.parametrize("N,d,r", [(3000, 2, 2.0), (60000, 2, 0.02), (1_200_000, 2, 0.0011), (40000, 3, 0.06)])
+def test_table_fetch_bit_packed_indices_round_trip(gpu, N, d, r):
+    """mpb200_table_fetch sends the row indices bit-packed (12 / 16 / 20 / 24 ... bits by sample count) and unpacks them
+    on the host: the caller's Int64 array must equal the device array, entry for entry, at every width and for entry
+    counts that are not a multiple of the packing group or the chunking"""
+    mp = gpu
+    from mpb200 import sharding
+    V = fx.uniform_samples(N, d, 4242 + N)
+    NN = mp.MetricNN(V)
+    D = NN.precompute(r).D
+    assert D.nnz >= 1 << 20                       # large enough to take the packed path
+    cp, rv, nz, _ = sharding.table_device_tensors(NN.table)
+    assert np.array_equal(D.rowval, rv.cpu().numpy())
+    assert np.array_equal(D.colptr, cp.cpu().numpy())
+    assert D.nzval.tobytes() == nz.cpu().numpy().tobytes()
+    assert D.rowval.min() >= 1 and D.rowval.max() <= N
+    NN.close()
