@@ -616,8 +616,11 @@ static int fetch_rows_narrow(mpb200_table *t, int64_t *rowval, cudaStream_t st, 
     // on a memory bus that is taking the nzval DMA at the same time)
     const int device = ctx().device;
     static const int env_threads = [] { const char *e = getenv("MPB200_FETCH_THREADS"); return e ? atoi(e) : 0; }();
+    // default: up to 8 threads, but no more than this process's share of the host cores when several ranks share the
+    // box (torchrun exports LOCAL_WORLD_SIZE): oversubscribed unpacking threads cost more than they give
+    static const unsigned local_world = [] { const char *e = getenv("LOCAL_WORLD_SIZE"); const int v = e ? atoi(e) : 1; return (unsigned)(v > 0 ? v : 1); }();
     const int nthreads = env_threads > 0 ? std::min(env_threads, kFetchChunks)
-                                         : (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+                                         : (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency() / local_world));
     for (int w = 0; w < nthreads; ++w)
         workers->emplace_back([=]() {
             cudaSetDevice(device);
