@@ -11,7 +11,6 @@ The neighbour iteration order (ascending index), findmin's first-minimum tie-bre
 "collision_checks" metadata (lookups actually consumed, one per segment test the lazy reference
 would have run) are preserved.
 """
-import heapq
 import math
 import time
 
@@ -22,6 +21,76 @@ from .simplecars import is_car_metric
 from .nearneighbors import MetricNN
 from .problems import MPSolution, goal_mask, sample_free
 from .statespaces import Euclidean, states_free, volume
+
+
+class PriorityQueue:
+    """Collections.PriorityQueue of Julia 0.5 (base/collections.jl; the reference uses it at fmt.jl:51,78,86): a binary
+    min-heap of key => priority pairs in an array with an index dictionary.  Restated -- not heapq with (cost, x)
+    tuples -- because the order in which EQUAL priorities leave the queue is a property of this particular heap
+    (percolate_up stops at a parent that is not strictly larger; percolate_down prefers the left child unless the right
+    one is strictly smaller), and FMT*'s expansion order, hence its tree, depends on it when costs tie (lattices)."""
+
+    def __init__(self):
+        self.xs = []          # (key, priority)
+        self.index = {}       # key -> 1-based position
+
+    def __len__(self):
+        return len(self.xs)
+
+    def _up(self, i):
+        xs = self.xs
+        x = xs[i - 1]
+        while i > 1:
+            j = i >> 1
+            if x[1] < xs[j - 1][1]:
+                self.index[xs[j - 1][0]] = i
+                xs[i - 1] = xs[j - 1]
+                i = j
+            else:
+                break
+        self.index[x[0]] = i
+        xs[i - 1] = x
+
+    def _down(self, i):
+        xs = self.xs
+        n = len(xs)
+        x = xs[i - 1]
+        while 2 * i <= n:
+            l, r = 2 * i, 2 * i + 1
+            j = l if (r > n or xs[l - 1][1] < xs[r - 1][1]) else r
+            if xs[j - 1][1] < x[1]:
+                self.index[xs[j - 1][0]] = i
+                xs[i - 1] = xs[j - 1]
+                i = j
+            else:
+                break
+        self.index[x[0]] = i
+        xs[i - 1] = x
+
+    def __setitem__(self, key, value):
+        """pq[key] = value: enqueue!, or re-prioritise an existing key"""
+        if key in self.index:
+            i = self.index[key]
+            old = self.xs[i - 1][1]
+            self.xs[i - 1] = (key, value)
+            if old < value:
+                self._down(i)
+            else:
+                self._up(i)
+        else:
+            self.xs.append((key, value))
+            self.index[key] = len(self.xs)
+            self._up(len(self.xs))
+
+    def dequeue(self):
+        x = self.xs[0]
+        y = self.xs.pop()
+        if self.xs:
+            self.xs[0] = y
+            self.index[y[0]] = 1
+            self._down(1)
+        del self.index[x[0]]
+        return x[0]
 
 
 def fmt_radius(N, d, rm, free_volume_ub):
@@ -130,7 +199,7 @@ def fmtstar(P, N=None, rm=1.0, connections="R", r=0.0, ensure_goal_ct=1, init_id
         raise RuntimeError("P.V[init_idx] must be the init state (fmt.jl:48-66)")
     Wm[init_idx - 1] = False
     H[init_idx - 1] = True
-    heap = []
+    heap = PriorityQueue()                               # HHeap (fmt.jl:51); init_idx is dequeued at once (:67)
     z = init_idx
     fcp, frv, fnz = DF.colptr, DF.rowval, DF.nzval
     bcp, brv, bnz = DB.colptr, DB.rowval, DB.nzval
@@ -168,14 +237,14 @@ def fmtstar(P, N=None, rm=1.0, connections="R", r=0.0, ensure_goal_ct=1, init_id
             if (ok[t_i] if lazy else evalid[e]):             # is_free_motion(V[y_min], V[x], CC, SS)
                 A[x - 1] = y_min
                 C[x - 1] = c_min
-                heapq.heappush(heap, (c_min, x))
+                heap[x] = c_min                            # HHeap[x] = c_min (fmt.jl:78)
                 H_new.append(x)
                 Wm[x - 1] = False
         if H_new:
             H[np.asarray(H_new) - 1] = True
         H[z - 1] = False
-        if heap:
-            _, z = heapq.heappop(heap)
+        if len(heap):
+            z = heap.dequeue()
         else:
             break
 

@@ -1,9 +1,48 @@
 """Test infrastructure: FMT* (fmt.jl:4-119) restated over the ORACLE's lazy predicates -- per-vertex
 r-ball queries (cached on first touch, nearneighbors.jl:129-135), per-candidate lazy edge checks
 (fmt.jl:75) -- written independently of the product's planner."""
-import heapq
-
 import numpy as np
+
+
+class JuliaHeap:
+    """Julia 0.5 Collections.PriorityQueue semantics (binary heap, strict comparisons when percolating), written for the
+    tests independently of the product's class: equal priorities leave in the order THIS heap shape gives them."""
+
+    def __init__(self):
+        self.a = [None]          # 1-based: a[i] = [priority, key]
+
+    def empty(self):
+        return len(self.a) == 1
+
+    def push(self, key, pr):
+        a = self.a
+        a.append([pr, key])
+        i = len(a) - 1
+        item = a[i]
+        while i > 1 and item[0] < a[i // 2][0]:
+            a[i] = a[i // 2]
+            i //= 2
+        a[i] = item
+
+    def pop(self):
+        a = self.a
+        top = a[1]
+        last = a.pop()
+        n = len(a) - 1
+        if n >= 1:
+            i = 1
+            while True:
+                l, r = 2 * i, 2 * i + 1
+                if l > n:
+                    break
+                j = r if (r <= n and not (a[l][0] < a[r][0])) else l
+                if a[j][0] < last[0]:
+                    a[i] = a[j]
+                    i = j
+                else:
+                    break
+            a[i] = last
+        return top[1]
 
 
 def fmt_oracle(V, is_goal, neighborsF, neighborsB, point_free, edge_free, checkpts=True):
@@ -17,7 +56,7 @@ def fmt_oracle(V, is_goal, neighborsF, neighborsB, point_free, edge_free, checkp
     C = np.zeros(N)
     W[0] = False
     H[0] = True
-    heap = []
+    heap = JuliaHeap()
     z = 1
     checks = 0
     while not is_goal[z - 1]:
@@ -38,14 +77,14 @@ def fmt_oracle(V, is_goal, neighborsF, neighborsB, point_free, edge_free, checkp
             if ok:
                 A[x - 1] = y_min
                 C[x - 1] = c_min
-                heapq.heappush(heap, (c_min, x))
+                heap.push(x, c_min)
                 H_new.append(x)
                 W[x - 1] = False
         for x in H_new:
             H[x - 1] = True
         H[z - 1] = False
-        if heap:
-            _, z = heapq.heappop(heap)
+        if not heap.empty():
+            z = heap.pop()
         else:
             break
     sol = [z]

@@ -156,3 +156,32 @@ def test_fmt_lazy_wavefront_batched_checks_equal_the_precomputed_table(gpu, orc,
     # the lazy mode asked the device about far fewer edges than the table holds
     assert ml["collision_checks"] < mt["precomputed_edge_checks"]
     Pt.V.close(); Pl.V.close()
+
+
+def test_fmt_on_a_lattice_with_tied_costs_follows_the_reference_queue(gpu, orc):
+    """equal path costs are the rule on a lattice: the expansion order then depends on Collections.PriorityQueue's heap
+    shape (restated in planners.PriorityQueue and, independently, in tests/oracle_fmt.py)"""
+    mp = gpu
+    n = 24
+    g = np.stack(np.meshgrid(np.arange(n, dtype=np.float64), np.arange(n, dtype=np.float64), indexing="ij"), -1).reshape(-1, 2)
+    V = (g + 0.5) / n
+    O = orc.Obstacles2D(fx.ISRR_2H)
+    So = orc.StateSpace([0, 0], [1, 1])
+    SS = mp.UnitHypercube(2)
+    CC = mp.PointRobot2D(fx.product_shape(mp, fx.ISRR_2H))
+    r = 1.6 / n
+    goal = V[-1].copy()
+    P = mp.MPProblem(SS, V[0], mp.PointGoal(goal), CC, V=mp.MetricNN(V, SS.dist, V[0]))
+    status, cost, _ = mp.fmtstar(P, r=r)
+    T = orc.KDTree(V).rball(r)
+    col = lambda v: (T[1][T[0][v - 1] - 1:T[0][v] - 1], T[2][T[0][v - 1] - 1:T[0][v] - 1])
+
+    def edge(y0, x0):
+        ok, cnt = orc.motions_free_straight(O, So, V[y0:y0 + 1], V[x0:x0 + 1])
+        return bool(ok[0]), cnt
+
+    ref = fmt_oracle(V, np.all(V == goal, axis=1), col, col, lambda i: bool(orc.states_free(O, So, V[i:i + 1])[0]), edge)
+    assert ref["solved"] and status == "solved"
+    assert P.solution.metadata["path"] == ref["path"] and np.array_equal(P.solution.metadata["tree"], ref["tree"])
+    assert cost == ref["cost"] and P.solution.metadata["collision_checks"] == ref["checks"]
+    P.V.close()
