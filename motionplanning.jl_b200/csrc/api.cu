@@ -1100,7 +1100,8 @@ int mpb200_car_inball_build(mpb200_samples *s, int32_t kind, double turning_radi
     MPB_CHECK_ARG(s->d == 3, "car spaces need SE2 states (d = 3: x, y, theta)");
     MPB_CHECK_ARG(r >= 0 && r == r && chopval == chopval, "r must be a non-negative number");
     if (int rc = car_args(kind, turning_radius, 1.0)) return rc;
-    MPB_CHECK_ARG(tableB == nullptr || tableB != tableF, "tableF and tableB must be different handles");
+    MPB_CHECK_ARG(tableB == nullptr || (tableB != tableF && (*tableB == nullptr || *tableB != *tableF)),
+                  "tableF and tableB must be different handles");
     // the (x, y) columns as a 2-D sample set (the reference's KD-tree lower-bound structure), made once
     if (!s->shadow_xy) {
         mpb200_samples *xy = new (std::nothrow) mpb200_samples();
