@@ -33,12 +33,12 @@ constexpr double kInf = __builtin_huge_val();
 __device__ __forceinline__ double mod2pi(double x) {
     double q = trunc(x * 0.15915494309189535);
     double r = __fma_rn(-q, kTwoPi, x);
-    if (x >= 0.0) {
-        if (r < 0.0) { q -= 1.0; r = __fma_rn(-q, kTwoPi, x); }
-        else if (r >= kTwoPi) { q += 1.0; r = __fma_rn(-q, kTwoPi, x); }
-    } else {
-        if (r > 0.0) { q += 1.0; r = __fma_rn(-q, kTwoPi, x); }
-        else if (r <= -kTwoPi) { q -= 1.0; r = __fma_rn(-q, kTwoPi, x); }
+    const bool pos = x >= 0.0;
+    const bool down = pos ? (r < 0.0) : (r <= -kTwoPi);   // quotient one too large in magnitude towards +inf
+    const bool up = pos ? (r >= kTwoPi) : (r > 0.0);
+    if (down || up) {                                      // rare: x / 2pi rounded across an integer
+        q += up ? 1.0 : -1.0;
+        r = __fma_rn(-q, kTwoPi, x);
     }
     if (r == 0.0) return 0.0;
     return r < 0.0 ? r + kTwoPi : r;
@@ -70,11 +70,11 @@ __device__ __noinline__ void sincos_(double x, double *sn, double *cs) {
     pc = pc * t2 + 0.5;
     const double c = 1.0 - t2 * pc;
     const int q = (int)((long long)kf & 3);
-    if (q == 0) { *sn = s; *cs = c; }
-    else if (q == 1) { *sn = c; *cs = -s; }
-    else if (q == 2) { *sn = -s; *cs = -c; }
-    else { *sn = -c; *cs = s; }
-    if (x < 0.0) *sn = -*sn;
+    // quadrant by selects (no divergence): q = 0: (s, c)  1: (c, -s)  2: (-s, -c)  3: (-c, s)
+    const double a = (q & 1) ? c : s, b = (q & 1) ? s : c;
+    const double sq = (q & 2) ? -a : a;
+    *cs = ((q + 1) & 2) ? -b : b;
+    *sn = (x < 0.0) ? -sq : sq;
 }
 __device__ __forceinline__ double sin_(double x) { double s, c; sincos_(x, &s, &c); return s; }
 __device__ __forceinline__ double cos_(double x) { double s, c; sincos_(x, &s, &c); return c; }
@@ -101,10 +101,13 @@ __device__ __forceinline__ double atan01(double a) {
 }
 __device__ __noinline__ double atan2_(double y, double x) {
     const double ax = fabs(x), ay = fabs(y);
-    double ang;
-    if (ax == 0.0 && ay == 0.0) ang = 0.0;
-    else if (ay <= ax) ang = atan01(ay / ax);
-    else ang = 1.5707963267948966 - atan01(ax / ay);
+    // one evaluation of the [0, 1] kernel on min / max, then selects (the same values as the two-branch form)
+    const bool swap = !(ay <= ax);
+    const double num = swap ? ax : ay, den = swap ? ay : ax;
+    const bool zero = ax == 0.0 && ay == 0.0;
+    double ang = atan01(zero ? 0.0 : num / den);
+    if (swap) ang = 1.5707963267948966 - ang;
+    if (zero) ang = 0.0;
     if (signbit(x)) ang = kPi - ang;
     return signbit(y) ? -ang : ang;
 }
