@@ -15,8 +15,10 @@
  * (orc_det_sincos, orc_det_atan2, orc_det_acos: argument reduction + fixed polynomials in basic IEEE operations,
  * each within a few ulp of the true function -- tests/test_oracle_cars.py measures it against libm), so that the
  * two agree bit for bit; sqrt and mod are exact on both sides (mod2piF = Julia's mod(x, 2pi): fmod + sign fix).
- * The algebra around them is pinned by closed-form known answers and by consistency (the returned control,
- * propagated from v, must arrive at w; Reeds-Shepp <= Dubins; symmetry): tests/test_oracle_cars.py.
+ * The algebra around them is pinned by golden vectors (the reference's formulas re-run in 40-digit mpmath arithmetic,
+ * tests/golden/gen_cars_golden.py -> cars.json), an independent geometric Dubins construction, closed-form known
+ * answers and consistency (the returned control, propagated from v, must arrive at w; Reeds-Shepp <= Dubins;
+ * symmetry): tests/test_oracle_cars.py.
  */
 #include "mp_oracle.h"
 #include <math.h>

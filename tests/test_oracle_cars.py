@@ -212,3 +212,31 @@ def test_is_free_motion_waypoints_and_count():
     bump = orc.Obstacles2D(("circle", (0.6, 0.5), 0.02))
     assert car.is_free_motion(bump, S, [0.5, 0.6, 0.0], [0.5, 0.4, math.pi])[0]          # right U-turn: missed
     assert not car.is_free_motion(bump, S, [0.5, 0.4, 0.0], [0.5, 0.6, math.pi])[0]      # left U-turn: caught
+
+
+def test_golden_vectors_from_the_reference_formulas_in_40_digit_arithmetic():
+    """tests/golden/cars.json (gen_cars_golden.py: the reference's formulas and sweep order re-run in mpmath)"""
+    import json
+    import os
+    G = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "cars.json")))
+    rt = G["turning_radius"]
+    compared_controls = 0
+    for case in G["cases"]:
+        v = np.array([float.fromhex(x) for x in case["v"]])
+        w = np.array([float.fromhex(x) for x in case["w"]])
+        for kind in ("dubins", "reedsshepp"):
+            g = case[kind]
+            c, segs = orc.SimpleCar(kind, rt).steer(v, w)
+            gc = float(g["cost"])
+            # float64 evaluation of lengths of a few units: absolute 1e-12 ... except next to the formulas' own
+            # discontinuities (mod2pi of an angle within rounding of 0 / 2pi adds a full turn: reproduced, not compared)
+            if abs(c - gc) > 1e-11 * max(1.0, gc):
+                assert abs(abs(c - gc) - TWO_PI * rt) < 1e-9 or g["gap"] < 1e-9, (kind, case["v"], case["w"], c, gc)
+                continue
+            if g["gap"] > 1e-7:          # the winner is unambiguous: same word, same directions, same durations
+                ctrl = g["control"]
+                assert len(segs) == len(ctrl)
+                for s, (t, u1, u2) in zip(segs, ctrl):
+                    assert abs(s[0] - float(t)) < 1e-10 and s[1] == float(u1) and abs(s[2] - float(u2)) < 1e-12
+                compared_controls += 1
+    assert compared_controls > 350
