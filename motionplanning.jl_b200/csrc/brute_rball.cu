@@ -122,25 +122,32 @@ slab_to_csc(const int *__restrict__ slab_j, const double *__restrict__ slab_s, i
 // the back (appended by their own rows' threads through an atomic slot: unordered).  One block per column sorts the
 // back part by sample index in shared memory (bitonic on index << 32 | slot, squared distances parked by slot) and
 // writes  sorted(back) ++ front.  np = power of two >= every column's back part, 16 bytes of shared memory each.
+// KeyT = uint32_t when (bits of N) + log2(np) <= 32 (key = index << log2(np) | slot), else uint64_t (index << 32 | slot).
+// A compare-exchange stage with stride <= 32 only touches the 64-element segment of the pairs a warp owns (pair p
+// belongs to segment p >> 5, and a warp always takes whole segments), so those stages synchronise the warp, not the
+// block: for 256 keys 6 of the 36 stages need __syncthreads.
+template <class KeyT>
 __global__ void __launch_bounds__(128)
-slab_merge_to_csc(const int *__restrict__ slab_j, const double *__restrict__ slab_s, int cap, int np, int64_t nq,
-                  const int *__restrict__ own, const int *__restrict__ remote, const int64_t *__restrict__ colptr,
+slab_merge_to_csc(const int *__restrict__ slab_j, const double *__restrict__ slab_s, int cap, int np, int slot_bits, int min_kr,
+                  int64_t nq, const int *__restrict__ own, const int *__restrict__ remote, const int64_t *__restrict__ colptr,
                   int64_t *__restrict__ rowval, double *__restrict__ nzval) {
-    extern __shared__ unsigned long long s_sort[];  // np keys, then np squared distances
-    unsigned long long *key = s_sort;
-    double *sv = reinterpret_cast<double *>(s_sort + np);
+    extern __shared__ unsigned long long s_sort[];  // np squared distances, then np keys
+    double *sv = reinterpret_cast<double *>(s_sort);
+    KeyT *key = reinterpret_cast<KeyT *>(s_sort + np);
+    const KeyT slot_mask = (KeyT)((KeyT(1) << slot_bits) - 1);
     for (int64_t w = blockIdx.x; w < nq; w += gridDim.x) {
         const int64_t base = colptr[w] - 1;
         const int kr = remote[w], ko = own[w];
-        int n = 32;
+        if (kr <= min_kr) continue;  // block-uniform: handled by slab_merge_warp
+        int n = 64;
         while (n < kr) n <<= 1;  // block-uniform: the smallest power of two that holds the unordered part
         for (int e = threadIdx.x; e < n; e += blockDim.x) {
             if (e < kr) {
                 const size_t at = (size_t)w * cap + (cap - 1 - e);
-                key[e] = ((unsigned long long)(unsigned)slab_j[at] << 32) | (unsigned)e;
+                key[e] = (KeyT)(((KeyT)(unsigned)slab_j[at] << slot_bits) | (KeyT)e);
                 sv[e] = slab_s[at];
             } else {
-                key[e] = ~0ULL;
+                key[e] = (KeyT)~KeyT(0);
             }
         }
         __syncthreads();
@@ -149,21 +156,105 @@ slab_merge_to_csc(const int *__restrict__ slab_j, const double *__restrict__ sla
                 for (int t = threadIdx.x; t < n / 2; t += blockDim.x) {
                     const int lo = ((t & ~(stride - 1)) << 1) | (t & (stride - 1)), hi = lo | stride;
                     const bool up = (lo & size) == 0;
-                    const unsigned long long a = key[lo], b = key[hi];
+                    const KeyT a = key[lo], b = key[hi];
                     if ((a > b) == up) { key[lo] = b; key[hi] = a; }
                 }
-                __syncthreads();
+                const int next = stride > 1 ? (stride >> 1) : size;  // stride of the stage that follows
+                if (stride >= 64 || next >= 64) __syncthreads(); else __syncwarp();
             }
+        __syncthreads();
         for (int e = threadIdx.x; e < kr; e += blockDim.x) {
-            const unsigned long long ky = key[e];
-            rowval[base + e] = (int64_t)(ky >> 32) + 1;
-            nzval[base + e] = sqrt(sv[(unsigned)ky]);
+            const KeyT ky = key[e];
+            rowval[base + e] = (int64_t)(ky >> slot_bits) + 1;
+            nzval[base + e] = sqrt(sv[(unsigned)(ky & slot_mask)]);
         }
         for (int e = threadIdx.x; e < ko; e += blockDim.x) {
             rowval[base + kr + e] = (int64_t)slab_j[(size_t)w * cap + e] + 1;
             nzval[base + kr + e] = sqrt(slab_s[(size_t)w * cap + e]);
         }
         __syncthreads();
+    }
+}
+// The same conversion with one WARP per column and the keys in registers (K per lane, element e = 32 r + lane):
+// compare-exchange stages with a stride below 32 are one shuffle per key, the others are register-to-register, and
+// nothing synchronises a block.  Key = index << 10 | slot (needs N < 2^22 and at most 1024 unordered entries; other
+// columns are left to slab_merge_to_csc).  After the sort every lane knows (index, slot) of its output positions and
+// fetches the squared distance from the slab row by slot.
+template <int K>
+__device__ __forceinline__ void warp_bitonic(unsigned (&k)[K], int lane) {
+#pragma unroll
+    for (int size = 2; size <= 32 * K; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            if (stride >= 32) {
+                const int rs = stride >> 5;
+#pragma unroll
+                for (int r = 0; r < K; ++r) {
+                    if ((r & rs) == 0) {
+                        const bool up = ((r << 5) & size) == 0;   // size >= 64 here: the bit lives in r
+                        const unsigned a = k[r], b = k[r | rs];
+                        const unsigned lo = min(a, b), hi = max(a, b);
+                        k[r] = up ? lo : hi;
+                        k[r | rs] = up ? hi : lo;
+                    }
+                }
+            } else {
+                const bool lower = (lane & stride) == 0;
+#pragma unroll
+                for (int r = 0; r < K; ++r) {
+                    const unsigned o = __shfl_xor_sync(0xffffffffu, k[r], stride);
+                    const bool up = (((r << 5) | lane) & size) == 0;
+                    k[r] = (lower == up) ? min(k[r], o) : max(k[r], o);
+                }
+            }
+        }
+    }
+}
+template <int K>
+__device__ __forceinline__ void merge_column_warp(const int *__restrict__ sj, const double *__restrict__ ss, int cap, int kr,
+                                                  int64_t *__restrict__ rv, double *__restrict__ nz, int lane) {
+    unsigned k[K];
+#pragma unroll
+    for (int r = 0; r < K; ++r) {
+        const int e = (r << 5) | lane;
+        k[r] = e < kr ? (((unsigned)sj[cap - 1 - e] << 10) | (unsigned)e) : 0xffffffffu;
+    }
+    warp_bitonic<K>(k, lane);
+#pragma unroll
+    for (int r = 0; r < K; ++r) {
+        const int e = (r << 5) | lane;
+        if (e < kr) {
+            rv[e] = (int64_t)(k[r] >> 10) + 1;
+            nz[e] = sqrt(ss[cap - 1 - (int)(k[r] & 1023u)]);
+        }
+    }
+}
+// WIDE = false: columns with at most 512 unordered entries; WIDE = true: those with 513 .. 1024 (32 keys per lane:
+// a kernel of its own so that the common case does not pay for its registers)
+template <bool WIDE>
+__global__ void __launch_bounds__(128)
+slab_merge_warp(const int *__restrict__ slab_j, const double *__restrict__ slab_s, int cap, int64_t nq,
+                const int *__restrict__ own, const int *__restrict__ remote, const int64_t *__restrict__ colptr,
+                int64_t *__restrict__ rowval, double *__restrict__ nzval) {
+    const int lane = threadIdx.x & 31;
+    const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t w = gw; w < nq; w += nw) {
+        const int kr = remote[w], ko = own[w];
+        if (WIDE ? (kr <= 512 || kr > 1024) : (kr > 512)) continue;  // more than 1024: the block-per-column kernel
+        const int64_t base = colptr[w] - 1;
+        const int *sj = slab_j + (size_t)w * cap;
+        const double *ss = slab_s + (size_t)w * cap;
+        int64_t *rv = rowval + base;
+        double *nz = nzval + base;
+        if (WIDE) merge_column_warp<32>(sj, ss, cap, kr, rv, nz, lane);
+        else if (kr > 256) merge_column_warp<16>(sj, ss, cap, kr, rv, nz, lane);
+        else if (kr > 128) merge_column_warp<8>(sj, ss, cap, kr, rv, nz, lane);
+        else if (kr > 64) merge_column_warp<4>(sj, ss, cap, kr, rv, nz, lane);
+        else if (kr > 0) merge_column_warp<2>(sj, ss, cap, kr, rv, nz, lane);
+        for (int e = lane; e < ko; e += 32) {   // the column's own entries: already ascending
+            rv[kr + e] = (int64_t)sj[e] + 1;
+            nz[kr + e] = sqrt(ss[e]);
+        }
     }
 }
 __global__ void add_counts(const int *__restrict__ a, const int *__restrict__ b, int64_t n, int *__restrict__ out) {
@@ -306,17 +397,48 @@ static int brute_build(mpb200_samples *s, double r, mpb200_table *t) {
     if (int rc = t->nzval.reserve(sizeof(double) * (size_t)(nnz + 1))) return rc;
     phase_mark(3);
     if (nq > 0 && nnz > 0) {
+        bool counted = false;
         if (single) {
             const double *slab_s = t->scratch.as<double>();
             const int *slab_j = reinterpret_cast<const int *>(slab_s + (size_t)cap * (size_t)nq);
             if (symmetric) {
-                int np = 32;
-                while (np < cap) np <<= 1;
-                const size_t smem = 16 * (size_t)np;
-                MPB_CUDA(cudaFuncSetAttribute(slab_merge_to_csc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                const unsigned gs = (unsigned)std::min<int64_t>(nq, (int64_t)ctx().sm_count * 32);
-                slab_merge_to_csc<<<gs, 128, smem, st>>>(slab_j, slab_s, cap, np, nq, counts + nq + 2, counts + 2 * nq + 2,
-                                                         t->colptr.as<int64_t>(), t->rowval.as<int64_t>(), t->nzval.as<double>());
+                int np = 64, slot_bits = 6;
+                while (np < cap) { np <<= 1; ++slot_bits; }
+                int idx_bits = 1;
+                while ((int64_t(1) << idx_bits) < N) ++idx_bits;
+                static const bool block_only = getenv("MPB200_SLAB_BLOCK_SORT") != nullptr;
+                const bool warp_sort = idx_bits <= 22 && !block_only;   // key = index << 10 | slot in 32 bits
+                if (warp_sort) {
+                    slab_merge_warp<false><<<(unsigned)(ctx().sm_count * 16), 128, 0, st>>>(
+                        slab_j, slab_s, cap, nq, counts + nq + 2, counts + 2 * nq + 2, t->colptr.as<int64_t>(),
+                        t->rowval.as<int64_t>(), t->nzval.as<double>());
+                    MPB_LAUNCHED();
+                    if (cap > 512) {
+                        slab_merge_warp<true><<<(unsigned)(ctx().sm_count * 8), 128, 0, st>>>(
+                            slab_j, slab_s, cap, nq, counts + nq + 2, counts + 2 * nq + 2, t->colptr.as<int64_t>(),
+                            t->rowval.as<int64_t>(), t->nzval.as<double>());
+                        MPB_LAUNCHED();
+                    }
+                }
+                if (!warp_sort || cap > 1024) {   // every column, or only those with more than 1024 unordered entries
+                    const int min_kr = warp_sort ? 1024 : -1;
+                    const bool narrow = idx_bits + slot_bits <= 32;
+                    const size_t smem = (narrow ? 12 : 16) * (size_t)np;
+                    const unsigned gs = (unsigned)std::min<int64_t>(nq, (int64_t)ctx().sm_count * 32);
+                    if (narrow) {
+                        MPB_CUDA(cudaFuncSetAttribute(slab_merge_to_csc<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                        slab_merge_to_csc<uint32_t><<<gs, 128, smem, st>>>(slab_j, slab_s, cap, np, slot_bits, min_kr, nq, counts + nq + 2,
+                                                                           counts + 2 * nq + 2, t->colptr.as<int64_t>(),
+                                                                           t->rowval.as<int64_t>(), t->nzval.as<double>());
+                    } else {
+                        MPB_CUDA(cudaFuncSetAttribute(slab_merge_to_csc<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                        slab_merge_to_csc<uint64_t><<<gs, 128, smem, st>>>(slab_j, slab_s, cap, np, 32, min_kr, nq, counts + nq + 2,
+                                                                           counts + 2 * nq + 2, t->colptr.as<int64_t>(),
+                                                                           t->rowval.as<int64_t>(), t->nzval.as<double>());
+                    }
+                } else {
+                    counted = true;   // the warp kernel was the only launch and has been counted
+                }
             } else
             slab_to_csc<<<(unsigned)(ctx().sm_count * 8), 256, 0, st>>>(slab_j, slab_s, cap, nq, t->colptr.as<int64_t>(),
                                                                        t->rowval.as<int64_t>(), t->nzval.as<double>());
@@ -331,7 +453,7 @@ static int brute_build(mpb200_samples *s, double r, mpb200_table *t) {
                                                                t->colptr.as<int64_t>(), t->rowval.as<int64_t>(),
                                                                t->nzval.as<double>(), 0, nullptr, nullptr);
         }
-        MPB_LAUNCHED();
+        if (!counted) MPB_LAUNCHED();
     }
     phase_mark(4);
     MPB_CUDA(cudaStreamSynchronize(st));
