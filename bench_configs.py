@@ -344,16 +344,28 @@ def kn(mp, orc, fx, args):
     state = {}
 
     def run():
+        import time as _tm
         r = nnm._knn_radius_guess(V, k)
         rounds = 0
+        tb = ts = 0.0
         while True:
             rounds += 1
+            SYNC(); t0 = _tm.perf_counter()
             NN.build_table(r)
-            if nnm._table_knn(NN.table, k, NN.table_knn) == 0:
+            SYNC(); t1 = _tm.perf_counter()
+            short = nnm._short_columns(NN.table, k)
+            tb += t1 - t0
+            if short == 0:
                 break
             r *= 1.3
+        SYNC(); t1 = _tm.perf_counter()
+        nnm._table_knn(NN.table, k, NN.table_knn)
+        SYNC(); t2 = _tm.perf_counter()
+        ts = t2 - t1
         nnm._table_union_transpose(NN.table_knn, NN.table_knn, NN.table_mknn)
-        state.update(r=r, rounds=rounds, nnz_ball=NN.table.nnz, nnz_mutual=NN.table_mknn.nnz)
+        SYNC(); t3 = _tm.perf_counter()
+        state.update(r=r, rounds=rounds, nnz_ball=NN.table.nnz, nnz_mutual=NN.table_mknn.nnz,
+                     ball_tables_s=tb, k_selection_s=ts, mutual_s=t3 - t2)
     t_gpu, _ = timed(run, reps=2)
     q = 64
     # oracle: brute force k-selection for q columns over all N samples

@@ -303,6 +303,8 @@ int mpb200_mc_collision_probability(const mpb200_mc_problem *p, const mpb200_obs
  *   full-range tables over the same sample set).  Columns are limited to 8192 entries.
  * Non-NULL *out handles are reused.  Edge validity works on the results like on any table. */
 int mpb200_table_knn(const mpb200_table *t, int k, mpb200_table **out, int64_t *nnz, int64_t *short_cols);
+/* only the question "does every column of t hold at least k entries?": *short_cols = columns that do not */
+int mpb200_table_short_columns(const mpb200_table *t, int k, int64_t *short_cols);
 int mpb200_table_union_transpose(const mpb200_table *a, const mpb200_table *b, mpb200_table **out, int64_t *nnz);
 
 /* ---- closest obstacle points under a weight matrix (Monte-Carlo proposal geometry) ----------

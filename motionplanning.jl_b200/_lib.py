@@ -89,6 +89,7 @@ SIGNATURES = {
     "mpb200_mc_collision_probability": (ctypes.c_int, [P(McProblem), c_vp, ctypes.c_uint64, c_i64, c_i64, P(McResult),
                                                        c_vp, c_vp]),
     "mpb200_table_knn": (ctypes.c_int, [c_vp, ctypes.c_int, P(c_vp), P(c_i64), P(c_i64)]),
+    "mpb200_table_short_columns": (ctypes.c_int, [c_vp, ctypes.c_int, P(c_i64)]),
     "mpb200_table_union_transpose": (ctypes.c_int, [c_vp, c_vp, P(c_vp), P(c_i64)]),
     "mpb200_close_points": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, ctypes.c_int, c_dbl, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "mpb200_xchg_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, c_i64, c_i64, P(c_vp), c_vp]),

@@ -204,6 +204,7 @@ int car_steer_device(int kind, double rturn, double speed, const double *dA, con
                      int *d_nseg, double *d_segs);
 int pipe_peak_device(int kind, double *ops_per_s);
 int table_knn_device(const mpb200_table *t, int k, mpb200_table *out, int64_t *short_cols, DevBuf &scan_tmp);
+int table_short_columns_device(const mpb200_table *t, int k, int64_t *short_cols);
 int table_union_transpose_device(const mpb200_table *a, const mpb200_table *b, mpb200_table *out, DevBuf &scan_tmp);
 int table_write_floor_device(const mpb200_table *t, double *ms);
 int close_points_device(const mpb200_obstacles *o, const double *dP, const double *dW, int64_t n, int dw, double r2,
@@ -1257,6 +1258,12 @@ int mpb200_table_knn(const mpb200_table *t, int k, mpb200_table **out, int64_t *
     if (nnz) *nnz = o->nnz;
     if (short_cols) *short_cols = n_short;
     return MPB200_OK;
+}
+int mpb200_table_short_columns(const mpb200_table *t, int k, int64_t *short_cols) {
+    MPB_REQUIRE_INIT();
+    MPB_CHECK_ARG(t != nullptr && short_cols != nullptr, "NULL argument");
+    MPB_CHECK_ARG(k >= 1, "k must be at least 1");
+    return table_short_columns_device(t, k, short_cols);
 }
 int mpb200_table_union_transpose(const mpb200_table *a, const mpb200_table *b, mpb200_table **out, int64_t *nnz) {
     MPB_REQUIRE_INIT();

@@ -201,6 +201,30 @@ static int copy_meta(const mpb200_table *src, mpb200_table *dst) {
     return 0;
 }
 
+__global__ void short_columns_kernel(const int64_t *__restrict__ colptr, int64_t ncols, int k, unsigned long long *__restrict__ n_short) {
+    unsigned long long mine = 0;
+    for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < ncols; w += (int64_t)gridDim.x * blockDim.x)
+        mine += (colptr[w + 1] - colptr[w]) < k ? 1 : 0;
+    for (int o = 16; o; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(n_short, mine);
+}
+
+// columns of t with fewer than k entries (the cheap question "is the radius large enough?" before any selection)
+int table_short_columns_device(const mpb200_table *t, int k, int64_t *short_cols) {
+    Context &c = ctx();
+    cudaStream_t st = c.stream;
+    MPB_CUDA(cudaMemsetAsync(c.d_scalar + 3, 0, sizeof(int64_t), st));
+    if (t->ncols > 0) {
+        const unsigned g = (unsigned)std::min<int64_t>(std::max<int64_t>(ceil_div(t->ncols, 256), 1), (int64_t)c.sm_count * 8);
+        short_columns_kernel<<<g, 256, 0, st>>>(t->colptr.as<int64_t>(), t->ncols, k, reinterpret_cast<unsigned long long *>(c.d_scalar + 3));
+        MPB_LAUNCHED();
+    }
+    MPB_CUDA(cudaMemcpyAsync(c.h_scalar + 3, c.d_scalar + 3, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    MPB_CUDA(cudaStreamSynchronize(st));
+    *short_cols = c.h_scalar[3];
+    return 0;
+}
+
 int table_knn_device(const mpb200_table *t, int k, mpb200_table *out, int64_t *short_cols, DevBuf &scan_tmp) {
     Context &c = ctx();
     cudaStream_t st = c.stream;

@@ -253,7 +253,9 @@ def _knn_radius_guess(V, k):
     N, d = V.shape
     ext = np.maximum(V.max(axis=0) - V.min(axis=0), 1e-300)
     zeta = math.pi ** (d / 2) / math.gamma(d / 2 + 1)
-    return float((1.6 * k / max(N, 1) * float(np.prod(ext)) / zeta) ** (1.0 / d))
+    # in 2-D / 3-D the columns that decide are the ones in the corners of the box, which see 1/2^d of a ball
+    corner = 2.0 ** d if d <= 3 else 1.0
+    return float(((1.25 if d <= 3 else 1.6) * corner * k / max(N, 1) * float(np.prod(ext)) / zeta) ** (1.0 / d))
 
 
 def _table_knn(src, k, dst):
@@ -261,6 +263,13 @@ def _table_knn(src, k, dst):
     nnz, short = _lib.c_i64(0), _lib.c_i64(0)
     _lib.check(_lib.lib().mpb200_table_knn(src.h, int(k), ctypes.byref(dst.h), ctypes.byref(nnz), ctypes.byref(short)))
     dst.nnz, dst.ncols = nnz.value, src.ncols
+    return short.value
+
+
+def _short_columns(table, k):
+    """columns of a device table with fewer than k entries (mpb200_table_short_columns)"""
+    short = _lib.c_i64(0)
+    _lib.check(_lib.lib().mpb200_table_short_columns(table.h, int(k), ctypes.byref(short)))
     return short.value
 
 
@@ -344,11 +353,12 @@ class MetricNN(SampleSet):
             self.table_knn, self.table_mknn = DeviceTable("knn"), DeviceTable("mknn")
         for _ in range(max_rounds):
             self.build_table(r)
-            if _table_knn(self.table, k, self.table_knn) == 0:
+            if _short_columns(self.table, k) == 0:         # the selection itself runs once, on the final table
                 break
             r *= grow
         else:
             raise RuntimeError("k-nearest search did not reach k = %d neighbours per sample" % k)
+        _table_knn(self.table, k, self.table_knn)
         _table_union_transpose(self.table_knn, self.table_knn, self.table_mknn)
         self.k = k
         self.cache_knn = ImmutableNNC(self.fetch_table(self.table_knn, "knn"), float(r))
@@ -421,13 +431,13 @@ class QuasiMetricNN(SampleSet):
             self.table_knnF, self.table_knnB, self.table_mknnF = DeviceTable("knnF"), DeviceTable("knnB"), DeviceTable("mknnF")
         for _ in range(max_rounds):
             self.build_tables(r)
-            shortF = _table_knn(self.tableF, k, self.table_knnF)
-            shortB = _table_knn(self.tableB, k, self.table_knnB)
-            if shortF == 0 and shortB == 0:
+            if _short_columns(self.tableF, k) == 0 and _short_columns(self.tableB, k) == 0:
                 break
             r *= grow
         else:
             raise RuntimeError("k-nearest search did not reach k = %d neighbours per sample" % k)
+        _table_knn(self.tableF, k, self.table_knnF)
+        _table_knn(self.tableB, k, self.table_knnB)
         _table_union_transpose(self.table_knnF, self.table_knnB, self.table_mknnF)
         self.k = k
         self.cache_knnF = ImmutableNNC(self.fetch_table(self.table_knnF, "knnF"), float(r))
