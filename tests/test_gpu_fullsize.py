@@ -149,3 +149,39 @@ def test_k3_wide_sparse_cloud_small_radius_takes_the_cuda_core_path(gpu, orc):
     assert D.nzval.tobytes() == ref[2].tobytes()
     assert D.nnz >= 2 * 600
     NN.close()
+
+
+@pytest.mark.parametrize("kind", ["reedsshepp", "dubins"])
+def test_f4_car_tables_at_bench_size(gpu, orc, kind):
+    """bench config F4 (N = 200k SE2 states, turning radius 0.01, r = 0.025): 96 columns in three windows of the index
+    range, both directions for Dubins, and the arc-waypoint edge bits of those columns, byte for byte"""
+    import math
+    mp = gpu
+    N, rturn, r = 200_000, 0.01, 0.025
+    rng = np.random.Generator(np.random.PCG64(20240605))
+    V = np.column_stack([rng.random(N), rng.random(N), rng.uniform(0, 2 * math.pi, N)])
+    SS = (mp.ReedsSheppMetricSpace if kind == "reedsshepp" else mp.DubinsQuasiMetricSpace)(rturn)
+    mp.setup_steering(SS, r)
+    car = orc.SimpleCar(kind, rturn)
+    CC = mp.PointRobot2D(mp.obstaclesets.ISRR_2H())
+    O = orc.Obstacles2D(fx.ISRR_2H)
+    So = orc.StateSpace(SS.lo, SS.hi, ("view", [1, 2]))
+    if kind == "reedsshepp":
+        NN = mp.MetricNN(V, SS.dist, V[0])
+        tables = [(NN.precompute(r).D, True)]
+    else:
+        NN = mp.QuasiMetricNN(V, SS.dist, V[0])
+        cF, cB = NN.precompute(r)
+        tables = [(cF.D, True), (cB.D, False)]
+    bits, _ = NN.car_edges_free(CC, SS)
+    Dlast = tables[-1][0]                                # the table the edge bits belong to
+    ebits = unpack_bits(bits, Dlast.nnz)
+    for q0 in (0, N // 2 - 16, N - 32):
+        for D, fw in tables:
+            ref = car.inball(V, r, fw, q0=q0, q1=q0 + 32)
+            lo, hi = D.colptr[q0] - 1, D.colptr[q0 + 32] - 1
+            assert np.array_equal(D.colptr[q0:q0 + 33] - D.colptr[q0], ref[0] - 1)
+            assert np.array_equal(D.rowval[lo:hi], ref[1]) and D.nzval[lo:hi].tobytes() == ref[2].tobytes()
+        exp, _ = car.edges_free_csc(O, So, V, ref[0], ref[1], c0=q0)
+        assert np.array_equal(ebits[lo:hi], exp.astype(bool))
+    NN.close()
