@@ -76,8 +76,6 @@ __device__ __noinline__ void sincos_(double x, double *sn, double *cs) {
     *cs = ((q + 1) & 2) ? -b : b;
     *sn = (x < 0.0) ? -sq : sq;
 }
-__device__ __forceinline__ double sin_(double x) { double s, c; sincos_(x, &s, &c); return s; }
-__device__ __forceinline__ double cos_(double x) { double s, c; sincos_(x, &s, &c); return c; }
 
 __device__ __forceinline__ double atan01(double a) {
     const int ci = (int)(a * 4.0 + 0.5);
