@@ -177,3 +177,19 @@ def test_degenerate_sample_sets_and_argument_errors(gpu, orc):
     with pytest.raises(mp.MPB200Error, match="SE2"):
         NN2.precompute(0.1)
     NN2.close()
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_fmtstar_samples_and_solves_a_car_problem_from_scratch(gpu, kind):
+    """fmtstar!(P, N) on a car space with nothing precomputed: defaultNN (statespaces.jl:166-170), sample_free!
+    (SE2 states, goal samples), tables, checks, path: the reference's notebook flow"""
+    mp = gpu
+    SS = _space(mp, kind, 0.05)
+    CC = mp.PointRobot2D(mp.obstaclesets.ISRR_2H(), fixed_point_test=True)
+    P = mp.MPProblem(SS, [0.1, 0.1, 0.0], mp.BallGoal([0.9, 0.9], 0.08), CC)
+    status, cost, _ = mp.fmtstar(P, 2500, r=0.2, ensure_goal_ct=5, seed=3)
+    assert type(P.V).__name__ == ("MetricNN" if kind == "reedsshepp" else "QuasiMetricNN") and len(P.V) == 2500
+    assert status == "solved" and math.hypot(0.8, 0.8) - 0.08 <= cost < 4.0
+    path = P.solution.metadata["path"]
+    assert path[0] == 1 and mp.is_free_path(P.V.V[np.asarray(path) - 1], CC, SS)
+    P.V.close()
