@@ -352,6 +352,8 @@ class MetricNN(SampleSet):
         if not hasattr(self, "table_knn"):
             self.table_knn, self.table_mknn = DeviceTable("knn"), DeviceTable("mknn")
         for _ in range(max_rounds):
+            if _is_car(self.dist):
+                self.dist.chopval = r                      # setup_steering: the chop value follows the radius
             self.build_table(r)
             if _short_columns(self.table, k) == 0:         # the selection itself runs once, on the final table
                 break
@@ -365,8 +367,8 @@ class MetricNN(SampleSet):
         self.cache_mknn = ImmutableNNC(self.fetch_table(self.table_mknn, "mknn"), float(r))
         return self.cache_knn, self.cache_mknn
 
-    def car_edges_free(self, CC, SS, fetch=True):
-        return _car_edges_free(self, self.table, CC, SS, fetch)
+    def car_edges_free(self, CC, SS, fetch=True, table=None):
+        return _car_edges_free(self, table if table is not None else self.table, CC, SS, fetch)
 
     def precompute_checked(self, r, CC, SS):
         """precompute + edge validity through the fused pass -> (ImmutableNNC, edge chunks, checks)"""
@@ -430,6 +432,8 @@ class QuasiMetricNN(SampleSet):
         if not hasattr(self, "table_knnF"):
             self.table_knnF, self.table_knnB, self.table_mknnF = DeviceTable("knnF"), DeviceTable("knnB"), DeviceTable("mknnF")
         for _ in range(max_rounds):
+            if _is_car(self.dist):
+                self.dist.chopval = r
             self.build_tables(r)
             if _short_columns(self.tableF, k) == 0 and _short_columns(self.tableB, k) == 0:
                 break

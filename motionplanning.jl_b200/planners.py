@@ -143,17 +143,23 @@ def fmtstar(P, N=None, rm=1.0, connections="R", r=0.0, ensure_goal_ct=1, init_id
     lazy = edge_checks == "lazy"
     lq = isinstance(SS.dist, LinearQuadratic)
     car = is_car_metric(SS.dist)
-    if car and knn_mode:
-        raise NotImplementedError("k-nearest connections are not wired for the car spaces")
     ebits = None
-    if knn_mode and lq:
+    if knn_mode and (lq or (car and not SS.dist.symmetric)):
         cF, cB, cM = NN.precompute_knn(k, r)               # cost radius grows from r until every column holds k
         r = cB.r
         setup_steering(SS, r)                              # the steering horizon of the waypoint checks = the last radius
         NN.r = r
         DF, DB = cM.D, cB.D
         if not lazy:
-            ebits, _ = NN.lq_edges_free(CC, SS, table=NN.table_knnB)
+            ebits, _ = (NN.car_edges_free if car else NN.lq_edges_free)(CC, SS, table=NN.table_knnB)
+    elif knn_mode and car:                                 # Reeds-Shepp MetricNN: knnF = knnB = knn (forward lengths)
+        cK, cM = NN.precompute_knn(k, r)
+        r = cK.r
+        setup_steering(SS, r)
+        NN.r = r
+        DF, DB = cM.D, cK.D
+        if not lazy:
+            ebits, _ = NN.car_edges_free(CC, SS, table=NN.table_knn)
     elif knn_mode:
         cK, cM = NN.precompute_knn(k)
         DF, DB = cM.D, cK.D

@@ -193,3 +193,40 @@ def test_fmtstar_samples_and_solves_a_car_problem_from_scratch(gpu, kind):
     path = P.solution.metadata["path"]
     assert path[0] == 1 and mp.is_free_path(P.V.V[np.asarray(path) - 1], CC, SS)
     P.V.close()
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_fmt_k_nearest_connections_over_a_car_space(gpu, orc, kind):
+    """connections = :K on the car spaces: tables = k cheapest of the chopped-metric balls at the radius the growth loop
+    ends with (chop value = that radius), mutual forward neighbourhoods, same planner loop over the oracle's tables"""
+    mp = gpu
+    N, rturn, r0, k = 1200, 0.05, 0.12, 12
+    rng = np.random.Generator(np.random.PCG64(16))
+    SS = _space(mp, kind, rturn)
+    So = orc.StateSpace(SS.lo, SS.hi, ("view", [1, 2]))
+    B = orc.Boxes(fx.BOXES2D)
+    cand = _states(rng, 3 * N)
+    cand = cand[orc.states_free(B, So, cand)][:N - 2]
+    init, goal = np.array([0.1, 0.1, 0.0]), np.array([0.9, 0.9, 0.0])
+    V = np.vstack([init, cand, goal])
+    CC = mp.PointRobotNDBoxes([mp.BoxBounds(b) for b in fx.BOXES2D])
+    NNcls = mp.MetricNN if kind == "reedsshepp" else mp.QuasiMetricNN
+    P = mp.MPProblem(SS, init, mp.StateGoal(goal), CC, V=NNcls(V, SS.dist, init))
+    status, cost, _ = mp.fmtstar(P, r=r0, connections="K", k=k)
+    r = P.solution.metadata["r"]
+    assert r > r0                                          # the ball had to grow to hold k neighbours everywhere
+    car = orc.SimpleCar(kind, rturn)
+    TF = car.inball(V, r, True)
+    TB = TF if kind == "reedsshepp" else car.inball(V, r, False)
+    assert np.diff(TF[0]).min() >= k and np.diff(TB[0]).min() >= k
+    kF, kB = orc.knn_of_table(*TF, k), orc.knn_of_table(*TB, k)
+    M = orc.union_transpose(kF, kB, len(V))
+    col = lambda T, v: (T[1][T[0][v - 1] - 1:T[0][v] - 1], T[2][T[0][v - 1] - 1:T[0][v] - 1])
+    ref = fmt_oracle(V, np.all(V == goal, axis=1), lambda v: col(M, v), lambda v: col(kB, v),
+                     lambda i: bool(orc.states_free(B, So, V[i:i + 1])[0]),
+                     lambda y0, x0: car.is_free_motion(B, So, V[y0], V[x0]))
+    assert status == ("solved" if ref["solved"] else "failed")
+    assert P.solution.metadata["path"] == ref["path"] and np.array_equal(P.solution.metadata["tree"], ref["tree"])
+    if ref["solved"]:
+        assert abs(cost - ref["cost"]) <= 1e-12 * ref["cost"]
+    P.V.close()
