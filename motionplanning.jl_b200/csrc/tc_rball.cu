@@ -154,7 +154,14 @@ tc_rball_kernel(const double *__restrict__ V, const float *__restrict__ opB, con
     __shared__ __align__(128) float4 sB[4 * kTcN];   // 8 KB
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ uint32_t s_tmem;
+    // MODE 3: candidates that passed the tensor-core test wait in a per-warp queue until 32 of them can be checked
+    // exactly by 32 lanes at once (one candidate per lane), instead of one lane's loop stalling its whole warp
+    __shared__ uint32_t s_queue[(MODE == 3) ? kTcM / 32 : 1][(MODE == 3) ? 64 : 1];
+    __shared__ int s_own[(MODE == 3) ? kTcM : 1];   // entries appended to the front of each query row's slab
     const int tid = threadIdx.x, warp = tid >> 5;
+    const int lane = tid & 31;
+    if (MODE == 3) s_own[tid] = 0;
+    int q_count = 0;                                  // queued candidates of this warp (warp-uniform)
     const int64_t w = (int64_t)blockIdx.x * kTcM + tid;
     const bool active = w < nq;
     const int64_t q = q0 + w;
@@ -201,10 +208,45 @@ tc_rball_kernel(const double *__restrict__ V, const float *__restrict__ opB, con
     const uint32_t my_tmem = tmem + ((uint32_t)(warp * 32) << 16);
 
     int cnt = 0;
-    int64_t pend_j = -1;  // MODE 3: a partner append whose slot (an atomic's return value) has not been used yet
-    int pend_slot = 0;
-    double pend_s = 0.0;
     uint32_t phase = 0;
+    // MODE 3: exact FP64 test of the first n (<= 32) queued candidates, one per lane, and both appends.  A candidate is
+    // (sample j << 5 | query row of this warp).  Own column: the hits of one query are ranked in queue order (which is
+    // ascending j) with match_any / popc on top of the row's counter in shared memory, so the front of the slab row
+    // stays ascending without atomics; partner column: back of its slab row, slot from a global atomic.
+    auto drain = [&](int n) {
+        const bool act = lane < n;
+        const uint32_t c = act ? s_queue[warp][lane] : 0u;
+        const int ql = act ? (int)(c & 31u) : 32 + lane;          // inactive lanes match nobody
+        const int64_t j = (int64_t)(c >> 5);
+        const int64_t qg = (int64_t)blockIdx.x * kTcM + warp * 32 + (ql & 31);
+        double s64 = 0.0;
+        bool hit = false;
+        if (act) {
+            s64 = tc_exact_sq<D>(V + qg * D, V + j * D);
+            hit = s64 <= r2;
+        }
+        const unsigned hitmask = __ballot_sync(0xffffffffu, hit);
+        const unsigned peers = __match_any_sync(0xffffffffu, ql);
+        const unsigned lt = (1u << lane) - 1u;
+        int base = 0;
+        if (act) base = s_own[warp * 32 + ql];
+        __syncwarp();
+        if (hit) {
+            const int pos = base + __popc(peers & hitmask & lt);
+            if (pos < cap) { slab_j[qg * cap + pos] = (int)j; slab_s[qg * cap + pos] = s64; }
+            const int slot = atomicAdd(&rcounts[j], 1);
+            if (slot < cap) { slab_j[j * cap + (cap - 1 - slot)] = (int)qg; slab_s[j * cap + (cap - 1 - slot)] = s64; }
+        }
+        if (act && lane == __ffs(peers) - 1) s_own[warp * 32 + ql] = base + __popc(peers & hitmask);
+        __syncwarp();
+        // keep what is left of the queue at its front
+        const int rem = q_count - n;
+        const uint32_t keep = (lane < rem) ? s_queue[warp][n + lane] : 0u;
+        __syncwarp();
+        if (lane < rem) s_queue[warp][lane] = keep;
+        __syncwarp();
+        q_count = rem;
+    };
     // operand image: [tile of 128 samples][chunk 0..3][row 0..127]; an MMA tile = rows (t0 & 127) .. + kTcN of it
     constexpr int kStage = 4 * kTcN / kTcM;  // float4 per thread per tile
     float4 nextB[kStage];
@@ -250,7 +292,38 @@ tc_rball_kernel(const double *__restrict__ V, const float *__restrict__ opB, con
                 m2 = fmaxf(m2, __uint_as_float(rr[i + 2]));
                 m3 = fmaxf(m3, __uint_as_float(rr[i + 3]));
             }
-            if (fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) >= pass_at) {
+            const bool pass = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) >= pass_at;
+            if (MODE == 3) {
+                if (__any_sync(0xffffffffu, pass)) {   // warp-uniform
+                    uint32_t mask = 0;
+                    if (pass) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) mask |= (__uint_as_float(rr[i]) >= pass_at) ? (1u << i) : 0u;
+                        // only partners j with q < j < N (the pair's other half belongs to row j)
+                        const int64_t j0 = t0 + c0;
+                        const int64_t lo = q - j0;              // bits 0 .. lo are j <= q
+                        if (lo >= 31) mask = 0u;
+                        else if (lo >= 0) mask &= ~((2u << (int)lo) - 1u);
+                        const int64_t hi = N - j0;              // bits >= hi are padding samples
+                        if (hi <= 0) mask = 0u;
+                        else if (hi < 32) mask &= (1u << (int)hi) - 1u;
+                    }
+                    for (;;) {
+                        const bool has = mask != 0u;
+                        const unsigned bal = __ballot_sync(0xffffffffu, has);
+                        if (bal == 0u) break;
+                        if (has) {
+                            const int i = __ffs(mask) - 1;
+                            mask &= mask - 1u;
+                            s_queue[warp][q_count + __popc(bal & ((1u << lane) - 1u))] =
+                                ((uint32_t)(t0 + c0 + i) << 5) | (uint32_t)lane;
+                        }
+                        q_count += __popc(bal);
+                        __syncwarp();
+                        if (q_count >= 32) drain(32);
+                    }
+                }
+            } else if (pass) {
                 uint32_t mask = 0;
 #pragma unroll
                 for (int i = 0; i < 32; ++i) mask |= (__uint_as_float(rr[i]) >= pass_at) ? (1u << i) : 0u;
@@ -258,26 +331,7 @@ tc_rball_kernel(const double *__restrict__ V, const float *__restrict__ opB, con
                     const int i = __ffs(mask) - 1;
                     mask &= mask - 1;
                     const int64_t j = t0 + c0 + i;
-                    if (MODE == 3) {
-                        if (j < N && j > q) {  // the pair's other half (j < q, diagonal tile only) belongs to row j
-                            const double s64 = tc_exact_sq<D>(V + q * D, V + j * D);
-                            if (s64 <= r2) {
-                                // own column: entries fill the slab row from the front with a private counter (no atomic)
-                                if (cnt < cap) { slab_j[q * cap + cnt] = (int)j; slab_s[q * cap + cnt] = s64; }
-                                ++cnt;
-                                // partner's column: entries fill its slab row from the BACK, slot from an atomic counter.
-                                // The store that needs the returned slot is deferred to the next hit, so the atomic's
-                                // round trip overlaps the sweep instead of stalling the warp at every accepted pair.
-                                if (pend_j >= 0 && pend_slot < cap) {
-                                    slab_j[pend_j * cap + (cap - 1 - pend_slot)] = (int)q;
-                                    slab_s[pend_j * cap + (cap - 1 - pend_slot)] = pend_s;
-                                }
-                                pend_slot = atomicAdd(&rcounts[j], 1);
-                                pend_j = j;
-                                pend_s = s64;
-                            }
-                        }
-                    } else if (j < N && j != q) {
+                    if (j < N && j != q) {
                         const double s64 = tc_exact_sq<D>(V + q * D, V + j * D);
                         if (s64 <= r2) {
                             if (MODE == 2 && cnt < cap) {
@@ -294,11 +348,9 @@ tc_rball_kernel(const double *__restrict__ V, const float *__restrict__ opB, con
         __syncthreads();  // accumulator and sB are free for the next tile
     }
     if (MODE == 3) {
-        if (pend_j >= 0 && pend_slot < cap) {
-            slab_j[pend_j * cap + (cap - 1 - pend_slot)] = (int)q;
-            slab_s[pend_j * cap + (cap - 1 - pend_slot)] = pend_s;
-        }
-        if (active) counts[w] = cnt;  // own entries; the entries appended by partners are counted in rcounts
+        if (q_count > 0) drain(q_count);
+        __syncwarp();
+        if (active) counts[w] = s_own[tid];  // own entries; the entries appended by partners are counted in rcounts
     } else if (active) {
         counts[w] = cnt;
     }
