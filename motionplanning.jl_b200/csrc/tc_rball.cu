@@ -297,8 +297,24 @@ tc_rball_kernel(const double *__restrict__ V, const float *__restrict__ opB, con
                 if (__any_sync(0xffffffffu, pass)) {   // warp-uniform
                     uint32_t mask = 0;
                     if (pass) {
+                        // the four running maxima cover the columns i = k (mod 4): only the quarters whose maximum
+                        // passed are compared value by value (a passing lane typically has one candidate)
+                        if (m0 >= pass_at) {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) mask |= (__uint_as_float(rr[i]) >= pass_at) ? (1u << i) : 0u;
+                            for (int i = 0; i < 32; i += 4) mask |= (__uint_as_float(rr[i]) >= pass_at) ? (1u << i) : 0u;
+                        }
+                        if (m1 >= pass_at) {
+#pragma unroll
+                            for (int i = 1; i < 32; i += 4) mask |= (__uint_as_float(rr[i]) >= pass_at) ? (1u << i) : 0u;
+                        }
+                        if (m2 >= pass_at) {
+#pragma unroll
+                            for (int i = 2; i < 32; i += 4) mask |= (__uint_as_float(rr[i]) >= pass_at) ? (1u << i) : 0u;
+                        }
+                        if (m3 >= pass_at) {
+#pragma unroll
+                            for (int i = 3; i < 32; i += 4) mask |= (__uint_as_float(rr[i]) >= pass_at) ? (1u << i) : 0u;
+                        }
                         // only partners j with q < j < N (the pair's other half belongs to row j)
                         const int64_t j0 = t0 + c0;
                         const int64_t lo = q - j0;              // bits 0 .. lo are j <= q
