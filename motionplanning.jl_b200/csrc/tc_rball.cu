@@ -36,6 +36,11 @@ constexpr int kTcN = MPB_TC_N;  // samples per MMA tile (= TMEM columns per CTA)
 constexpr int kTcCtas = 512 / kTcN;
 constexpr int kTcK = 16;       // contraction length: d coordinates + 2 threshold slots, zero padded
 
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
 __device__ __forceinline__ float to_tf32(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -283,16 +288,23 @@ tc_rball_kernel(const double *__restrict__ V, const float *__restrict__ opB, con
         for (int c0 = 0; c0 < kTcN; c0 += 32) {
             uint32_t rr[32];
             tmem_ld32(my_tmem + (uint32_t)c0, rr);
-            float m0 = __uint_as_float(rr[0]), m1 = __uint_as_float(rr[1]), m2 = __uint_as_float(rr[2]),
-                  m3 = __uint_as_float(rr[3]);
+            // running maxima of the columns i = k (mod 4), three operands per instruction (FMNMX3)
+            float m0 = fmax3(__uint_as_float(rr[0]), __uint_as_float(rr[4]), __uint_as_float(rr[8]));
+            float m1 = fmax3(__uint_as_float(rr[1]), __uint_as_float(rr[5]), __uint_as_float(rr[9]));
+            float m2 = fmax3(__uint_as_float(rr[2]), __uint_as_float(rr[6]), __uint_as_float(rr[10]));
+            float m3 = fmax3(__uint_as_float(rr[3]), __uint_as_float(rr[7]), __uint_as_float(rr[11]));
 #pragma unroll
-            for (int i = 4; i < 32; i += 4) {
-                m0 = fmaxf(m0, __uint_as_float(rr[i]));
-                m1 = fmaxf(m1, __uint_as_float(rr[i + 1]));
-                m2 = fmaxf(m2, __uint_as_float(rr[i + 2]));
-                m3 = fmaxf(m3, __uint_as_float(rr[i + 3]));
+            for (int i = 12; i < 28; i += 8) {
+                m0 = fmax3(m0, __uint_as_float(rr[i]), __uint_as_float(rr[i + 4]));
+                m1 = fmax3(m1, __uint_as_float(rr[i + 1]), __uint_as_float(rr[i + 5]));
+                m2 = fmax3(m2, __uint_as_float(rr[i + 2]), __uint_as_float(rr[i + 6]));
+                m3 = fmax3(m3, __uint_as_float(rr[i + 3]), __uint_as_float(rr[i + 7]));
             }
-            const bool pass = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) >= pass_at;
+            m0 = fmaxf(m0, __uint_as_float(rr[28]));
+            m1 = fmaxf(m1, __uint_as_float(rr[29]));
+            m2 = fmaxf(m2, __uint_as_float(rr[30]));
+            m3 = fmaxf(m3, __uint_as_float(rr[31]));
+            const bool pass = fmaxf(fmax3(m0, m1, m2), m3) >= pass_at;
             if (MODE == 3) {
                 if (__any_sync(0xffffffffu, pass)) {   // warp-uniform
                     uint32_t mask = 0;
