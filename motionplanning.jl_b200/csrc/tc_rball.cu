@@ -15,13 +15,12 @@
 // the prefilter has no false negatives.  Up to four CTAs share an SM (4 x 128 TMEM columns), which
 // overlaps one CTA's MMA with the others' epilogues without an explicit pipeline.
 //
-// What bounds it: every FP32 accumulator has to come back through tcgen05.ld, and TMEM reads run at 64 B per
-// clock per SM (B300_MICROARCH.md, LDTM throughput): a 128 x 128 tile is 64 KB = 1024 clocks, i.e. 0.86 s for the
-// 4e12 pairs of C3 on 148 SMs -- measured 1.02 s.  A version with TMA bulk copies of the sample tiles, two TMEM
-// accumulators (MMA one tile ahead of the epilogue) and two loads in flight, at two CTAs per SM, was built and
-// measured at 1.38 s: it removes latency that was already hidden by the four co-resident CTAs and cannot touch the
-// read-back limit.  Getting under it needs fewer accumulator bytes per pair (sm_103a's tcgen05.ld.red, or 16-bit
-// accumulators with a re-derived error bound), not a better pipeline.
+// What bounded it (and what did not): earlier revisions took the accumulator read-back (tcgen05.ld at "64 B per clock
+// per SM") for the bound because the measured times sat just under it.  A full-size ncu capture showed tensor memory
+// busy 21% of the cycles and the issue slots / CTA barrier saturated by the RARE path instead: one lane's inline exact
+// recheck kept its warp, and at the barrier its CTA, waiting.  Full-range builds therefore (MODE 3) sweep each unordered
+// pair once and push the candidates that pass into a per-warp queue that is rechecked 32 at a time, one candidate per
+// lane: C3 went from 0.91 s to 0.31 s, 95 B per clock per SM of accumulators read back.
 #include "common.cuh"
 #include "scan.cuh"
 #include "tc_rball.cuh"
