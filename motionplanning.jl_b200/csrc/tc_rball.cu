@@ -18,9 +18,9 @@
 // What bounded it (and what did not): earlier revisions took the accumulator read-back (tcgen05.ld at "64 B per clock
 // per SM") for the bound because the measured times sat just under it.  A full-size ncu capture showed tensor memory
 // busy 21% of the cycles and the issue slots / CTA barrier saturated by the RARE path instead: one lane's inline exact
-// recheck kept its warp, and at the barrier its CTA, waiting.  Full-range builds therefore (MODE 3) sweep each unordered
-// pair once and push the candidates that pass into a per-warp queue that is rechecked 32 at a time, one candidate per
-// lane: C3 went from 0.91 s to 0.31 s, 95 B per clock per SM of accumulators read back.
+// recheck kept its warp, and at the barrier its CTA, waiting.  Every mode therefore pushes the candidates that pass into
+// a per-warp queue that is rechecked 32 at a time, one candidate per lane, and full-range builds (MODE 3) sweep each
+// unordered pair once: C3 went from 0.91 s to 0.31 s, 95 B per clock per SM of accumulators read back.
 #include "common.cuh"
 #include "scan.cuh"
 #include "tc_rball.cuh"
@@ -158,13 +158,13 @@ tc_rball_kernel(const double *__restrict__ V, const float *__restrict__ opB, con
     __shared__ __align__(128) float4 sB[4 * kTcN];   // 8 KB
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ uint32_t s_tmem;
-    // MODE 3: candidates that passed the tensor-core test wait in a per-warp queue until 32 of them can be checked
+    // candidates that passed the tensor-core test wait in a per-warp queue until 32 of them can be checked
     // exactly by 32 lanes at once (one candidate per lane), instead of one lane's loop stalling its whole warp
-    __shared__ uint32_t s_queue[(MODE == 3) ? kTcM / 32 : 1][(MODE == 3) ? 64 : 1];
-    __shared__ int s_own[(MODE == 3) ? kTcM : 1];   // entries appended to the front of each query row's slab
+    __shared__ uint32_t s_queue[kTcM / 32][64];
+    __shared__ int s_own[kTcM];   // accepted entries per query row (MODE 2 / 3: appended to the front of its slab row)
     const int tid = threadIdx.x, warp = tid >> 5;
     const int lane = tid & 31;
-    if (MODE == 3) s_own[tid] = 0;
+    s_own[tid] = 0;
     int q_count = 0;                                  // queued candidates of this warp (warp-uniform)
     const int64_t w = (int64_t)blockIdx.x * kTcM + tid;
     const bool active = w < nq;
@@ -222,7 +222,8 @@ tc_rball_kernel(const double *__restrict__ V, const float *__restrict__ opB, con
         const uint32_t c = act ? s_queue[warp][lane] : 0u;
         const int ql = act ? (int)(c & 31u) : 32 + lane;          // inactive lanes match nobody
         const int64_t j = (int64_t)(c >> 5);
-        const int64_t qg = (int64_t)blockIdx.x * kTcM + warp * 32 + (ql & 31);
+        const int64_t wl = (int64_t)blockIdx.x * kTcM + warp * 32 + (ql & 31);   // row of this launch (slab row in MODE 2)
+        const int64_t qg = q0 + wl;                                              // global sample index of the query
         double s64 = 0.0;
         bool hit = false;
         if (act) {
@@ -235,11 +236,13 @@ tc_rball_kernel(const double *__restrict__ V, const float *__restrict__ opB, con
         int base = 0;
         if (act) base = s_own[warp * 32 + ql];
         __syncwarp();
-        if (hit) {
+        if (hit && MODE != 0) {
             const int pos = base + __popc(peers & hitmask & lt);
-            if (pos < cap) { slab_j[qg * cap + pos] = (int)j; slab_s[qg * cap + pos] = s64; }
-            const int slot = atomicAdd(&rcounts[j], 1);
-            if (slot < cap) { slab_j[j * cap + (cap - 1 - slot)] = (int)qg; slab_s[j * cap + (cap - 1 - slot)] = s64; }
+            if (pos < cap) { slab_j[wl * cap + pos] = (int)j; slab_s[wl * cap + pos] = s64; }
+            if (MODE == 3) {
+                const int slot = atomicAdd(&rcounts[j], 1);
+                if (slot < cap) { slab_j[j * cap + (cap - 1 - slot)] = (int)qg; slab_s[j * cap + (cap - 1 - slot)] = s64; }
+            }
         }
         if (act && lane == __ffs(peers) - 1) s_own[warp * 32 + ql] = base + __popc(peers & hitmask);
         __syncwarp();
@@ -304,7 +307,7 @@ tc_rball_kernel(const double *__restrict__ V, const float *__restrict__ opB, con
             m2 = fmaxf(m2, __uint_as_float(rr[30]));
             m3 = fmaxf(m3, __uint_as_float(rr[31]));
             const bool pass = fmaxf(fmax3(m0, m1, m2), m3) >= pass_at;
-            if (MODE == 3) {
+            {
                 if (__any_sync(0xffffffffu, pass)) {   // warp-uniform
                     uint32_t mask = 0;
                     if (pass) {
@@ -326,11 +329,14 @@ tc_rball_kernel(const double *__restrict__ V, const float *__restrict__ opB, con
 #pragma unroll
                             for (int i = 3; i < 32; i += 4) mask |= (__uint_as_float(rr[i]) >= pass_at) ? (1u << i) : 0u;
                         }
-                        // only partners j with q < j < N (the pair's other half belongs to row j)
                         const int64_t j0 = t0 + c0;
-                        const int64_t lo = q - j0;              // bits 0 .. lo are j <= q
-                        if (lo >= 31) mask = 0u;
-                        else if (lo >= 0) mask &= ~((2u << (int)lo) - 1u);
+                        const int64_t lo = q - j0;
+                        if (MODE == 3) {   // only partners j with q < j < N (the pair's other half belongs to row j)
+                            if (lo >= 31) mask = 0u;
+                            else if (lo >= 0) mask &= ~((2u << (int)lo) - 1u);   // bits 0 .. lo are j <= q
+                        } else if (lo >= 0 && lo < 32) {
+                            mask &= ~(1u << (int)lo);                             // j == q
+                        }
                         const int64_t hi = N - j0;              // bits >= hi are padding samples
                         if (hi <= 0) mask = 0u;
                         else if (hi < 32) mask &= (1u << (int)hi) - 1u;
@@ -350,37 +356,14 @@ tc_rball_kernel(const double *__restrict__ V, const float *__restrict__ opB, con
                         if (q_count >= 32) drain(32);
                     }
                 }
-            } else if (pass) {
-                uint32_t mask = 0;
-#pragma unroll
-                for (int i = 0; i < 32; ++i) mask |= (__uint_as_float(rr[i]) >= pass_at) ? (1u << i) : 0u;
-                while (mask) {  // K4: the exact FP64 test decides membership and the stored distance
-                    const int i = __ffs(mask) - 1;
-                    mask &= mask - 1;
-                    const int64_t j = t0 + c0 + i;
-                    if (j < N && j != q) {
-                        const double s64 = tc_exact_sq<D>(V + q * D, V + j * D);
-                        if (s64 <= r2) {
-                            if (MODE == 2 && cnt < cap) {
-                                slab_j[w * cap + cnt] = (int)j;
-                                slab_s[w * cap + cnt] = s64;
-                            }
-                            ++cnt;
-                        }
-                    }
-                }
             }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();  // accumulator and sB are free for the next tile
     }
-    if (MODE == 3) {
-        if (q_count > 0) drain(q_count);
-        __syncwarp();
-        if (active) counts[w] = s_own[tid];  // own entries; the entries appended by partners are counted in rcounts
-    } else if (active) {
-        counts[w] = cnt;
-    }
+    if (q_count > 0) drain(q_count);
+    __syncwarp();
+    if (active) counts[w] = s_own[tid];  // MODE 3: own entries; the entries appended by partners are counted in rcounts
     if (warp == 0)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(kTcN));
 }
@@ -443,6 +426,8 @@ template <int D>
 int tc_sweep(mpb200_samples *s, const TcPlan &P, double r, int64_t nq_run, int *counts, int cap, int *slab_j,
              double *slab_s, int *rcounts) {
     cudaStream_t st = ctx().stream;
+    if (P.Npad >= (int64_t(1) << 27))  // queued candidates are packed as (sample << 5 | row)
+        return fail(MPB200_EARG, "the tensor-core all-pairs sweep supports fewer than 2^27 samples");
     const unsigned nb = (unsigned)ceil_div(nq_run > 0 ? nq_run : 1, kTcM);
     if (rcounts) {  // symmetric: full range, q0 == 0, slabs present; rcounts = atomic counters of the partner appends
         MPB_CUDA(cudaMemsetAsync(rcounts, 0, sizeof(int) * (size_t)nq_run, st));
