@@ -124,8 +124,10 @@ def c3(mp, orc, fx, args):
                              unit="TFLOP/s", frac=(flops / t_nn / 1e12 / bf16) if bf16 else None, traffic=None,
                              peak_kind="measured bf16 sustained (MEASURED_PEAKS.json); the kernel issues TF32 MMAs, whose dense rate is half of bf16",
                              algorithmic_flops_per_launch=flops,
-                             note="bounded in practice by the TMEM read-back of every FP32 accumulator (DESIGN.md 10), not by the tensor pipe; "
-                                  "the sweep multiplies each unordered pair once (symmetric form), so half of the algorithmic 2 N^2 d is actually issued"),
+                             note="the contraction is K = 16 per pair, so the tensor pipe is never the limiter: the kernel is bound by its "
+                                  "epilogue (accumulator read-back + running maxima) and, until candidates were queued per warp, by the rare "
+                                  "exact-recheck path (ncu: DESIGN.md 10); the sweep multiplies each unordered pair once (symmetric form), so "
+                                  "half of the algorithmic 2 N^2 d is actually issued"),
                cpu_baseline=dict(value=q / t_cpu, unit="queries/s", cores=1, kind="port",
                                  sample="brute-force oracle on %d of %d query columns; edges %.3g/s on their %d stored edges"
                                         % (q, N, len(ref[1]) / max(t_cpu_e, 1e-9), len(ref[1]))))
